@@ -1,0 +1,165 @@
+/*
+ * xsdba_b200 -- C ABI of the B200 (sm_100a) quantile-mapping hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / numpy / xarray types.
+ * Each entry point names the interface of the reference (Ouranosinc/xsdba v0.7.0, paths relative
+ * to src/xsdba/) that it replaces.  The Python host layer (xsdba_b200/_adjustment.py) binds these
+ * with ctypes and mirrors the reference's L4 functions (eqm_train, dqm_train, qm_adjust,
+ * dqm_adjust, qdm_adjust); INTEGRATION.md shows the binding a maintainer of the reference adds.
+ *
+ * Conventions
+ *  - "dev" pointers are CUDA device pointers, "host" pointers are ordinary host memory.
+ *  - Series arrays are addressed by element strides: element (point p, time t) of an array x is
+ *    x[p*stride_pt + t*stride_time].  The reference's natural (time, lat, lon) C order is
+ *    stride_pt = 1, stride_time = n_pts ("time-major"); (lat, lon, time) is stride_pt = n_time,
+ *    stride_time = 1 ("point-major").  Kernels are tuned for time-major.
+ *  - Trained tables are point-major: af / hist_q are [n_pts][n_groups][nq], scaling is
+ *    [n_pts][n_groups]  (the reference's output dims (<points>, month|dayofyear|group, quantiles),
+ *    base.py:652-694).
+ *  - kind: '+' (43) or '*' (42), as in utils.get_correction / apply_correction (utils.py:130-162).
+ *  - Every function returns 0 on success, a negative XSDBA_ERR_* for argument errors, or a
+ *    positive cudaError_t.  Nothing throws across the ABI.  Functions are re-entrant; the only
+ *    state is the caller-owned grouping handle (immutable after creation) and the caller's stream.
+ *  - Inputs are never modified (the reference's numba quantile sorts its input in place when the
+ *    reshape is a view; this library does not).
+ */
+#ifndef XSDBA_B200_H
+#define XSDBA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XSDBA_OK 0
+#define XSDBA_ERR_INVALID_ARGUMENT (-1)
+#define XSDBA_ERR_UNSUPPORTED (-2)      /* valid in the reference, not built here yet (e.g. grouped linear) */
+#define XSDBA_ERR_SEGMENT_TOO_LONG (-3) /* a (point, group) segment exceeds the shared-memory sorter */
+#define XSDBA_ERR_NO_DEVICE (-4)
+#define XSDBA_ERR_OUT_OF_MEMORY (-5)
+
+#define XSDBA_KIND_ADD 43 /* '+' */
+#define XSDBA_KIND_MUL 42 /* '*' */
+
+#define XSDBA_INTERP_NEAREST 0
+#define XSDBA_INTERP_LINEAR 1
+
+#define XSDBA_EXTRAP_CONSTANT 0
+#define XSDBA_EXTRAP_NAN 1
+
+#define XSDBA_MAX_SEGMENT 32768 /* longest (point, group) segment the in-SM sorter takes (float32) */
+
+typedef struct xsdba_grouping xsdba_grouping_t;
+
+/* Library / build information. */
+int xsdba_version(void);
+const char* xsdba_status_string(int status);
+/* Number of kernels this library has launched in this process (all streams); bench.py reports the
+ * delta over its timed region as "gpu_launches". */
+int64_t xsdba_launch_count(void);
+
+/*
+ * Grouping handle: replaces base.Grouper.group / get_index / apply's membership logic
+ * (base.py:232-345, 410-420) and the rolling(center=True).construct window gather (base.py:261-265).
+ *
+ * grp_idx_host[t] is the 0-based group of time step t (month-1, dayofyear-1, 0 for group="time"),
+ * or -1 for "in no group".  window is the Grouper window (odd or even, >= 1): a reducing function
+ * sees, for every member t of a group, the samples x[t - window/2 + j], j = 0..window-1, NaN outside
+ * [0, n_time) -- positional, like xarray.  The handle owns small device tables derived from this.
+ */
+int xsdba_grouping_create(xsdba_grouping_t** out, const int32_t* grp_idx_host, int64_t n_time,
+                          int32_t n_groups, int32_t window);
+int xsdba_grouping_destroy(xsdba_grouping_t* g);
+int64_t xsdba_grouping_max_segment(const xsdba_grouping_t* g); /* longest segment incl. window slots */
+int32_t xsdba_grouping_n_groups(const xsdba_grouping_t* g);
+
+/*
+ * Train: replaces _adjustment.eqm_train.func (_adjustment.py:253-286; normalize = 0) and
+ * _adjustment.dqm_train.func (_adjustment.py:150-190; normalize = 1) for every group at once, i.e.
+ * Grouper.apply + nbutils.quantile (nbutils.py:108-148, 198-271) + utils.get_correction
+ * (utils.py:130-143).  q_dev holds nq nodes already cast to the data dtype (nbutils.py:253).
+ * scaling_dev may be NULL when normalize = 0.  Groups without members give NaN rows.
+ */
+int xsdba_qm_train_f32(const float* ref_dev, const float* hist_dev, int64_t n_pts, int64_t stride_pt,
+                       int64_t stride_time, const xsdba_grouping_t* grp, const float* q_dev, int32_t nq,
+                       int32_t kind, int32_t normalize, float* af_dev, float* hist_q_dev,
+                       float* scaling_dev, void* cuda_stream);
+int xsdba_qm_train_f64(const double* ref_dev, const double* hist_dev, int64_t n_pts, int64_t stride_pt,
+                       int64_t stride_time, const xsdba_grouping_t* grp, const double* q_dev, int32_t nq,
+                       int32_t kind, int32_t normalize, double* af_dev, double* hist_q_dev,
+                       double* scaling_dev, void* cuda_stream);
+
+/*
+ * Quantiles only: replaces nbutils.quantile over grouped segments (nbutils.py:224-271), used for
+ * hist_q_raw (_adjustment.py:254-256) and by callers that want ref_q.  out is [n_pts][n_groups][nq].
+ */
+int xsdba_group_quantile_f32(const float* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                             const xsdba_grouping_t* grp, const float* q_dev, int32_t nq, float* out_dev,
+                             void* cuda_stream);
+int xsdba_group_quantile_f64(const double* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                             const xsdba_grouping_t* grp, const double* q_dev, int32_t nq, double* out_dev,
+                             void* cuda_stream);
+
+/*
+ * Adjust (EQM / DQM flavour): replaces _adjustment.qm_adjust.func (_adjustment.py:660-669) =
+ * utils.interp_on_quantiles (utils.py:408-513; 1-D SciPy interp1d rule for group="time", 2-D
+ * Euclidean-nearest griddata rule + nbutils._extrapolate_on_quantiles for month/dayofyear groups,
+ * with add_cyclic_bounds, utils.py:284-314) followed by utils.apply_correction (utils.py:146-162).
+ * grp gives the group of each sim time step (its window is ignored).  n_groups == 1 selects the
+ * 1-D rule.  Grouped interp = LINEAR returns XSDBA_ERR_UNSUPPORTED (Qhull path).
+ * scen has the same strides as sim.
+ */
+int xsdba_qm_adjust_f32(const float* sim_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                        const xsdba_grouping_t* grp, const float* af_dev, const float* hist_q_dev,
+                        int32_t nq, int32_t interp, int32_t extrap, int32_t kind, float* scen_dev,
+                        void* cuda_stream);
+int xsdba_qm_adjust_f64(const double* sim_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                        const xsdba_grouping_t* grp, const double* af_dev, const double* hist_q_dev,
+                        int32_t nq, int32_t interp, int32_t extrap, int32_t kind, double* scen_dev,
+                        void* cuda_stream);
+
+/*
+ * Adjust (QDM): replaces _adjustment.qdm_adjust.func (_adjustment.py:872-881): per-group percentile
+ * ranks (utils.rank with pct=True -> bottleneck.nanrankdata, utils.py:612-638; Grouper.apply with
+ * main_only = !rank_window, base.py:438-439), factor lookup on the shared quantile axis, then
+ * apply_correction.  sim_q_dev (float64, same strides as sim) may be NULL.
+ */
+int xsdba_qdm_adjust_f32(const float* sim_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                         const xsdba_grouping_t* grp, const float* af_dev, const float* q_dev, int32_t nq,
+                         int32_t interp, int32_t extrap, int32_t kind, int32_t rank_window,
+                         float* scen_dev, double* sim_q_dev, void* cuda_stream);
+int xsdba_qdm_adjust_f64(const double* sim_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                         const xsdba_grouping_t* grp, const double* af_dev, const double* q_dev, int32_t nq,
+                         int32_t interp, int32_t extrap, int32_t kind, int32_t rank_window,
+                         double* scen_dev, double* sim_q_dev, void* cuda_stream);
+
+/*
+ * Percentile ranks only: replaces Grouper.apply(utils.rank, x, main_only = !rank_window, pct = True).
+ */
+int xsdba_group_rank_f32(const float* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                         const xsdba_grouping_t* grp, int32_t rank_window, double* rank_dev,
+                         void* cuda_stream);
+int xsdba_group_rank_f64(const double* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                         const xsdba_grouping_t* grp, int32_t rank_window, double* rank_dev,
+                         void* cuda_stream);
+
+/*
+ * End-to-end host entry point (what the xarray-facing layer calls with numpy buffers): EQM
+ * train(ref, hist) + adjust(sim) on HOST arrays in the reference's (time, points) C order
+ * (time-major, contiguous).  Points are streamed through the GPU in slabs on internal streams
+ * (H2D copy, train, adjust, D2H copy overlapped); af/hist_q (point-major, may be NULL) and scen
+ * (time-major) are written back to host.  Pinned host memory gives full PCIe rate; pageable works.
+ * grp_train carries the Grouper window; grp_sim the sim time axis.  mode: 0 = EQM, 1 = QDM.
+ */
+int xsdba_qm_train_adjust_host_f32(const float* ref_host, const float* hist_host, const float* sim_host,
+                                   int64_t n_pts, const xsdba_grouping_t* grp_train,
+                                   const xsdba_grouping_t* grp_sim, const float* q_host, int32_t nq,
+                                   int32_t kind, int32_t mode, int32_t interp, int32_t extrap,
+                                   float* scen_host, float* af_host, float* hist_q_host,
+                                   int64_t slab_pts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XSDBA_B200_H */

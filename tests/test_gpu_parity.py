@@ -1,0 +1,152 @@
+"""GPU parity: the CUDA path (through the C ABI / host mirror) against the CPU oracle on the same
+seeded inputs.  Bit-exact for quantiles, ranks, nearest lookups; <= 1e-6 (f32) / 1e-12 (f64) relative
+for the rest (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import qm_oracle as o
+import synth
+from conftest import bits_equal
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _xs():
+    import xsdba_b200 as xs
+    return xs
+
+
+def _time(calendar, n_years, start=1981):
+    xs = _xs()
+    return xs.TimeAxis.daily(start, n_years, calendar), o.daily_time_axis(start, n_years, calendar)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+CASES = [
+    # group, window, calendar, years, nq, kind, var, dtype
+    ("time", 1, "noleap", 3, 50, "+", "tas", np.float32),
+    ("time.month", 1, "noleap", 6, 50, "+", "tas", np.float32),
+    ("time.month", 1, "standard", 4, 20, "*", "pr", np.float32),
+    ("time.month", 1, "noleap", 4, 50, "+", "tas", np.float64),
+    ("time.dayofyear", 31, "noleap", 4, 100, "*", "pr", np.float32),
+    ("time.dayofyear", 5, "standard", 5, 30, "+", "tas", np.float32),
+    ("time.dayofyear", 31, "360_day", 3, 50, "+", "tas", np.float64),
+    ("time.season", 1, "noleap", 3, 40, "+", "tas", np.float32),
+]
+
+
+def _make(case, n_pts=37, seed=0):
+    group, window, cal, years, nq, kind, var, dt = case
+    rng = np.random.default_rng(seed)
+    tx, to = _time(cal, years)
+    gen = getattr(synth, var)
+    ref, hist, sim = (gen(rng, to, n_pts, w, dt) for w in ("ref", "hist", "sim"))
+    ref[:, 3] = np.nan            # an all-NaN point (mask must be preserved bit-exactly)
+    hist[:, 3] = np.nan
+    hist[5:, 4] = np.nan          # a point with only 5 valid hist samples
+    return tx, to, ref, hist, sim
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-w{c[1]}-{c[2]}-{c[5]}-{np.dtype(c[7]).name}")
+def test_eqm_train_matches_oracle(case):
+    xs = _xs()
+    group, window, cal, years, nq, kind, var, dt = case
+    tx, to, ref, hist, sim = _make(case)
+    q = o.equally_spaced_nodes(nq).astype(dt)
+    gidx, G, _ = o.group_index(to, group)
+    af_o, hq_o = o.eqm_train(ref.T.copy(), hist.T.copy(), gidx, G, window, q, kind)
+    ds = xs.eqm_train(xs.Dataset({"ref": ref, "hist": hist}, time=tx), group=xs.Grouper(group, window), kind=kind,
+                      quantiles=q)
+    af, hq = _np(ds.af), _np(ds.hist_q)
+    assert af.shape == (ref.shape[1], G, nq)
+    if dt == np.float32:
+        assert bits_equal(hq, hq_o)
+        assert bits_equal(af, af_o)
+    else:
+        np.testing.assert_allclose(hq, hq_o, rtol=1e-12, atol=0, equal_nan=True)
+        np.testing.assert_allclose(af, af_o, rtol=1e-9, atol=1e-12 * np.nanmax(np.abs(hq_o)), equal_nan=True)
+    # point-major input gives the same tables
+    ds2 = xs.eqm_train(xs.Dataset({"ref": ref.T.copy(), "hist": hist.T.copy()}, time=tx, time_axis=-1),
+                       group=xs.Grouper(group, window), kind=kind, quantiles=q)
+    assert bits_equal(_np(ds2.af), af) and bits_equal(_np(ds2.hist_q), hq)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-w{c[1]}-{c[2]}-{c[5]}-{np.dtype(c[7]).name}")
+@pytest.mark.parametrize("extrap", ["constant", "nan"])
+def test_qm_adjust_nearest_matches_oracle(case, extrap):
+    xs = _xs()
+    group, window, cal, years, nq, kind, var, dt = case
+    tx, to, ref, hist, sim = _make(case, n_pts=13)
+    q = o.equally_spaced_nodes(nq).astype(dt)
+    gidx, G, _ = o.group_index(to, group)
+    af_o, hq_o = o.eqm_train(ref.T.copy(), hist.T.copy(), gidx, G, window, q, kind)
+    scen_o = o.qm_adjust(sim.T.copy(), af_o, hq_o, group=group, time=to, interp="nearest", extrapolation=extrap,
+                         kind=kind)
+    out = xs.qm_adjust(xs.Dataset({"sim": sim, "af": af_o, "hist_q": hq_o}, time=tx), group=xs.Grouper(group, window),
+                       interp="nearest", extrapolation=extrap, kind=kind)
+    scen = _np(out.scen).T
+    assert bits_equal(scen, scen_o)  # nearest lookup is an exact table pick
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("extrap", ["constant", "nan"])
+def test_qm_adjust_time_linear_matches_oracle(dt, extrap):
+    xs = _xs()
+    case = ("time", 1, "noleap", 3, 50, "+", "tas", dt)
+    tx, to, ref, hist, sim = _make(case, n_pts=11)
+    q = o.equally_spaced_nodes(50).astype(dt)
+    gidx, G, _ = o.group_index(to, "time")
+    af_o, hq_o = o.eqm_train(ref.T.copy(), hist.T.copy(), gidx, G, 1, q, "+")
+    scen_o = o.qm_adjust(sim.T.copy(), af_o, hq_o, group="time", time=to, interp="linear", extrapolation=extrap, kind="+")
+    out = xs.qm_adjust(xs.Dataset({"sim": sim, "af": af_o, "hist_q": hq_o}, time=tx), group="time", interp="linear",
+                       extrapolation=extrap, kind="+")
+    np.testing.assert_allclose(_np(out.scen).T, scen_o, rtol=1e-6 if dt == np.float32 else 1e-12, atol=0, equal_nan=True)
+
+
+QDM_CASES = [
+    ("time", 1, "noleap", 3, 50, "*", "pr", np.float32, False),
+    ("time.month", 1, "noleap", 4, 50, "*", "pr", np.float32, False),
+    ("time.dayofyear", 31, "noleap", 4, 100, "*", "pr", np.float32, False),
+    ("time.dayofyear", 31, "noleap", 3, 100, "*", "pr", np.float32, True),
+    ("time.dayofyear", 7, "standard", 5, 20, "+", "tas", np.float64, True),
+    ("time.month", 1, "noleap", 3, 30, "+", "tas", np.float64, False),
+]
+
+
+@pytest.mark.parametrize("case", QDM_CASES, ids=lambda c: f"{c[0]}-w{c[1]}-{c[2]}-{c[5]}-{np.dtype(c[7]).name}-rw{int(c[8])}")
+def test_qdm_adjust_matches_oracle(case):
+    xs = _xs()
+    group, window, cal, years, nq, kind, var, dt, rank_window = case
+    tx, to, ref, hist, sim = _make(case[:8], n_pts=9)
+    sim[:, 2] = np.round(sim[:, 2])  # ties -> average ranks
+    q = o.equally_spaced_nodes(nq).astype(dt)
+    gidx, G, _ = o.group_index(to, group)
+    af_o, hq_o = o.eqm_train(ref.T.copy(), hist.T.copy(), gidx, G, window, q, kind)
+    scen_o, simq_o = o.qdm_adjust(sim.T.copy(), af_o, q, group=group, time=to, window=window, interp="nearest",
+                                  extrapolation="constant", kind=kind, rank_window=rank_window)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)
+        out = xs.qdm_adjust(xs.Dataset({"sim": sim, "af": af_o, "quantiles": q}, time=tx),
+                            group=xs.Grouper(group, window), interp="nearest", extrapolation="constant", kind=kind,
+                            rank_window=rank_window)
+    assert bits_equal(_np(out.sim_q).T, simq_o)      # ranks are exact rationals in float64
+    assert bits_equal(_np(out.scen).T, scen_o)
+
+
+def test_group_quantile_reference_golden(golden):
+    """The CUDA quantiles against outputs of the reference's own numba kernel (tests/golden)."""
+    xs = _xs()
+    for tag, dt in (("f32", np.float32), ("f64", np.float64)):
+        for nq in (50, 100):
+            a, q, ref = (golden[f"quant_{tag}_{nq}_{k}"] for k in ("in", "q", "out"))
+            t = xs.TimeAxis.daily(2000, 3, "noleap")[: a.shape[1]]
+            got = _np(xs.group_quantile(a, time=t, group="time", quantiles=q, time_axis=-1))[:, 0, :]
+            assert bits_equal(got, ref), (tag, nq)
+    a, q, ref = golden["quant_long_in"], golden["quant_long_q"], golden["quant_long_out"]
+    t = xs.TimeAxis.daily(1981, 30, "noleap")
+    assert bits_equal(_np(xs.group_quantile(a, time=t, group="time", quantiles=q, time_axis=-1))[:, 0, :], ref)

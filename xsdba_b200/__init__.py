@@ -1,0 +1,9 @@
+"""xsdba_b200 -- Blackwell (sm_100a) quantile-mapping hot path behind the xsdba train/adjust API."""
+from .base import Grouper, parse_group  # noqa: F401
+from .calendar import TimeAxis  # noqa: F401
+from ._adjustment import (  # noqa: F401
+    Dataset, dqm_train, eqm_train, group_quantile, group_rank, qdm_adjust, qm_adjust,
+)
+from .utils import equally_spaced_nodes  # noqa: F401
+
+__version__ = "0.1.0"

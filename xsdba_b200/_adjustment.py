@@ -1,0 +1,246 @@
+"""Host mirror of the reference's L4 compute functions for the quantile-mapping path.
+
+``eqm_train`` / ``dqm_train`` / ``qm_adjust`` / ``qdm_adjust`` have the argument names and meaning of
+``xsdba._adjustment`` (_adjustment.py:86-286, 594-886) but take a :class:`Dataset` of arrays instead
+of an ``xarray.Dataset`` (xarray is not a dependency): series are ``(time, *points)`` (time_axis=0,
+the reference's natural netCDF order, fastest on the GPU) or ``(*points, time)`` (time_axis=-1).
+Inputs may be numpy arrays or torch CUDA tensors; outputs are torch CUDA tensors.  All arithmetic runs
+in the CUDA library through the C ABI -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib
+from .base import Grouper, parse_group
+from .calendar import TimeAxis
+
+
+class Dataset(dict):
+    """Minimal stand-in for the ``xr.Dataset`` the reference passes around: a dict of arrays with
+    attribute access plus the time coordinate(s)."""
+
+    def __init__(self, data=None, *, time: TimeAxis | None = None, time_axis: int = 0, **kw):
+        super().__init__(data or {}, **kw)
+        self.time = time
+        self.time_axis = time_axis
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def assign(self, **kw):
+        out = Dataset(self, time=self.time, time_axis=self.time_axis)
+        out.update(kw)
+        return out
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise _lib.XsdbaB200Error("xsdba_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _as_device(x, dtype=None):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(np.asarray(x))
+    if dtype is not None and x.dtype != dtype:
+        x = x.to(dtype)
+    if not x.is_cuda:
+        x = x.to(_device(), non_blocking=True)
+    return x
+
+
+def _series(x, time_axis, n_time, dtype=None):
+    """-> (tensor, n_pts, stride_pt, stride_time, points_shape)."""
+    x = _as_device(x, dtype)
+    if x.dtype not in (torch.float32, torch.float64):
+        x = x.to(torch.float32)
+    ax = time_axis % x.ndim
+    if ax not in (0, x.ndim - 1):
+        x = x.movedim(ax, 0)
+        ax = 0
+    x = x.contiguous()
+    if x.shape[ax] != n_time:
+        raise ValueError(f"time axis has {x.shape[ax]} steps, the time coordinate has {n_time}")
+    if ax == 0:
+        pts_shape = tuple(x.shape[1:])
+        n_pts = int(np.prod(pts_shape)) if pts_shape else 1
+        return x, n_pts, 1, n_pts, pts_shape
+    pts_shape = tuple(x.shape[:-1])
+    n_pts = int(np.prod(pts_shape)) if pts_shape else 1
+    return x, n_pts, n_time, 1, pts_shape
+
+
+def _widest(*xs):
+    dt = torch.float32
+    for x in xs:
+        d = x.dtype if isinstance(x, torch.Tensor) else torch.from_numpy(np.empty(0, np.asarray(x).dtype)).dtype
+        if d == torch.float64:
+            dt = torch.float64
+    return dt  # base.py:681-685: output dtype = widest input dtype
+
+
+def _sfx(dt):
+    return "f32" if dt == torch.float32 else "f64"
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _reject_unsupported(**kw):
+    for k, v in kw.items():
+        if v is not None:
+            raise NotImplementedError(f"{k} is not built in xsdba_b200 yet (SURVEY.md 8f rank 1)")
+
+
+def _train(ds, *, group, kind, quantiles, normalize, adapt_freq_thresh=None, jitter_under_thresh_value=None,
+           jitter_over_thresh_value=None, jitter_over_thresh_upper_bnd=None, max_tail_factor=None):
+    _reject_unsupported(adapt_freq_thresh=adapt_freq_thresh, jitter_under_thresh_value=jitter_under_thresh_value,
+                        jitter_over_thresh_value=jitter_over_thresh_value,
+                        jitter_over_thresh_upper_bnd=jitter_over_thresh_upper_bnd, max_tail_factor=max_tail_factor)
+    if kind not in _lib.KIND:
+        raise ValueError("kind must be + or *.")  # utils.py:139
+    group = parse_group(group)
+    time = ds.time
+    if time is None:
+        raise ValueError("the Dataset needs a time coordinate (ds.time)")
+    lib = _lib.load()
+    dt = _widest(ds["ref"], ds["hist"])
+    ref, n_pts, sp, st, pshape = _series(ds["ref"], ds.time_axis, len(time), dt)
+    hist, n_pts_h, sp_h, st_h, _ = _series(ds["hist"], ds.time_axis, len(time), dt)
+    if n_pts_h != n_pts:
+        raise ValueError("ref and hist must have the same points")
+    h = group.handle(time)
+    G = h.n_groups
+    q = _as_device(np.asarray(quantiles), dt).contiguous()
+    nq = q.numel()
+    af = torch.empty((n_pts, G, nq), dtype=dt, device=ref.device)
+    hq = torch.empty_like(af)
+    sc = torch.empty((n_pts, G), dtype=dt, device=ref.device) if normalize else None
+    fn = getattr(lib, f"xsdba_qm_train_{_sfx(dt)}")
+    status = fn(ref.data_ptr(), hist.data_ptr(), n_pts, sp, st, h.ptr, q.data_ptr(), nq, _lib.KIND[kind],
+                1 if normalize else 0, af.data_ptr(), hq.data_ptr(), sc.data_ptr() if normalize else None, _stream())
+    _lib.check(status, "dqm_train" if normalize else "eqm_train")
+    nan_like = lambda t: torch.full_like(t, float("nan"))  # noqa: E731
+    out = Dataset(time=None)
+    out["af"] = af.reshape(*pshape, G, nq)
+    out["hist_q"] = hq.reshape(*pshape, G, nq)
+    out["hist_q_raw"] = None  # all-NaN dummy in the reference unless max_tail_factor (_adjustment.py:273-275)
+    if normalize:
+        out["scaling"] = sc.reshape(*pshape, G)
+    out["quantiles"] = q
+    out[group.prop] = group.get_coordinate(time)
+    out.group = group
+    out.kind = kind
+    return out
+
+
+def eqm_train(ds, *, group, kind, quantiles, **kw):
+    """EQM train on every group: ``xsdba._adjustment.eqm_train`` (_adjustment.py:193-286)."""
+    return _train(ds, group=group, kind=kind, quantiles=quantiles, normalize=False, **kw)
+
+
+def dqm_train(ds, *, group, kind, quantiles, **kw):
+    """DQM train on every group: ``xsdba._adjustment.dqm_train`` (_adjustment.py:86-190)."""
+    return _train(ds, group=group, kind=kind, quantiles=quantiles, normalize=True, **kw)
+
+
+def group_quantile(x, *, time, group, quantiles, time_axis=0):
+    """``Grouper.apply(nbutils.quantile, x, q=quantiles)`` (nbutils.py:224-271) -> (*points, G, nq)."""
+    group = parse_group(group)
+    lib = _lib.load()
+    dt = _widest(x)
+    xs, n_pts, sp, st, pshape = _series(x, time_axis, len(time), dt)
+    h = group.handle(time)
+    q = _as_device(np.asarray(quantiles), dt).contiguous()
+    out = torch.empty((n_pts, h.n_groups, q.numel()), dtype=dt, device=xs.device)
+    fn = getattr(lib, f"xsdba_group_quantile_{_sfx(dt)}")
+    _lib.check(fn(xs.data_ptr(), n_pts, sp, st, h.ptr, q.data_ptr(), q.numel(), out.data_ptr(), _stream()),
+               "group_quantile")
+    return out.reshape(*pshape, h.n_groups, q.numel())
+
+
+def _tables(ds, n_pts, G, dt, names):
+    out = []
+    for name in names:
+        t = _as_device(ds[name], dt).contiguous()
+        nq = t.shape[-1]
+        if t.numel() != n_pts * G * nq:
+            raise ValueError(f"{name} has shape {tuple(t.shape)}, expected (*points={n_pts}, {G}, nq)")
+        out.append(t)
+    return out
+
+
+def qm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None, max_tail_factor=None):
+    """``xsdba._adjustment.qm_adjust`` (_adjustment.py:594-676): ds holds af, hist_q, sim."""
+    _reject_unsupported(adapt_freq_thresh=adapt_freq_thresh, max_tail_factor=max_tail_factor)
+    if interp not in ("nearest", "linear", "cubic") or extrapolation not in _lib.EXTRAP:
+        raise ValueError("interp must be nearest/linear/cubic and extrapolation constant/nan")
+    if interp == "cubic":
+        raise NotImplementedError("cubic interpolation is not built in xsdba_b200 yet")
+    group = parse_group(group)
+    lib = _lib.load()
+    time = ds.time
+    dt = _widest(ds["sim"], ds["af"])
+    sim, n_pts, sp, st, pshape = _series(ds["sim"], ds.time_axis, len(time), dt)
+    h = group.handle(time, with_window=False)
+    af, hq = _tables(ds, n_pts, h.n_groups, dt, ("af", "hist_q"))
+    nq = af.shape[-1]
+    scen = torch.empty_like(sim)
+    fn = getattr(lib, f"xsdba_qm_adjust_{_sfx(dt)}")
+    status = fn(sim.data_ptr(), n_pts, sp, st, h.ptr, af.data_ptr(), hq.data_ptr(), nq, _lib.INTERP[interp],
+                _lib.EXTRAP[extrapolation], _lib.KIND[kind], scen.data_ptr(), _stream())
+    _lib.check(status, "qm_adjust")
+    return Dataset({"scen": scen}, time=time, time_axis=0 if st != 1 or sim.ndim == 1 else -1)
+
+
+def qdm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None, rank_window=None,
+               max_tail_factor=None):
+    """``xsdba._adjustment.qdm_adjust`` (_adjustment.py:783-886): ds holds af, quantiles, sim."""
+    _reject_unsupported(adapt_freq_thresh=adapt_freq_thresh, max_tail_factor=max_tail_factor)
+    if interp == "cubic":
+        raise NotImplementedError("cubic interpolation is not built in xsdba_b200 yet")
+    group = parse_group(group)
+    if rank_window is None:
+        rank_window = False
+        if group.window > 1:
+            warnings.warn("QDM ranks within exact groups (rank_window=False); xsdba>=0.8 will honour the grouping "
+                          "window (rank_window=True).", category=DeprecationWarning, stacklevel=2)  # _adjustment.py:858-871
+    lib = _lib.load()
+    time = ds.time
+    dt = _widest(ds["sim"], ds["af"])
+    sim, n_pts, sp, st, pshape = _series(ds["sim"], ds.time_axis, len(time), dt)
+    h = group.handle(time, with_window=bool(rank_window))
+    (af,) = _tables(ds, n_pts, h.n_groups, dt, ("af",))
+    q = _as_device(ds["quantiles"], dt).contiguous()
+    nq = af.shape[-1]
+    scen = torch.empty_like(sim)
+    sim_q = torch.empty(sim.shape, dtype=torch.float64, device=sim.device)
+    fn = getattr(lib, f"xsdba_qdm_adjust_{_sfx(dt)}")
+    status = fn(sim.data_ptr(), n_pts, sp, st, h.ptr, af.data_ptr(), q.data_ptr(), nq, _lib.INTERP[interp],
+                _lib.EXTRAP[extrapolation], _lib.KIND[kind], 1 if rank_window else 0, scen.data_ptr(),
+                sim_q.data_ptr(), _stream())
+    _lib.check(status, "qdm_adjust")
+    return Dataset({"scen": scen, "sim_q": sim_q}, time=time, time_axis=0 if st != 1 or sim.ndim == 1 else -1)
+
+
+def group_rank(x, *, time, group, rank_window=False, time_axis=0):
+    """``Grouper.apply(utils.rank, x, main_only=not rank_window, pct=True)`` (utils.py:573-638) -> float64."""
+    group = parse_group(group)
+    lib = _lib.load()
+    dt = _widest(x)
+    xs, n_pts, sp, st, _ = _series(x, time_axis, len(time), dt)
+    h = group.handle(time, with_window=bool(rank_window))
+    out = torch.empty(xs.shape, dtype=torch.float64, device=xs.device)
+    fn = getattr(lib, f"xsdba_group_rank_{_sfx(dt)}")
+    _lib.check(fn(xs.data_ptr(), n_pts, sp, st, h.ptr, 1 if rank_window else 0, out.data_ptr(), _stream()), "rank")
+    return out

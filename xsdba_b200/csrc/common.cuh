@@ -1,0 +1,252 @@
+// Shared device helpers for the xsdba_b200 kernels (sm_100a).
+//
+// Arithmetic notes (these pin bit-parity with the reference, see oracle/qm_oracle.py header):
+//  * quantile virtual index  vi = (n-1)*q  rounded once in float64   (nbutils.py:131, LLVM-folded)
+//  * gamma cast to the data type; lerp branches are FMAs             (nbutils.py:101-104, contract)
+//  * SciPy interp1d / numpy.interp / cKDTree arithmetic is NOT contracted: every product / sum is
+//    rounded separately  -> __fmul_rn / __fadd_rn / __dmul_rn / __dadd_rn below.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace xsdba {
+
+template <typename T> struct Num;
+template <> struct Num<float> {
+  static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+  static __device__ __forceinline__ float nan() { return __int_as_float(0x7fc00000); }
+  static __device__ __forceinline__ float mn(float a, float b) { return fminf(a, b); }
+  static __device__ __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+template <> struct Num<double> {
+  static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+  static __device__ __forceinline__ double nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+  static __device__ __forceinline__ double mn(double a, double b) { return fmin(a, b); }
+  static __device__ __forceinline__ double mx(double a, double b) { return fmax(a, b); }
+  static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+
+template <typename T> __device__ __forceinline__ bool is_nan(T v) { return v != v; }
+
+// ---------------------------------------------------------------------------------------------
+// Column sort in shared memory.  sm is [n_pad][C] (column c of row r at sm[r*C + c]); n_pad is a
+// power of two; NaNs have been replaced by +inf by the caller.  Every column is sorted ascending.
+// v0: one compare-exchange per thread per step (bitonic network), __syncthreads between stages.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int C>
+__device__ void sort_columns(T* sm, int n_pad) {
+  const int half_items = (n_pad >> 1) * C;
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int id = threadIdx.x; id < half_items; id += blockDim.x) {
+        const int c = id % C;
+        const int p = id / C;
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+        const int l = i | j;
+        const bool asc = (i & k) == 0;
+        const T a = sm[i * C + c];
+        const T b = sm[l * C + c];
+        const T lo = Num<T>::mn(a, b);
+        const T hi = Num<T>::mx(a, b);
+        sm[i * C + c] = asc ? lo : hi;
+        sm[l * C + c] = asc ? hi : lo;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Value at position i (may be negative, python-style) of the reference's sorted full-length row:
+// positions [0, n) are the sorted valid values, positions [n, S) are NaN (numba sorts NaNs last).
+template <typename T, int C>
+__device__ __forceinline__ T sorted_at(const T* col, long long i, int n, int S) {
+  if (i < 0) i += S;
+  if (i < 0 || i >= n) return Num<T>::nan();
+  return col[(size_t)i * C];
+}
+
+// Type-7 quantile of one sorted column: _nan_quantile_1d + _get_indexes + _linear_interpolation
+// (nbutils.py:24-148).  col points at sm[0*C + c]; n = number of valid values; S = segment length.
+template <typename T, int C>
+__device__ __forceinline__ T quantile_sorted(const T* col, int n, int S, T qk) {
+  const double vi = (double)(n - 1) * (double)qk;   // nbutils.py:131
+  long long prev = (long long)floor(vi);
+  long long next = prev + 1;
+  if (vi >= (double)(n - 1)) { prev = -1; next = -1; }  // nbutils.py:47-51
+  if (vi < 0.0) { prev = 0; next = 0; }                 // nbutils.py:53-56
+  if (vi != vi) { prev = -1; next = -1; }               // nbutils.py:57-62
+  const T left = sorted_at<T, C>(col, prev, n, S);
+  const T right = sorted_at<T, C>(col, next, n, S);
+  const T gamma = (T)(vi - (double)prev);               // nbutils.py:142
+  const T diff = right - left;
+  T res = (gamma >= (T)0.5) ? Num<T>::fma(-diff, (T)1 - gamma, right)   // nbutils.py:103-104
+                            : Num<T>::fma(diff, gamma, left);           // nbutils.py:101-102
+  if (is_nan(res)) res = sorted_at<T, C>(col, (long long)n - 1, n, S);  // nbutils.py:146
+  return res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Factor lookup tables (interp_on_quantiles).  For a tile of C points the kernel stages up to three
+// rows of the cyclically padded tables (group row r-1, r, r+1) in shared memory, NaN nodes dropped
+// (utils.py:351-352, 381-382), as xs/ys[slot][k][C]; nv[slot][C] is the number of kept nodes.
+// blo/bhi (first/last non-NaN hist_q of the centre row) and clo/chi (first/last non-NaN af) feed
+// the extrapolation rule (nbutils.py:375-416; utils.py:362-368).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int C>
+struct Tables {
+  T* xs;     // [3][nq][C]
+  T* ys;     // [3][nq][C]
+  int* nv;   // [3][C]
+  T* blo;    // [C]
+  T* bhi;
+  T* clo;
+  T* chi;
+  int nq;
+  // global fallbacks for rows further than +-1 (rare): raw tables of this tile's points
+  const T* gx;      // hist_q (per point) or q (shared, x_shared = true)
+  const T* gy;      // af
+  bool x_shared;
+  int G;            // number of groups (rows are cyclic)
+  long long pt_stride;  // G*nq
+};
+
+// number of nodes strictly less than x (searchsorted side='left') in compacted column
+template <typename TX, typename T, int C>
+__device__ __forceinline__ int lower_bound_col(const T* xs, int n, TX x) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((TX)xs[mid * C] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// 1-D rule = scipy.interpolate.interp1d as called by utils._interp_on_quantiles_1D (utils.py:350-377)
+template <typename TX, typename T, int C>
+__device__ T lookup_1d(const Tables<T, C>& tb, int c, TX x, int interp, int extrap) {
+  if (is_nan(x)) return Num<T>::nan();
+  const int n = tb.nv[1 * C + c];
+  if (n == 0) return Num<T>::nan();
+  const T* xs = tb.xs + (size_t)1 * tb.nq * C + c;
+  const T* ys = tb.ys + (size_t)1 * tb.nq * C + c;
+  // _check_bounds / fill_value (scipy _interpolate.py: interp1d._evaluate)
+  if (x < (TX)xs[0]) return extrap == 0 ? tb.clo[c] : Num<T>::nan();
+  if (x > (TX)xs[(size_t)(n - 1) * C]) return extrap == 0 ? tb.chi[c] : Num<T>::nan();
+  if (interp == 0) {
+    // nearest: x_bds = x/2.0 ; x_bds[1:] + x_bds[:-1] in the node dtype, searchsorted side='left'
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const T bd = Num<T>::add(Num<T>::mul(xs[(size_t)(mid + 1) * C], (T)0.5), Num<T>::mul(xs[(size_t)mid * C], (T)0.5));
+      if ((TX)bd < x) lo = mid + 1; else hi = mid;
+    }
+    return ys[(size_t)lo * C];
+  }
+  if (n < 2) return Num<T>::nan();
+  if (sizeof(T) == 8 && sizeof(TX) == 8) {
+    // float64 nodes and values: interp1d delegates to numpy.interp (compiled_base.c arr_interp)
+    int j = lower_bound_col<TX, T, C>(xs, n, x);           // #nodes < x
+    if (j < n && (TX)xs[(size_t)j * C] == x) {
+      // largest index with xs[j] <= x
+      while (j + 1 < n && (TX)xs[(size_t)(j + 1) * C] == x) ++j;
+      return ys[(size_t)j * C];
+    }
+    j -= 1;  // xs[j] < x < xs[j+1]
+    const double x0 = xs[(size_t)j * C], x1 = xs[(size_t)(j + 1) * C];
+    const double y0 = ys[(size_t)j * C], y1 = ys[(size_t)(j + 1) * C];
+    const double slope = __ddiv_rn(__dsub_rn(y1, y0), __dsub_rn(x1, x0));
+    double r = __dadd_rn(__dmul_rn(slope, __dsub_rn((double)x, x0)), y0);
+    if (r != r) {
+      r = __dadd_rn(__dmul_rn(slope, __dsub_rn((double)x, x1)), y1);
+      if (r != r && y0 == y1) r = y0;
+    }
+    return (T)r;
+  }
+  // interp1d._call_linear: searchsorted(x, x_new) clipped to [1, n-1]; two-term form.
+  int idx = lower_bound_col<TX, T, C>(xs, n, x);
+  idx = idx < 1 ? 1 : (idx > n - 1 ? n - 1 : idx);
+  const T x_lo = xs[(size_t)(idx - 1) * C], x_hi = xs[(size_t)idx * C];
+  const T y_lo = ys[(size_t)(idx - 1) * C], y_hi = ys[(size_t)idx * C];
+  const T den = Num<T>::sub(x_hi, x_lo);  // node dtype
+  const TX w_hi = Num<TX>::div(Num<TX>::sub(x, (TX)x_lo), (TX)den);
+  const TX w_lo = Num<TX>::div(Num<TX>::sub((TX)x_hi, x), (TX)den);
+  return (T)Num<TX>::add(Num<TX>::mul(w_hi, (TX)y_hi), Num<TX>::mul(w_lo, (TX)y_lo));
+}
+
+// best candidate of one compacted row for the 2-D Euclidean-nearest rule
+template <typename TX, typename T, int C>
+__device__ __forceinline__ void nearest_in_row(const T* xs, const T* ys, int n, TX x, double dg2, double& best_d2,
+                                               T& best_y) {
+  if (n == 0) return;
+  const int i = lower_bound_col<TX, T, C>(xs, n, x);
+  double dbest = 1e300;  // placeholder, replaced below
+  int ibest = -1;
+  if (i > 0) { dbest = fabs((double)x - (double)xs[(size_t)(i - 1) * C]); ibest = i - 1; }
+  if (i < n) {
+    const double d = fabs((double)xs[(size_t)i * C] - (double)x);
+    if (ibest < 0 || d < dbest) { dbest = d; ibest = i; }
+  }
+  const double d2 = __dadd_rn(__dmul_rn(dbest, dbest), dg2);
+  if (d2 < best_d2) { best_d2 = d2; best_y = ys[(size_t)ibest * C]; }
+}
+
+// 2-D rule = scipy griddata(method="nearest") on points (hist_q, group coordinate) in raw units
+// + _extrapolate_on_quantiles (utils.py:380-400, 477-513; nbutils.py:392-416).  r is the group of
+// the sample (0-based); rows are the cyclically padded table rows r-1..r+1 (+ global fallback).
+template <typename TX, typename T, int C>
+__device__ T lookup_2d_nearest(const Tables<T, C>& tb, int c, long long pt, int r, TX x, int extrap) {
+  if (is_nan(x)) return Num<T>::nan();
+  const int nq = tb.nq;
+  double best_d2 = __longlong_as_double(0x7ff0000000000000LL);
+  T best_y = Num<T>::nan();
+  nearest_in_row<TX, T, C>(tb.xs + (size_t)1 * nq * C + c, tb.ys + (size_t)1 * nq * C + c, tb.nv[1 * C + c], x, 0.0,
+                           best_d2, best_y);
+  // padded row coordinate of the sample is r+1 in [1, G]; padded rows exist for 0..G+1
+  for (int dist = 1; dist <= tb.G + 1; ++dist) {
+    const double dg2 = (double)dist * (double)dist;
+    if (dg2 >= best_d2) break;  // nothing at this row distance can be strictly nearer
+    for (int sgn = -1; sgn <= 1; sgn += 2) {
+      const int pr = r + 1 + sgn * dist;  // padded row index
+      if (pr < 0 || pr > tb.G + 1) continue;
+      if (dist == 1) {
+        const int slot = 1 + sgn;
+        nearest_in_row<TX, T, C>(tb.xs + (size_t)slot * nq * C + c, tb.ys + (size_t)slot * nq * C + c,
+                                 tb.nv[slot * C + c], x, dg2, best_d2, best_y);
+      } else {
+        // rare: scan the raw row in global memory (padded row pr is group (pr-1) mod G)
+        const int g = (pr - 1 + tb.G) % tb.G;
+        const T* gx = tb.x_shared ? tb.gx : tb.gx + pt * tb.pt_stride + (long long)g * nq;
+        const T* gy = tb.gy + pt * tb.pt_stride + (long long)g * nq;
+        for (int k = 0; k < nq; ++k) {
+          const T xv = gx[k], yv = gy[k];
+          if (is_nan(xv) || is_nan(yv)) continue;
+          const double d = fabs((double)x - (double)xv);
+          const double d2 = __dadd_rn(__dmul_rn(d, d), dg2);
+          if (d2 < best_d2) { best_d2 = d2; best_y = yv; }
+        }
+      }
+    }
+  }
+  T out = best_y;
+  // _extrapolate_on_quantiles: integer group coordinate -> np.interp returns the row's own bound
+  const double xd = (double)x;
+  if (xd < (double)tb.blo[c]) out = extrap == 0 ? tb.clo[c] : Num<T>::nan();
+  if (xd > (double)tb.bhi[c]) out = extrap == 0 ? tb.chi[c] : Num<T>::nan();
+  return out;
+}
+
+template <typename T> __device__ __forceinline__ T apply_corr(T x, T f, int kind) {
+  return kind == 43 ? Num<T>::add(x, f) : Num<T>::mul(x, f);  // utils.py:146-162
+}
+
+}  // namespace xsdba

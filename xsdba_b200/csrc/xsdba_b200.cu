@@ -1,0 +1,638 @@
+// xsdba_b200: CUDA kernels (sm_100a) + C ABI for the quantile-mapping hot path of xsdba.
+// See include/xsdba_b200.h for the boundary and DESIGN.md for the kernel inventory.
+#include "../../include/xsdba_b200.h"
+#include "common.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace xsdba;
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+
+constexpr int kThreads = 256;
+constexpr int kSortBytes = 128 * 1024;  // shared-memory budget of the column sorter
+
+struct DevTable {
+  int32_t* off = nullptr;   // [G+1]
+  int32_t* rows = nullptr;  // time index, or -1 for a window slot outside the series
+  int64_t total = 0;
+  int32_t max_len = 0;
+};
+
+}  // namespace
+
+struct xsdba_grouping {
+  int64_t n_time = 0;
+  int32_t n_groups = 0;
+  int32_t window = 1;
+  int device = 0;
+  DevTable members;   // exact group members (window = 1), ascending time
+  DevTable segments;  // members x window slots (aliases `members` when window == 1)
+};
+
+namespace {
+
+// =============================================================================================
+// K1: group-segmented quantiles / train.  grid = (ceil(n_pts / C), n_groups).
+// One CTA stages the whole segment of C neighbouring points in shared memory ([n_pad][C], column =
+// point, so time-major inputs are read as contiguous C*sizeof(T)-byte rows), sorts each column and
+// evaluates the nq type-7 quantiles.  mode 0: train (ref, hist -> af, hist_q[, scaling]);
+// mode 1: quantiles of `ref` only -> af (used as `out`).
+// =============================================================================================
+template <typename T, int C>
+__device__ void load_segment(T* sm, const T* __restrict__ src, long long n0, long long n_pts, long long sp,
+                             long long st, const int32_t* __restrict__ rows, int S, int n_pad) {
+  const int total = n_pad * C;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int r = idx / C;
+    const int c = idx % C;
+    T v = Num<T>::nan();
+    if (r < S && n0 + c < n_pts) {
+      const int t = rows[r];
+      if (t >= 0) v = src[(n0 + c) * sp + (long long)t * st];
+    }
+    sm[idx] = v;
+  }
+}
+
+// Per-column valid count (and float64 sum of the valid values when want_sum).  blockDim % C == 0, so
+// idx % C is constant per thread.
+template <typename T, int C>
+__device__ void count_columns(const T* sm, int n_pad, int* cnt /*[C]*/, double* sum /*[C]*/, bool want_sum) {
+  if (threadIdx.x < C) { cnt[threadIdx.x] = 0; sum[threadIdx.x] = 0.0; }
+  __syncthreads();
+  const int total = n_pad * C;
+  int my_cnt = 0;
+  double my_sum = 0.0;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const T v = sm[idx];
+    if (!is_nan(v)) {
+      ++my_cnt;
+      if (want_sum) my_sum += (double)v;
+    }
+  }
+  const int c = threadIdx.x % C;
+  atomicAdd(&cnt[c], my_cnt);
+  if (want_sum) atomicAdd(&sum[c], my_sum);
+  __syncthreads();
+}
+
+// NaN -> +inf sort keys; optional DQM normalisation x + (-mu) or x * (1/mu) of the valid values
+// (_adjustment.py:167-168 through utils.invert / apply_correction, utils.py:146-177).
+template <typename T, int C>
+__device__ void make_keys(T* sm, int n_pad, const int* cnt, const double* sum, int normalize, int kind) {
+  const int c = threadIdx.x % C;
+  T inv = (T)0;
+  if (normalize) {
+    const T mu = (T)(sum[c] / (double)cnt[c]);
+    inv = kind == XSDBA_KIND_ADD ? -mu : Num<T>::div((T)1, mu);
+  }
+  const int total = n_pad * C;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    T v = sm[idx];
+    if (is_nan(v)) {
+      v = Num<T>::inf();
+    } else if (normalize) {
+      v = kind == XSDBA_KIND_ADD ? Num<T>::add(v, inv) : Num<T>::mul(v, inv);
+      if (is_nan(v)) v = Num<T>::inf();  // (cannot happen for finite data; keeps the sorter NaN-free)
+    }
+    sm[idx] = v;
+  }
+  __syncthreads();
+}
+
+template <typename T, int C>
+__global__ void __launch_bounds__(kThreads)
+train_kernel(const T* __restrict__ ref, const T* __restrict__ hist, long long n_pts, long long sp, long long st,
+             const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
+             const T* __restrict__ q, int nq, int kind, int normalize, int mode, T* __restrict__ af,
+             T* __restrict__ hist_q, T* __restrict__ scaling, int n_pad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sum = reinterpret_cast<double*>(smem_raw);   // [C]
+  double* mu_ref = sum + C;                            // [C]
+  int* cnt = reinterpret_cast<int*>(mu_ref + C);       // [C]
+  T* refq = reinterpret_cast<T*>(smem_raw + C * 24);   // [nq][C]  (24 = 8 + 8 + 4, padded to 8)
+  T* sm = refq + (size_t)nq * C;                       // [n_pad][C]
+
+  const int g = blockIdx.y;
+  const long long n0 = (long long)blockIdx.x * C;
+  const int S = seg_off[g + 1] - seg_off[g];
+  const int32_t* rows = seg_rows + seg_off[g];
+  const long long out_stride = (long long)n_groups * nq;
+
+  if (S == 0) {  // group without members: NaN rows (template of base.map_blocks, base.py:652-694)
+    for (int item = threadIdx.x; item < C * nq; item += blockDim.x) {
+      const int c = item / nq, k = item % nq;
+      if (n0 + c >= n_pts) continue;
+      const long long o = (n0 + c) * out_stride + (long long)g * nq + k;
+      af[o] = Num<T>::nan();
+      if (mode == 0) hist_q[o] = Num<T>::nan();
+    }
+    if (mode == 0 && scaling && threadIdx.x < C && n0 + threadIdx.x < n_pts)
+      scaling[(n0 + threadIdx.x) * n_groups + g] = Num<T>::nan();
+    return;
+  }
+
+  const int n_pass = mode == 0 ? 2 : 1;
+  for (int pass = 0; pass < n_pass; ++pass) {
+    const T* src = pass == 0 ? ref : hist;
+    load_segment<T, C>(sm, src, n0, n_pts, sp, st, rows, S, n_pad);
+    __syncthreads();
+    count_columns<T, C>(sm, n_pad, cnt, sum, normalize != 0);
+    make_keys<T, C>(sm, n_pad, cnt, sum, normalize, kind);
+    sort_columns<T, C>(sm, n_pad);
+    // quantiles: item -> (point c, node k), k fastest so that global writes are contiguous
+    for (int item = threadIdx.x; item < C * nq; item += blockDim.x) {
+      const int c = item / nq, k = item % nq;
+      const T v = quantile_sorted<T, C>(sm + c, cnt[c], S, q[k]);
+      if (mode == 1) {
+        if (n0 + c < n_pts) af[(n0 + c) * out_stride + (long long)g * nq + k] = v;
+      } else if (pass == 0) {
+        refq[k * C + c] = v;
+      } else if (n0 + c < n_pts) {
+        const long long o = (n0 + c) * out_stride + (long long)g * nq + k;
+        const T rq = refq[k * C + c];
+        hist_q[o] = v;
+        af[o] = kind == XSDBA_KIND_ADD ? Num<T>::sub(rq, v) : Num<T>::div(rq, v);  // utils.py:130-143
+      }
+    }
+    if (normalize && mode == 0 && threadIdx.x < C) {
+      const int c = threadIdx.x;
+      const T mu = (T)(sum[c] / (double)cnt[c]);
+      if (pass == 0) {
+        mu_ref[c] = (double)mu;
+      } else if (scaling && n0 + c < n_pts) {
+        const T mr = (T)mu_ref[c];  // scaling = get_correction(mu_hist, mu_ref)  (_adjustment.py:177-179)
+        scaling[(n0 + c) * n_groups + g] = kind == XSDBA_KIND_ADD ? Num<T>::sub(mr, mu) : Num<T>::div(mr, mu);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// =============================================================================================
+// Table staging shared by the adjust kernels: rows r-1, r, r+1 (cyclic) of the tile's tables into
+// shared memory, NaN nodes dropped, bounds / constants of the centre row recorded.
+// =============================================================================================
+template <typename T, int C>
+__device__ void stage_tables(Tables<T, C>& tb, long long n0, long long n_pts, int r, bool grouped) {
+  const int nq = tb.nq;
+  const int n_slots = grouped ? 3 : 1;
+  // raw copy: lane -> point, so shared-memory writes are conflict free
+  for (int idx = threadIdx.x; idx < n_slots * nq * C; idx += blockDim.x) {
+    const int c = idx % C;
+    const int k = (idx / C) % nq;
+    const int s = idx / (C * nq);
+    const int slot = grouped ? s : 1;
+    const int g = grouped ? (r + slot - 1 + tb.G) % tb.G : 0;
+    T xv = Num<T>::nan(), yv = Num<T>::nan();
+    if (n0 + c < n_pts) {
+      const long long o = (n0 + c) * tb.pt_stride + (long long)g * nq + k;
+      xv = tb.x_shared ? tb.gx[k] : tb.gx[o];
+      yv = tb.gy[o];
+    }
+    tb.xs[((size_t)slot * nq + k) * C + c] = xv;
+    tb.ys[((size_t)slot * nq + k) * C + c] = yv;
+  }
+  __syncthreads();
+  // compaction: one thread per (slot, point)
+  for (int idx = threadIdx.x; idx < n_slots * C; idx += blockDim.x) {
+    const int c = idx % C;
+    const int slot = grouped ? idx / C : 1;
+    T* xs = tb.xs + (size_t)slot * nq * C + c;
+    T* ys = tb.ys + (size_t)slot * nq * C + c;
+    T blo = Num<T>::nan(), bhi = Num<T>::nan(), clo = Num<T>::nan(), chi = Num<T>::nan();
+    bool have_b = false, have_c = false;
+    int w = 0;
+    for (int k = 0; k < nq; ++k) {
+      const T xv = xs[(size_t)k * C], yv = ys[(size_t)k * C];
+      if (!is_nan(xv)) { if (!have_b) { blo = xv; have_b = true; } bhi = xv; }
+      if (!is_nan(yv)) { if (!have_c) { clo = yv; have_c = true; } chi = yv; }
+      if (!is_nan(xv) && !is_nan(yv)) { xs[(size_t)w * C] = xv; ys[(size_t)w * C] = yv; ++w; }
+    }
+    tb.nv[slot * C + c] = w;
+    if (slot == 1) { tb.blo[c] = blo; tb.bhi[c] = bhi; tb.clo[c] = clo; tb.chi[c] = chi; }
+  }
+  __syncthreads();
+}
+
+template <typename T, int C>
+__device__ Tables<T, C> carve_tables(unsigned char* base, int nq) {
+  Tables<T, C> tb;
+  tb.nq = nq;
+  tb.xs = reinterpret_cast<T*>(base);
+  tb.ys = tb.xs + (size_t)3 * nq * C;
+  tb.blo = tb.ys + (size_t)3 * nq * C;
+  tb.bhi = tb.blo + C;
+  tb.clo = tb.bhi + C;
+  tb.chi = tb.clo + C;
+  tb.nv = reinterpret_cast<int*>(tb.chi + C);
+  return tb;
+}
+template <typename T, int C>
+constexpr size_t tables_bytes(int nq) { return ((size_t)6 * nq * C + 4 * C) * sizeof(T) + 3 * C * sizeof(int); }
+
+// =============================================================================================
+// K2: streaming adjust, EQM / DQM flavour.  grid = (ceil(n_pts/32), n_groups); each warp walks the
+// time steps of its group, lane = point: read sim (coalesced for time-major), look the factor up,
+// apply, write scen.
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+adjust_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long st,
+              const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows, int n_groups,
+              const T* __restrict__ af, const T* __restrict__ hist_q, int nq, int interp, int extrap, int kind,
+              T* __restrict__ scen) {
+  constexpr int C = 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Tables<T, C> tb = carve_tables<T, C>(smem_raw, nq);
+  tb.gx = hist_q; tb.gy = af; tb.x_shared = false; tb.G = n_groups; tb.pt_stride = (long long)n_groups * nq;
+
+  const int g = blockIdx.y;
+  const long long n0 = (long long)blockIdx.x * C;
+  const int m0 = mem_off[g], m1 = mem_off[g + 1];
+  if (m0 == m1) return;
+  const bool grouped = n_groups > 1;
+  stage_tables<T, C>(tb, n0, n_pts, g, grouped);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const long long pt = n0 + lane;
+  if (pt >= n_pts) return;
+  for (int m = m0 + warp; m < m1; m += n_warps) {
+    const long long o = pt * sp + (long long)mem_rows[m] * st;
+    const T x = sim[o];
+    const T f = grouped ? lookup_2d_nearest<T, T, C>(tb, lane, pt, g, x, extrap)
+                        : lookup_1d<T, T, C>(tb, lane, x, interp, extrap);
+    scen[o] = apply_corr<T>(x, f, kind);
+  }
+}
+
+// =============================================================================================
+// K3: per-group percentile ranks (+ QDM factor lookup).  grid = (ceil(n_pts / C), n_groups).
+// The segment (exact members, or members x window when rank_window) of C points is sorted in shared
+// memory; every member then finds its average-tie rank by two binary searches in its sorted column.
+//   r = avgrank / n_valid ; sim_q = mx * (r - mn) / (mx - mn)         (utils.py:629-634)
+// With do_adjust: af lookup on the shared quantile axis and scen = sim (+|*) af (_adjustment.py:873-881).
+// =============================================================================================
+template <typename T, int C>
+__global__ void __launch_bounds__(kThreads)
+rank_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long st,
+            const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows,
+            const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
+            const T* __restrict__ af, const T* __restrict__ q, int nq, int interp, int extrap, int kind,
+            int do_adjust, T* __restrict__ scen, double* __restrict__ sim_q, int n_pad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* mnmx = reinterpret_cast<double*>(smem_raw);      // [2][C]
+  double* sum = mnmx + 2 * C;                              // [C] (unused sum slot of count_columns)
+  int* cnt = reinterpret_cast<int*>(sum + C);              // [C]
+  unsigned char* p = smem_raw + C * 28 + ((C * 28) % 8 ? 4 : 0);
+  T* sm = reinterpret_cast<T*>(p);                         // [n_pad][C]
+  Tables<T, C> tb = carve_tables<T, C>(p + (size_t)n_pad * C * sizeof(T), nq);
+
+  const int g = blockIdx.y;
+  const long long n0 = (long long)blockIdx.x * C;
+  const int m0 = mem_off[g], m1 = mem_off[g + 1];
+  if (m0 == m1) return;
+  const int S = seg_off[g + 1] - seg_off[g];
+  const bool grouped = n_groups > 1;
+
+  load_segment<T, C>(sm, sim, n0, n_pts, sp, st, seg_rows + seg_off[g], S, n_pad);
+  __syncthreads();
+  count_columns<T, C>(sm, n_pad, cnt, sum, false);
+  make_keys<T, C>(sm, n_pad, cnt, sum, 0, kind);
+  sort_columns<T, C>(sm, n_pad);
+  if (do_adjust) {
+    tb.gx = q; tb.gy = af; tb.x_shared = true; tb.G = n_groups; tb.pt_stride = (long long)n_groups * nq;
+    stage_tables<T, C>(tb, n0, n_pts, g, grouped);
+  }
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x, n = cnt[c];
+    double mn = __longlong_as_double(0x7ff8000000000000LL), mx = mn;
+    if (n > 0) {
+      const T* col = sm + c;
+      const T vmin = col[0], vmax = col[(size_t)(n - 1) * C];
+      int ub = 1; while (ub < n && col[(size_t)ub * C] == vmin) ++ub;          // multiplicity of the minimum
+      int lb = n - 1; while (lb > 0 && col[(size_t)(lb - 1) * C] == vmax) --lb;  // first index of the maximum
+      mn = ((double)(ub + 1) * 0.5) / (double)n;          // avg rank of ranks 1..ub
+      mx = ((double)(lb + n + 1) * 0.5) / (double)n;      // avg rank of ranks lb+1..n
+    }
+    mnmx[c] = mn; mnmx[C + c] = mx;
+  }
+  __syncthreads();
+
+  // members: item -> (member m, point c), c fastest (coalesced for time-major)
+  const int n_mem = m1 - m0;
+  for (int item = threadIdx.x; item < n_mem * C; item += blockDim.x) {
+    const int c = item % C;
+    const long long pt = n0 + c;
+    if (pt >= n_pts) continue;
+    const long long o = pt * sp + (long long)mem_rows[m0 + item / C] * st;
+    const T x = sim[o];
+    double sq = __longlong_as_double(0x7ff8000000000000LL);
+    const int n = cnt[c];
+    if (!is_nan(x) && n > 0) {
+      const T* col = sm + c;
+      int lo = 0, hi = n;  // lower bound: #values < x
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[(size_t)mid * C] < x) lo = mid + 1; else hi = mid; }
+      const int lb = lo;
+      hi = n;              // upper bound: #values <= x
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[(size_t)mid * C] <= x) lo = mid + 1; else hi = mid; }
+      const int ub = lo;
+      const double r = ((double)(lb + ub + 1) * 0.5) / (double)n;
+      const double mn = mnmx[c], mx = mnmx[C + c];
+      sq = __ddiv_rn(__dmul_rn(mx, __dsub_rn(r, mn)), __dsub_rn(mx, mn));
+    }
+    if (sim_q) sim_q[o] = sq;
+    if (do_adjust) {
+      const T f = grouped ? lookup_2d_nearest<double, T, C>(tb, c, pt, g, sq, extrap)
+                          : lookup_1d<double, T, C>(tb, c, sq, interp, extrap);
+      scen[o] = apply_corr<T>(x, f, kind);
+    }
+  }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? XSDBA_OK : (int)e; }
+#define XS_CUDA(call)                                  \
+  do {                                                 \
+    cudaError_t _e = (call);                           \
+    if (_e != cudaSuccess) return (int)_e;             \
+  } while (0)
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+template <typename T> int pick_cols(int n_pad) {
+  int c = (int)(kSortBytes / sizeof(T)) / n_pad;
+  if (c >= 32) return 32;
+  int p = 1; while (p * 2 <= c) p *= 2;
+  return c < 1 ? 0 : p;
+}
+
+template <typename K> int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) XS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return XSDBA_OK;
+}
+
+template <typename T, int C>
+int launch_train_c(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
+                   const T* q, int nq, int kind, int normalize, int mode, T* af, T* hq, T* scaling, int n_pad,
+                   cudaStream_t s) {
+  const size_t smem = (size_t)C * 24 + ((size_t)nq * C + (size_t)n_pad * C) * sizeof(T);
+  auto kern = train_kernel<T, C>;
+  int rc = set_smem(kern, smem);
+  if (rc) return rc;
+  dim3 grid((unsigned)((n_pts + C - 1) / C), (unsigned)grp->n_groups);
+  kern<<<grid, kThreads, smem, s>>>(ref, hist, n_pts, sp, st, grp->segments.off, grp->segments.rows, grp->n_groups, q,
+                                    nq, kind, normalize, mode, af, hq, scaling, n_pad);
+  ++g_launches;
+  return cuda_status(cudaGetLastError());
+}
+
+template <typename T>
+int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
+                 const T* q, int nq, int kind, int normalize, int mode, T* af, T* hq, T* scaling, void* stream) {
+  if (!ref || !grp || !q || !af || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (mode == 0 && (!hist || !hq)) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (normalize && mode == 0 && !scaling) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (n_pts == 0) return XSDBA_OK;
+  if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
+  const int n_pad = std::max(2, next_pow2(grp->segments.max_len));
+  const int C = pick_cols<T>(n_pad);
+  cudaStream_t s = (cudaStream_t)stream;
+#define XS_CASE(CC) case CC: return launch_train_c<T, CC>(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, n_pad, s)
+  switch (C) {
+    XS_CASE(32); XS_CASE(16); XS_CASE(8); XS_CASE(4); XS_CASE(2); XS_CASE(1);
+    default: return XSDBA_ERR_SEGMENT_TOO_LONG;
+  }
+#undef XS_CASE
+}
+
+template <typename T>
+int launch_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* af,
+                  const T* hq, int nq, int interp, int extrap, int kind, T* scen, void* stream) {
+  if (!sim || !grp || !af || !hq || !scen || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (extrap != XSDBA_EXTRAP_CONSTANT && extrap != XSDBA_EXTRAP_NAN) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (grp->n_groups > 1 && interp != XSDBA_INTERP_NEAREST) return XSDBA_ERR_UNSUPPORTED;
+  if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
+  if (n_pts == 0) return XSDBA_OK;
+  const size_t smem = tables_bytes<T, 32>(nq);
+  if (smem > 200 * 1024) return XSDBA_ERR_UNSUPPORTED;
+  auto kern = adjust_kernel<T>;
+  int rc = set_smem(kern, smem);
+  if (rc) return rc;
+  dim3 grid((unsigned)((n_pts + 31) / 32), (unsigned)grp->n_groups);
+  kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows,
+                                                       grp->n_groups, af, hq, nq, interp, extrap, kind, scen);
+  ++g_launches;
+  return cuda_status(cudaGetLastError());
+}
+
+template <typename T, int C>
+int launch_rank_c(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
+                  const DevTable& seg, const T* af, const T* q, int nq, int interp, int extrap, int kind,
+                  int do_adjust, T* scen, double* sim_q, int n_pad, cudaStream_t s) {
+  const size_t head = (size_t)C * 28 + (((size_t)C * 28) % 8 ? 4 : 0);
+  const size_t smem = head + (size_t)n_pad * C * sizeof(T) + tables_bytes<T, C>(do_adjust ? nq : 0);
+  if (smem > 220 * 1024) return XSDBA_ERR_SEGMENT_TOO_LONG;
+  auto kern = rank_kernel<T, C>;
+  int rc = set_smem(kern, smem);
+  if (rc) return rc;
+  dim3 grid((unsigned)((n_pts + C - 1) / C), (unsigned)grp->n_groups);
+  kern<<<grid, kThreads, smem, s>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows, seg.off, seg.rows,
+                                    grp->n_groups, af, q, do_adjust ? nq : 0, interp, extrap, kind, do_adjust, scen,
+                                    sim_q, n_pad);
+  ++g_launches;
+  return cuda_status(cudaGetLastError());
+}
+
+template <typename T>
+int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* af,
+                const T* q, int nq, int interp, int extrap, int kind, int rank_window, int do_adjust, T* scen,
+                double* sim_q, void* stream) {
+  if (!sim || !grp || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (do_adjust) {
+    if (!af || !q || !scen || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
+    if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
+    if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR) return XSDBA_ERR_INVALID_ARGUMENT;
+    if (extrap != XSDBA_EXTRAP_CONSTANT && extrap != XSDBA_EXTRAP_NAN) return XSDBA_ERR_INVALID_ARGUMENT;
+    if (grp->n_groups > 1 && interp != XSDBA_INTERP_NEAREST) return XSDBA_ERR_UNSUPPORTED;
+  } else if (!sim_q) {
+    return XSDBA_ERR_INVALID_ARGUMENT;
+  }
+  if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
+  if (n_pts == 0) return XSDBA_OK;
+  const DevTable& seg = rank_window ? grp->segments : grp->members;
+  const int n_pad = std::max(2, next_pow2(seg.max_len));
+  int C = pick_cols<T>(n_pad);
+  cudaStream_t s = (cudaStream_t)stream;
+#define XS_CASE(CC) case CC: return launch_rank_c<T, CC>(sim, n_pts, sp, st, grp, seg, af, q, nq, interp, extrap, kind, do_adjust, scen, sim_q, n_pad, s)
+  switch (C) {
+    XS_CASE(32); XS_CASE(16); XS_CASE(8); XS_CASE(4); XS_CASE(2); XS_CASE(1);
+    default: return XSDBA_ERR_SEGMENT_TOO_LONG;
+  }
+#undef XS_CASE
+}
+
+int upload_table(const std::vector<int32_t>& off, const std::vector<int32_t>& rows, DevTable& t) {
+  XS_CUDA(cudaMalloc(&t.off, off.size() * sizeof(int32_t)));
+  XS_CUDA(cudaMalloc(&t.rows, std::max<size_t>(rows.size(), 1) * sizeof(int32_t)));
+  XS_CUDA(cudaMemcpy(t.off, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (!rows.empty()) XS_CUDA(cudaMemcpy(t.rows, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  t.total = (int64_t)rows.size();
+  t.max_len = 0;
+  for (size_t g = 0; g + 1 < off.size(); ++g) t.max_len = std::max(t.max_len, off[g + 1] - off[g]);
+  return XSDBA_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int xsdba_version(void) { return 100; }
+
+int64_t xsdba_launch_count(void) { return g_launches.load(); }
+
+const char* xsdba_status_string(int status) {
+  switch (status) {
+    case XSDBA_OK: return "ok";
+    case XSDBA_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case XSDBA_ERR_UNSUPPORTED: return "valid in xsdba but not supported by xsdba_b200 yet";
+    case XSDBA_ERR_SEGMENT_TOO_LONG: return "a (point, group) segment is longer than the in-SM sorter accepts";
+    case XSDBA_ERR_NO_DEVICE: return "no CUDA device";
+    case XSDBA_ERR_OUT_OF_MEMORY: return "out of memory";
+    default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown error";
+  }
+}
+
+int xsdba_grouping_create(xsdba_grouping_t** out, const int32_t* grp_idx_host, int64_t n_time, int32_t n_groups,
+                          int32_t window) {
+  if (!out || !grp_idx_host || n_time <= 0 || n_groups <= 0 || window < 1 || n_time > 0x7fffffff)
+    return XSDBA_ERR_INVALID_ARGUMENT;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return XSDBA_ERR_NO_DEVICE;
+  for (int64_t t = 0; t < n_time; ++t)
+    if (grp_idx_host[t] < -1 || grp_idx_host[t] >= n_groups) return XSDBA_ERR_INVALID_ARGUMENT;
+  xsdba_grouping* g = new (std::nothrow) xsdba_grouping();
+  if (!g) return XSDBA_ERR_OUT_OF_MEMORY;
+  g->n_time = n_time; g->n_groups = n_groups; g->window = window;
+  cudaGetDevice(&g->device);
+  std::vector<int32_t> off(n_groups + 1, 0), rows;
+  for (int64_t t = 0; t < n_time; ++t) if (grp_idx_host[t] >= 0) ++off[grp_idx_host[t] + 1];
+  for (int i = 0; i < n_groups; ++i) off[i + 1] += off[i];
+  rows.resize(off[n_groups]);
+  {
+    std::vector<int32_t> cur(off.begin(), off.end() - 1);
+    for (int64_t t = 0; t < n_time; ++t) if (grp_idx_host[t] >= 0) rows[cur[grp_idx_host[t]]++] = (int32_t)t;
+  }
+  int rc = upload_table(off, rows, g->members);
+  if (rc == XSDBA_OK) {
+    if (window == 1) {
+      g->segments = g->members;
+    } else {
+      // rolling(center=True).construct: slot j of the row centred on t is x[t - window/2 + j]  (base.py:261-265)
+      const int half = window / 2;
+      std::vector<int32_t> soff(n_groups + 1), srows;
+      if ((int64_t)rows.size() * window > 0x7fffffff) { rc = XSDBA_ERR_SEGMENT_TOO_LONG; }
+      else {
+        srows.reserve(rows.size() * (size_t)window);
+        for (int i = 0; i < n_groups; ++i) {
+          soff[i] = (int32_t)srows.size();
+          for (int m = off[i]; m < off[i + 1]; ++m)
+            for (int j = 0; j < window; ++j) {
+              const int64_t tt = (int64_t)rows[m] - half + j;
+              srows.push_back(tt >= 0 && tt < n_time ? (int32_t)tt : -1);
+            }
+        }
+        soff[n_groups] = (int32_t)srows.size();
+        rc = upload_table(soff, srows, g->segments);
+      }
+    }
+  }
+  if (rc != XSDBA_OK) { xsdba_grouping_destroy(g); return rc; }
+  if (g->segments.max_len > XSDBA_MAX_SEGMENT) { xsdba_grouping_destroy(g); return XSDBA_ERR_SEGMENT_TOO_LONG; }
+  *out = g;
+  return XSDBA_OK;
+}
+
+int xsdba_grouping_destroy(xsdba_grouping_t* g) {
+  if (!g) return XSDBA_OK;
+  if (g->segments.off != g->members.off) { cudaFree(g->segments.off); cudaFree(g->segments.rows); }
+  cudaFree(g->members.off);
+  cudaFree(g->members.rows);
+  delete g;
+  return XSDBA_OK;
+}
+
+int64_t xsdba_grouping_max_segment(const xsdba_grouping_t* g) { return g ? g->segments.max_len : -1; }
+int32_t xsdba_grouping_n_groups(const xsdba_grouping_t* g) { return g ? g->n_groups : -1; }
+
+int xsdba_qm_train_f32(const float* ref, const float* hist, int64_t n_pts, int64_t sp, int64_t st,
+                       const xsdba_grouping_t* grp, const float* q, int32_t nq, int32_t kind, int32_t normalize,
+                       float* af, float* hq, float* scaling, void* stream) {
+  return launch_train<float>(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, 0, af, hq, scaling, stream);
+}
+int xsdba_qm_train_f64(const double* ref, const double* hist, int64_t n_pts, int64_t sp, int64_t st,
+                       const xsdba_grouping_t* grp, const double* q, int32_t nq, int32_t kind, int32_t normalize,
+                       double* af, double* hq, double* scaling, void* stream) {
+  return launch_train<double>(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, 0, af, hq, scaling, stream);
+}
+int xsdba_group_quantile_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                             const float* q, int32_t nq, float* out, void* stream) {
+  return launch_train<float>(x, nullptr, n_pts, sp, st, grp, q, nq, XSDBA_KIND_ADD, 0, 1, out, nullptr, nullptr, stream);
+}
+int xsdba_group_quantile_f64(const double* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                             const double* q, int32_t nq, double* out, void* stream) {
+  return launch_train<double>(x, nullptr, n_pts, sp, st, grp, q, nq, XSDBA_KIND_ADD, 0, 1, out, nullptr, nullptr, stream);
+}
+
+int xsdba_qm_adjust_f32(const float* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                        const float* af, const float* hq, int32_t nq, int32_t interp, int32_t extrap, int32_t kind,
+                        float* scen, void* stream) {
+  return launch_adjust<float>(sim, n_pts, sp, st, grp, af, hq, nq, interp, extrap, kind, scen, stream);
+}
+int xsdba_qm_adjust_f64(const double* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                        const double* af, const double* hq, int32_t nq, int32_t interp, int32_t extrap, int32_t kind,
+                        double* scen, void* stream) {
+  return launch_adjust<double>(sim, n_pts, sp, st, grp, af, hq, nq, interp, extrap, kind, scen, stream);
+}
+
+int xsdba_qdm_adjust_f32(const float* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                         const float* af, const float* q, int32_t nq, int32_t interp, int32_t extrap, int32_t kind,
+                         int32_t rank_window, float* scen, double* sim_q, void* stream) {
+  return launch_rank<float>(sim, n_pts, sp, st, grp, af, q, nq, interp, extrap, kind, rank_window, 1, scen, sim_q, stream);
+}
+int xsdba_qdm_adjust_f64(const double* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                         const double* af, const double* q, int32_t nq, int32_t interp, int32_t extrap, int32_t kind,
+                         int32_t rank_window, double* scen, double* sim_q, void* stream) {
+  return launch_rank<double>(sim, n_pts, sp, st, grp, af, q, nq, interp, extrap, kind, rank_window, 1, scen, sim_q, stream);
+}
+int xsdba_group_rank_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                         int32_t rank_window, double* rank, void* stream) {
+  return launch_rank<float>(x, n_pts, sp, st, grp, nullptr, nullptr, 0, 0, 0, XSDBA_KIND_ADD, rank_window, 0, nullptr, rank, stream);
+}
+int xsdba_group_rank_f64(const double* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                         int32_t rank_window, double* rank, void* stream) {
+  return launch_rank<double>(x, n_pts, sp, st, grp, nullptr, nullptr, 0, 0, 0, XSDBA_KIND_ADD, rank_window, 0, nullptr, rank, stream);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// host end-to-end entry point (defined in host_pipeline.inc)
+// ---------------------------------------------------------------------------------------------
+#include "host_pipeline.inc"
