@@ -670,3 +670,64 @@ def loess_smoothing(y, time_coord, d=1, f=0.5, niter=2, weights="tricube", equal
         equal_spacing = True
     dx = float(x[1] - x[0]) if equal_spacing else 0
     return loess_nb(x, y, f=f, niter=niter, weights=weights, d=d, dx=dx, skipna=skipna)
+
+
+# ----------------------------------------------------------------------------------------------
+# tie detection for the 2-D nearest rule (test helper)
+# ----------------------------------------------------------------------------------------------
+
+def nearest_2d_candidates(newx, newg, oldx, oldy, oldg, chunk=256):
+    """Brute-force version of the 2-D nearest rule: for every query return (ymin, ymax, n_tied) over
+    ALL nodes at the minimal squared distance ``dx*dx + dg*dg`` (float64, SciPy's arithmetic).
+
+    SciPy's cKDTree breaks exact distance ties by tree-traversal order, which the reference does not
+    control ("parity unpinned on ties").  Tests use this to require bit-equality
+    wherever the nearest node is unique and "one of the tied nodes" elsewhere.
+    """
+    m = ~(np.isnan(oldx) | np.isnan(oldy) | np.isnan(oldg))
+    px = oldx[m].astype(np.float64)
+    pg = oldg[m].astype(np.float64)
+    py = oldy[m]
+    n = newx.shape[0]
+    ymin = np.full(n, np.nan)
+    ymax = np.full(n, np.nan)
+    ntied = np.zeros(n, np.int64)
+    if px.size == 0:
+        return ymin, ymax, ntied
+    for s in range(0, n, chunk):
+        x = newx[s:s + chunk].astype(np.float64)[:, None]
+        g = np.asarray(newg[s:s + chunk], np.float64)[:, None]
+        dx = x - px[None, :]
+        dg = g - pg[None, :]
+        d2 = dx * dx + dg * dg
+        best = np.nanmin(np.where(np.isnan(d2), np.inf, d2), axis=1, keepdims=True)
+        tied = d2 == best
+        yy = np.where(tied, py[None, :].astype(np.float64), np.nan)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ymin[s:s + chunk] = np.nanmin(yy, axis=1)
+            ymax[s:s + chunk] = np.nanmax(yy, axis=1)
+        ntied[s:s + chunk] = tied.sum(axis=1)
+    bad = np.isnan(newx) | np.isnan(np.asarray(newg, np.float64))
+    ymin[bad] = np.nan
+    ymax[bad] = np.nan
+    return ymin, ymax, ntied
+
+
+def qm_adjust_factor_bounds(newx, af, xq, *, group, time, extrapolation):
+    """For grouped nearest lookups: (lo, hi) factor each value may legally take -- equal wherever the
+    nearest node is unique, the min/max over the tied nodes otherwise; extrapolation applied.
+    ``xq`` is hist_q [N,G,nq] (EQM/DQM) or the shared quantile axis [nq] (QDM, newx = sim_q)."""
+    N, T = newx.shape
+    _, G, coords = group_index(time, group)
+    newg = group_index(time, group)[0].astype(np.int64) + (0 if group.endswith("season") else 1)
+    lo = np.empty((N, T)); hi = np.empty((N, T))
+    for i in range(N):
+        x_i = np.broadcast_to(xq, (G, af.shape[-1])) if xq.ndim == 1 else xq[i]
+        oldx, cc = add_cyclic_bounds(x_i, coords)
+        oldy, _ = add_cyclic_bounds(af[i], coords)
+        oldg = np.broadcast_to(cc[:, None], oldx.shape)
+        a, b, _ = nearest_2d_candidates(newx[i], newg, oldx, oldy, oldg)
+        lo[i] = extrapolate_on_quantiles(a, oldx, oldg, oldy, newx[i], newg, extrapolation)
+        hi[i] = extrapolate_on_quantiles(b, oldx, oldg, oldy, newx[i], newg, extrapolation)
+    return lo, hi

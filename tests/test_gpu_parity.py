@@ -89,7 +89,23 @@ def test_qm_adjust_nearest_matches_oracle(case, extrap):
     out = xs.qm_adjust(xs.Dataset({"sim": sim, "af": af_o, "hist_q": hq_o}, time=tx), group=xs.Grouper(group, window),
                        interp="nearest", extrapolation=extrap, kind=kind)
     scen = _np(out.scen).T
-    assert bits_equal(scen, scen_o)  # nearest lookup is an exact table pick
+    if group == "time":
+        assert bits_equal(scen, scen_o)  # interp1d nearest is an exact, tie-defined table pick
+        return
+    # 2-D nearest: bit-exact wherever the nearest node is unique; where two nodes are exactly
+    # equidistant SciPy's cKDTree picks by traversal order ("parity unpinned on ties"):
+    # there the CUDA value must be one of the tied candidates.
+    lo, hi = o.qm_adjust_factor_bounds(sim.T.copy(), af_o, hq_o, group=group, time=to, extrapolation=extrap)
+    simT = sim.T
+    s_lo = o.apply_correction(simT, lo.astype(dt), kind).astype(dt)
+    s_hi = o.apply_correction(simT, hi.astype(dt), kind).astype(dt)
+    unique = (s_lo == s_hi) | (np.isnan(s_lo) & np.isnan(s_hi))
+    assert unique.mean() > 0.9  # (the 5-valid-sample point has many duplicated nodes = ties)
+    assert bits_equal(np.where(unique, scen, 0), np.where(unique, scen_o, 0))
+    tie = ~unique
+    mn, mx = np.minimum(s_lo, s_hi)[tie], np.maximum(s_lo, s_hi)[tie]  # >2 nodes may tie: any of them is legal
+    assert ((scen[tie] >= mn) & (scen[tie] <= mx)).all()
+    assert ((scen_o[tie] >= mn) & (scen_o[tie] <= mx)).all()
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
@@ -135,7 +151,20 @@ def test_qdm_adjust_matches_oracle(case):
                             group=xs.Grouper(group, window), interp="nearest", extrapolation="constant", kind=kind,
                             rank_window=rank_window)
     assert bits_equal(_np(out.sim_q).T, simq_o)      # ranks are exact rationals in float64
-    assert bits_equal(_np(out.scen).T, scen_o)
+    scen = _np(out.scen).T
+    if group == "time":
+        assert bits_equal(scen, scen_o)
+        return
+    # exact ties between two quantile nodes are resolved by SciPy's KD-tree traversal order (unpinned)
+    lo, hi = o.qm_adjust_factor_bounds(simq_o, af_o, q, group=group, time=to, extrapolation="constant")
+    s_lo = o.apply_correction(sim.T, lo.astype(dt), kind).astype(dt)
+    s_hi = o.apply_correction(sim.T, hi.astype(dt), kind).astype(dt)
+    unique = (s_lo == s_hi) | (np.isnan(s_lo) & np.isnan(s_hi))
+    assert unique.mean() > 0.95
+    assert bits_equal(np.where(unique, scen, 0), np.where(unique, scen_o, 0))
+    tie = ~unique
+    mn, mx = np.minimum(s_lo, s_hi)[tie], np.maximum(s_lo, s_hi)[tie]
+    assert ((scen[tie] >= mn) & (scen[tie] <= mx)).all()
 
 
 def test_group_quantile_reference_golden(golden):

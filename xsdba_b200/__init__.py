@@ -5,5 +5,6 @@ from ._adjustment import (  # noqa: F401
     Dataset, dqm_train, eqm_train, group_quantile, group_rank, qdm_adjust, qm_adjust,
 )
 from .utils import equally_spaced_nodes  # noqa: F401
+from .adjustment import EmpiricalQuantileMapping, QuantileDeltaMapping, train_adjust_host  # noqa: F401
 
 __version__ = "0.1.0"

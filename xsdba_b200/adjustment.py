@@ -1,0 +1,95 @@
+"""Class-level mirror of ``xsdba.adjustment`` for the quantile-mapping family (adjustment.py:414-742).
+
+``Cls.train(ref, hist, ...) -> obj`` and ``obj.adjust(sim, ...)`` keep the reference's argument names
+and defaults; ``obj.ds`` holds the trained ``af`` / ``hist_q`` (/ ``scaling``) like the reference's
+trained Dataset, so an object can also be rebuilt from saved tables with ``from_dataset``.
+Arrays are ``(time, *points)`` (time_axis=0) or ``(*points, time)`` (time_axis=-1); a
+:class:`~xsdba_b200.calendar.TimeAxis` plays the role of the xarray time coordinate.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _adjustment as L4
+from . import _lib
+from .base import parse_group
+from .utils import equally_spaced_nodes
+
+
+class _TrainAdjust:
+    _train_fn = None
+
+    def __init__(self, ds, group, kind):
+        self.ds, self.group, self.kind = ds, group, kind
+
+    @classmethod
+    def from_dataset(cls, ds, *, group, kind):
+        """Rebuild a trained object from tables it did not train (base.py:80-91)."""
+        return cls(ds, parse_group(group), kind)
+
+    @classmethod
+    def train(cls, ref, hist, *, time, nquantiles=20, kind="+", group="time", window=1, time_axis=0, **kw):
+        group = parse_group(group, window)
+        if np.isscalar(nquantiles):
+            dtype = getattr(ref, "dtype", np.float32)
+            npdt = np.float64 if "64" in str(dtype) else np.float32
+            quantiles = equally_spaced_nodes(int(nquantiles)).astype(npdt)  # adjustment.py:480-483 (no end points)
+        else:
+            quantiles = np.asarray(nquantiles)
+        ds = cls._train_fn(L4.Dataset({"ref": ref, "hist": hist}, time=time, time_axis=time_axis), group=group,
+                           kind=kind, quantiles=quantiles, **kw)
+        return cls(ds, group, kind)
+
+
+class EmpiricalQuantileMapping(_TrainAdjust):
+    """adjustment.py:414-528."""
+    _train_fn = staticmethod(L4.eqm_train)
+
+    def adjust(self, sim, *, time, interp="nearest", extrapolation="constant", time_axis=0):
+        ds = L4.Dataset({"sim": sim, "af": self.ds["af"], "hist_q": self.ds["hist_q"]}, time=time, time_axis=time_axis)
+        return L4.qm_adjust(ds, group=self.group, interp=interp, extrapolation=extrapolation, kind=self.kind)["scen"]
+
+
+class QuantileDeltaMapping(EmpiricalQuantileMapping):
+    """adjustment.py:674-742 (train is EQM's)."""
+
+    def adjust(self, sim, *, time, interp="nearest", extrapolation="constant", rank_window=None, time_axis=0,
+               extra_output=False):
+        ds = L4.Dataset({"sim": sim, "af": self.ds["af"], "quantiles": self.ds["quantiles"]}, time=time,
+                        time_axis=time_axis)
+        out = L4.qdm_adjust(ds, group=self.group, interp=interp, extrapolation=extrapolation, kind=self.kind,
+                            rank_window=rank_window)
+        return out if extra_output else out["scen"]  # OPTIONS[EXTRA_OUTPUT] (adjustment.py:738)
+
+
+def train_adjust_host(ref: np.ndarray, hist: np.ndarray, sim: np.ndarray, *, time, sim_time, nquantiles=50,
+                      group="time.month", window=1, kind="+", method="eqm", interp="nearest",
+                      extrapolation="constant", slab_points=16384, out=None, return_tables=False):
+    """EQM / QDM train + adjust on HOST (numpy, time-major ``(time, *points)``, float32) arrays through
+    the C ABI's end-to-end entry point: slabs of points are streamed H2D -> kernels -> D2H on two streams.
+    This is the call the xarray-facing Adjustment classes make for in-memory data."""
+    lib = _lib.load()
+    group = parse_group(group, window)
+    for a in (ref, hist, sim):
+        if a.dtype != np.float32 or not a.flags.c_contiguous:
+            raise ValueError("train_adjust_host takes C-contiguous float32 arrays")
+    pshape = ref.shape[1:]
+    n_pts = int(np.prod(pshape)) if pshape else 1
+    if ref.shape[0] != len(time) or hist.shape != ref.shape or sim.shape[0] != len(sim_time) or sim.shape[1:] != pshape:
+        raise ValueError("shape mismatch between ref / hist / sim and their time coordinates")
+    ht = group.handle(time)
+    hs = group.handle(sim_time, with_window=False)
+    q = equally_spaced_nodes(nquantiles).astype(np.float32) if np.isscalar(nquantiles) else np.asarray(nquantiles, np.float32)
+    scen = np.empty_like(sim) if out is None else out
+    af = hq = None
+    if return_tables:
+        af = np.empty(pshape + (ht.n_groups, q.size), np.float32)
+        hq = np.empty_like(af)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    st = lib.xsdba_qm_train_adjust_host_f32(p(ref), p(hist), p(sim), n_pts, ht.ptr, hs.ptr, p(q), q.size,
+                                            _lib.KIND[kind], {"eqm": 0, "qdm": 1}[method], _lib.INTERP[interp],
+                                            _lib.EXTRAP[extrapolation], p(scen), p(af), p(hq), int(slab_points))
+    _lib.check(st, "train_adjust_host")
+    return (scen, af, hq) if return_tables else scen

@@ -8,8 +8,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "xsdba_b200.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "common.cuh"), os.path.join(HERE, "csrc", "sort.cuh"),
-        os.path.join(os.path.dirname(HERE), "include", "xsdba_b200.h")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc")))] + [
+    os.path.join(os.path.dirname(HERE), "include", "xsdba_b200.h")]
 OUT = os.path.join(HERE, "libxsdba_b200.so")
 
 NVCC_FLAGS = [
