@@ -179,3 +179,43 @@ def test_group_quantile_reference_golden(golden):
     a, q, ref = golden["quant_long_in"], golden["quant_long_q"], golden["quant_long_out"]
     t = xs.TimeAxis.daily(1981, 30, "noleap")
     assert bits_equal(_np(xs.group_quantile(a, time=t, group="time", quantiles=q, time_axis=-1))[:, 0, :], ref)
+
+
+@pytest.mark.parametrize("group,window,nq,kind,var", [("time.month", 1, 50, "+", "tas"), ("time.dayofyear", 31, 100, "*", "pr")])
+def test_train_full_size_segments(group, window, nq, kind, var):
+    """30-year daily series: 840-930-slot segments, the shape the register-blocked sorter is built for."""
+    xs = _xs()
+    case = (group, window, "noleap", 30, nq, kind, var, np.float32)
+    tx, to, ref, hist, sim = _make(case, n_pts=33, seed=3)
+    q = o.equally_spaced_nodes(nq).astype(np.float32)
+    gidx, G, _ = o.group_index(to, group)
+    sel = np.arange(G) if G <= 12 else np.array([0, 1, 14, 15, 16, 100, 200, 349, 350, 363, 364])
+    ds = xs.eqm_train(xs.Dataset({"ref": ref, "hist": hist}, time=tx), group=xs.Grouper(group, window), kind=kind,
+                      quantiles=q)
+    af, hq = _np(ds.af), _np(ds.hist_q)
+    for g in sel:  # the oracle's window gather is slow: check a subset of the day-of-year groups
+        ref_q = o.nan_quantile(o.group_segment(ref.T.copy(), gidx, g, window), q)
+        hist_q = o.nan_quantile(o.group_segment(hist.T.copy(), gidx, g, window), q)
+        assert bits_equal(hq[:, g], hist_q), g
+        assert bits_equal(af[:, g], o.get_correction(hist_q, ref_q, kind).astype(np.float32)), g
+
+
+def test_dqm_train_matches_oracle():
+    xs = _xs()
+    for case in [("time.month", 1, "noleap", 5, 50, "+", "tas", np.float32), ("time.dayofyear", 31, "noleap", 4, 50, "*", "pr", np.float32),
+                 ("time", 1, "noleap", 3, 20, "*", "pr", np.float64)]:
+        group, window, cal, years, nq, kind, var, dt = case
+        tx, to, ref, hist, sim = _make(case, n_pts=35)
+        q = o.equally_spaced_nodes(nq).astype(dt)
+        gidx, G, _ = o.group_index(to, group)
+        af_o, hq_o, sc_o = o.dqm_train(ref.T.copy(), hist.T.copy(), gidx, G, window, q, kind)
+        ds = xs.dqm_train(xs.Dataset({"ref": ref, "hist": hist}, time=tx), group=xs.Grouper(group, window), kind=kind,
+                          quantiles=q)
+        # group means are accumulated in a different order than the oracle's (SURVEY.md H6): tolerance, not bits
+        rtol = 2e-6 if dt == np.float32 else 1e-12
+        scale = np.nanmax(np.abs(hq_o[np.isfinite(hq_o)]))
+        np.testing.assert_allclose(_np(ds.scaling), sc_o, rtol=rtol, atol=rtol * scale, equal_nan=True)
+        np.testing.assert_allclose(_np(ds.hist_q), hq_o, rtol=rtol, atol=rtol * scale, equal_nan=True)
+        fin = np.isfinite(af_o)
+        assert (np.isfinite(_np(ds.af)) == fin).all()
+        np.testing.assert_allclose(_np(ds.af)[fin], af_o[fin], rtol=50 * rtol, atol=50 * rtol * scale)

@@ -1,0 +1,153 @@
+// Register-blocked column sorter for the fast train / rank kernels (float32, 32 columns per CTA).
+//
+// Layout: buf[row][32] floats in shared memory, column = lane, so every access of a warp hits 32
+// different banks whatever the rows are (rows are warp-uniform).  The 2^(NB+1) rows are two halves of
+// 2^NB rows; each half is sorted ascending by a bitonic network, and the caller then selects order
+// statistics from the two sorted runs by a merge-path binary search (two_run_pair below) -- this
+// skips the last, most expensive merge phase (NB+1 stages over every element) for the ~100 order
+// statistics the quantile step needs.
+//
+// The network runs in "passes".  In one pass a thread owns the 32 elements of its column whose
+// in-half index differs only in 5 chosen bits S = {s0..s4}: it loads them into registers, applies
+// every consecutive stage of the network whose exchange bit lies in S, and stores them back.  With
+// 1024 threads = 32 warps x 32 lanes a CTA covers 2 halves x 16 blocks x 32 columns per pass, i.e.
+// one block per thread, and the 45 stages of a 512-row half take 7 passes (7 LDS + 7 STS + 45 FMNMX
+// per element instead of 2 LDS + 2 STS + 2 FMNMX per element per stage).
+//
+// Direction of a stage of phase p (merging runs of 2^p) is given by bit p of the element index:
+// if that bit is in S it is a compile-time function of the register index, otherwise it is
+// warp-uniform and selected by one branch per pass (template parameter DESC).  Phase NB is always
+// ascending.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace xsdba {
+
+template <int B0, int B1, int B2, int B3, int B4>
+struct BitSet {
+  static constexpr int b[5] = {B0, B1, B2, B3, B4};
+  static constexpr int mask = (1 << B0) | (1 << B1) | (1 << B2) | (1 << B3) | (1 << B4);
+  // register-index bit that controls element bit `bit`, or -1
+  static __host__ __device__ constexpr int pos(int bit) {
+    return bit == B0 ? 0 : bit == B1 ? 1 : bit == B2 ? 2 : bit == B3 ? 3 : bit == B4 ? 4 : -1;
+  }
+  // element-index offset of register i
+  static __host__ __device__ constexpr int off(int i) {
+    return ((i & 1) << B0) | (((i >> 1) & 1) << B1) | (((i >> 2) & 1) << B2) | (((i >> 3) & 1) << B3) |
+           (((i >> 4) & 1) << B4);
+  }
+  // spread the low bits of v over the element bits NOT in S (ascending), NB bits in total
+  template <int NB>
+  static __device__ __forceinline__ int deposit(int v) {
+    int e = 0, k = 0;
+#pragma unroll
+    for (int bit = 0; bit < NB; ++bit) {
+      if (!((mask >> bit) & 1)) { e |= ((v >> k) & 1) << bit; ++k; }
+    }
+    return e;
+  }
+};
+
+// one stage (phase, exchange bit) on the 32 registers of a thread
+template <class S, bool DESC, int TOP, int PHASE, int BIT>
+__device__ __forceinline__ void sort_stage(float (&r)[32]) {
+  constexpr int pos = S::pos(BIT);
+  constexpr int ppos = S::pos(PHASE);
+  static_assert(pos >= 0, "exchange bit must be in the pass's bit set");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    if (i & (1 << pos)) continue;
+    const int j = i | (1 << pos);
+    const bool desc = (PHASE >= TOP) ? false : (ppos >= 0 ? (((i >> ppos) & 1) != 0) : DESC);
+    const float lo = fminf(r[i], r[j]);
+    const float hi = fmaxf(r[i], r[j]);
+    r[i] = desc ? hi : lo;
+    r[j] = desc ? lo : hi;
+  }
+}
+
+// stage lists are encoded as ints PHASE*16 + BIT
+template <class S, bool DESC, int TOP, int... ST>
+__device__ __forceinline__ void sort_stages(float (&r)[32]) {
+  (sort_stage<S, DESC, TOP, ST / 16, ST % 16>(r), ...);
+}
+
+// One pass.  NB = log2(rows per half); RT_PHASE = the phase whose direction bit is warp-uniform in this
+// pass (-1 if none).  half_rows_base points at buf[half * 2^NB][lane].
+template <class S, int NB, int RT_PHASE, int... ST>
+__device__ __forceinline__ void sort_pass(float* __restrict__ half_col, int block_idx) {
+  const int ebase = S::template deposit<NB>(block_idx);
+  float* p = half_col + ebase * 32;
+  float r[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = p[S::off(i) * 32];
+  bool desc = false;
+  if (RT_PHASE >= 0 && RT_PHASE < NB) desc = ((ebase >> (RT_PHASE < 0 ? 0 : RT_PHASE)) & 1) != 0;
+  if (desc) sort_stages<S, true, NB, ST...>(r);
+  else sort_stages<S, false, NB, ST...>(r);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) p[S::off(i) * 32] = r[i];
+}
+
+#define XS_ST(p, b) ((p) * 16 + (b))
+
+// Sort both 512-row halves of buf[1024][32] ascending.  blockDim.x == 1024; ends with __syncthreads.
+__device__ __forceinline__ void sort_halves_512(float* buf) {
+  constexpr int NB = 9;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* hc = buf + (size_t)(warp >> 4) * (1 << NB) * 32 + lane;
+  const int blk = warp & 15;
+  // pass 1: phases 1..5 on bits {0..4}; phase-5 direction (bit 5) is warp-uniform
+  sort_pass<BitSet<0, 1, 2, 3, 4>, NB, 5,
+            XS_ST(1, 0), XS_ST(2, 1), XS_ST(2, 0), XS_ST(3, 2), XS_ST(3, 1), XS_ST(3, 0), XS_ST(4, 3), XS_ST(4, 2),
+            XS_ST(4, 1), XS_ST(4, 0), XS_ST(5, 4), XS_ST(5, 3), XS_ST(5, 2), XS_ST(5, 1), XS_ST(5, 0)>(hc, blk);
+  __syncthreads();
+  // pass 2: phase 6 bits 5..1 (direction bit 6 warp-uniform)
+  sort_pass<BitSet<1, 2, 3, 4, 5>, NB, 6, XS_ST(6, 5), XS_ST(6, 4), XS_ST(6, 3), XS_ST(6, 2), XS_ST(6, 1)>(hc, blk);
+  __syncthreads();
+  // pass 3: phase 6 bit 0 (direction bit 6 in S), phase 7 bits 6..3 (direction bit 7 warp-uniform)
+  sort_pass<BitSet<0, 3, 4, 5, 6>, NB, 7, XS_ST(6, 0), XS_ST(7, 6), XS_ST(7, 5), XS_ST(7, 4), XS_ST(7, 3)>(hc, blk);
+  __syncthreads();
+  // pass 4: phase 7 bits 2..0 (direction bit 7 in S), phase 8 bits 7,6 (direction bit 8 warp-uniform)
+  sort_pass<BitSet<0, 1, 2, 6, 7>, NB, 8, XS_ST(7, 2), XS_ST(7, 1), XS_ST(7, 0), XS_ST(8, 7), XS_ST(8, 6)>(hc, blk);
+  __syncthreads();
+  // pass 5: phase 8 bits 5..1 (direction bit 8 warp-uniform)
+  sort_pass<BitSet<1, 2, 3, 4, 5>, NB, 8, XS_ST(8, 5), XS_ST(8, 4), XS_ST(8, 3), XS_ST(8, 2), XS_ST(8, 1)>(hc, blk);
+  __syncthreads();
+  // pass 6: phase 8 bit 0 (direction bit 8 in S), phase 9 bits 8..5 (ascending)
+  sort_pass<BitSet<0, 5, 6, 7, 8>, NB, -1, XS_ST(8, 0), XS_ST(9, 8), XS_ST(9, 7), XS_ST(9, 6), XS_ST(9, 5)>(hc, blk);
+  __syncthreads();
+  // pass 7: phase 9 bits 4..0 (ascending)
+  sort_pass<BitSet<0, 1, 2, 3, 4>, NB, -1, XS_ST(9, 4), XS_ST(9, 3), XS_ST(9, 2), XS_ST(9, 1), XS_ST(9, 0)>(hc, blk);
+  __syncthreads();
+}
+
+// Order statistics i and i+1 (0-based) of the union of two ascending runs A[0..nA), B[0..nB) of one
+// column (element k of a run at run[k*32]).  Requires 0 <= i < nA + nB.  v1 = +inf if i+1 == nA+nB.
+__device__ __forceinline__ void two_run_pair(const float* __restrict__ A, int nA, const float* __restrict__ B, int nB,
+                                             int i, float& v0, float& v1) {
+  const int k = i + 1;  // number of elements <= the wanted one
+  int lo = k - nB > 0 ? k - nB : 0;
+  int hi = k < nA ? k : nA;
+  while (lo < hi) {  // smallest a with A[a] >= B[k-a-1]  (a = how many of the k come from A)
+    const int mid = (lo + hi) >> 1;
+    if (A[mid * 32] < B[(k - mid - 1) * 32]) lo = mid + 1; else hi = mid;
+  }
+  const int a = lo, b = k - lo;
+  const float inf = __int_as_float(0x7f800000);
+  const float a_prev = a > 0 ? A[(a - 1) * 32] : -inf;
+  const float b_prev = b > 0 ? B[(b - 1) * 32] : -inf;
+  const float a_next = a < nA ? A[a * 32] : inf;
+  const float b_next = b < nB ? B[b * 32] : inf;
+  v0 = fmaxf(a_prev, b_prev);
+  v1 = fminf(a_next, b_next);
+}
+
+// single order statistic
+__device__ __forceinline__ float two_run_at(const float* A, int nA, const float* B, int nB, int i) {
+  float v0, v1;
+  two_run_pair(A, nA, B, nB, i, v0, v1);
+  return v0;
+}
+
+}  // namespace xsdba

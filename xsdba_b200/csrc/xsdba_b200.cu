@@ -2,10 +2,12 @@
 // See include/xsdba_b200.h for the boundary and DESIGN.md for the kernel inventory.
 #include "../../include/xsdba_b200.h"
 #include "common.cuh"
+#include "sort.cuh"
 
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -174,6 +176,172 @@ train_kernel(const T* __restrict__ ref, const T* __restrict__ hist, long long n_
       }
     }
     __syncthreads();
+  }
+}
+
+// =============================================================================================
+// K1f: fast train / quantile kernel -- float32, time-major (stride_pt == 1), segments <= 1024 slots.
+// grid = (ceil(n_pts/32), n_groups), 1024 threads, one CTA per SM (128 KB sort buffer).  Column = lane
+// = gridpoint: the 128-byte rows of the time-major input land in shared memory as they are, and every
+// later shared-memory access is bank-conflict free.  See sort.cuh for the sorter.
+// =============================================================================================
+constexpr int kFastThreads = 1024;
+constexpr int kFastMaxNq = 128;
+
+struct FastSmem {
+  static constexpr size_t buf = 0;                                  // float [1024][32]
+  static constexpr size_t rows = buf + 1024 * 32 * 4;               // int   [1024]
+  static constexpr size_t pcnt = rows + 1024 * 4;                   // int   [32][32]
+  static constexpr size_t psum = pcnt + 32 * 32 * 4;                // double[32][32]
+  static constexpr size_t cnt = psum + 32 * 32 * 8;                 // int   [2][32]
+  static constexpr size_t mu = cnt + 2 * 32 * 4;                    // float [2][32]  (ref, hist means)
+  static constexpr size_t q = mu + 2 * 32 * 4;                      // float [kFastMaxNq]
+  static constexpr size_t refq = q + kFastMaxNq * 4;                // float [nq][33]
+  static __host__ __device__ constexpr size_t total(int nq) { return refq + (size_t)3 * nq * 33 * 4; }
+};
+
+__global__ void __launch_bounds__(kFastThreads, 1)
+train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist, long long n_pts, long long st,
+                  const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
+                  const float* __restrict__ q, int nq, int kind, int normalize, int mode, float* __restrict__ af,
+                  float* __restrict__ hist_q, float* __restrict__ scaling) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* buf = reinterpret_cast<float*>(smem_raw + FastSmem::buf);
+  int* rows_tab = reinterpret_cast<int*>(smem_raw + FastSmem::rows);
+  int* pcnt = reinterpret_cast<int*>(smem_raw + FastSmem::pcnt);
+  double* psum = reinterpret_cast<double*>(smem_raw + FastSmem::psum);
+  int* cnt = reinterpret_cast<int*>(smem_raw + FastSmem::cnt);
+  float* mu = reinterpret_cast<float*>(smem_raw + FastSmem::mu);
+  float* qs = reinterpret_cast<float*>(smem_raw + FastSmem::q);
+  float* refq = reinterpret_cast<float*>(smem_raw + FastSmem::refq);
+  float* outh = refq + (size_t)nq * 33;
+  float* outa = outh + (size_t)nq * 33;
+
+  const int g = blockIdx.y;
+  const long long n0 = (long long)blockIdx.x * 32;
+  const int S = seg_off[g + 1] - seg_off[g];
+  const long long out_stride = (long long)n_groups * nq;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float fnan = Num<float>::nan(), finf = Num<float>::inf();
+  const int nqp = (nq + 31) & ~31;
+
+  if (S == 0) {  // group without members: NaN rows
+    for (int item = tid; item < 32 * nqp; item += kFastThreads) {
+      const int c = item / nqp, k = item % nqp;
+      if (k >= nq || n0 + c >= n_pts) continue;
+      const long long o = (n0 + c) * out_stride + (long long)g * nq + k;
+      af[o] = fnan;
+      if (mode == 0) hist_q[o] = fnan;
+    }
+    if (mode == 0 && scaling && tid < 32 && n0 + tid < n_pts) scaling[(n0 + tid) * n_groups + g] = fnan;
+    return;
+  }
+  {
+    const int32_t* rows = seg_rows + seg_off[g];
+    rows_tab[tid] = tid < S ? rows[tid] : -1;
+    if (tid < nq) qs[tid] = q[tid];
+  }
+  __syncthreads();
+
+  const bool col_ok = n0 + lane < n_pts;
+  const int half = warp & 1;
+  const int n_pass = mode == 0 ? 2 : 1;
+  for (int pass = 0; pass < n_pass; ++pass) {
+    const float* __restrict__ src = (pass == 0 ? ref : hist) + n0 + lane;
+    // ---- load: warp w takes slots w, w+32, ...; slot s -> half s&1, in-half row s>>1 ------------
+    float v[32];
+    int my_cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int t = rows_tab[warp + 32 * i];
+      v[i] = (t >= 0 && col_ok) ? src[(long long)t * st] : fnan;
+    }
+    double my_sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (v[i] == v[i]) { ++my_cnt; if (normalize) my_sum += (double)v[i]; }
+    }
+    pcnt[warp * 32 + lane] = my_cnt;
+    if (normalize) psum[warp * 32 + lane] = my_sum;
+    __syncthreads();
+    if (tid < 64) {  // (h, c): valid count of each half of each column
+      const int h = tid >> 5;
+      int n = 0;
+#pragma unroll
+      for (int w = 0; w < 16; ++w) n += pcnt[(2 * w + h) * 32 + lane];
+      cnt[h * 32 + lane] = n;
+    }
+    if (normalize && tid >= 64 && tid < 96) {
+      double s = 0.0; int n = 0;
+      for (int w = 0; w < 32; ++w) { s += psum[w * 32 + lane]; n += pcnt[w * 32 + lane]; }
+      mu[pass * 32 + lane] = (float)(s / (double)n);
+    }
+    if (normalize) {
+      __syncthreads();
+      // dqm_train: x + (-mean) or x * (1/mean)   (_adjustment.py:167-168)
+      const float m = mu[pass * 32 + lane];
+      const float inv = kind == XSDBA_KIND_ADD ? -m : __fdiv_rn(1.0f, m);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = kind == XSDBA_KIND_ADD ? __fadd_rn(v[i], inv) : __fmul_rn(v[i], inv);
+    }
+    {
+      float* dst = buf + ((size_t)half * 512 + (warp >> 1)) * 32 + lane;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) dst[(size_t)i * 16 * 32] = (v[i] == v[i]) ? v[i] : finf;
+    }
+    __syncthreads();
+    sort_halves_512(buf);
+    // ---- quantiles from the two sorted runs -------------------------------------------------------
+    for (int item = tid; item < nq * 32; item += kFastThreads) {
+      const int k = item >> 5;  // warp-uniform node, lane = column
+      const int nA = cnt[lane], nB = cnt[32 + lane], n = nA + nB;
+      const float* A = buf + lane;
+      const float* B = buf + 512 * 32 + lane;
+      float res = fnan;
+      if (n > 0) {
+        const float amax = nA > 0 ? A[(size_t)(nA - 1) * 32] : -finf;
+        const float bmax = nB > 0 ? B[(size_t)(nB - 1) * 32] : -finf;
+        const float vmax = fmaxf(amax, bmax);
+        const double vi = (double)(n - 1) * (double)qs[k];  // nbutils.py:131
+        float left, right, gamma;
+        if (vi >= (double)(n - 1)) {  // nbutils.py:47-51: position -1 of the full-length sorted row
+          left = right = (n < S) ? fnan : vmax;
+          gamma = (float)(vi + 1.0);
+        } else if (vi < 0.0) {
+          left = right = two_run_at(A, nA, B, nB, 0);
+          gamma = (float)vi;
+        } else {
+          const int i = (int)vi;
+          two_run_pair(A, nA, B, nB, i, left, right);
+          gamma = (float)(vi - (double)i);  // nbutils.py:142
+        }
+        const float diff = right - left;
+        res = gamma >= 0.5f ? __fmaf_rn(-diff, 1.0f - gamma, right) : __fmaf_rn(diff, gamma, left);
+        if (res != res) res = vmax;  // nbutils.py:146
+      }
+      if (mode == 1) {
+        outa[k * 33 + lane] = res;
+      } else if (pass == 0) {
+        refq[k * 33 + lane] = res;
+      } else {
+        const float rq = refq[k * 33 + lane];
+        outh[k * 33 + lane] = res;
+        outa[k * 33 + lane] = kind == XSDBA_KIND_ADD ? __fsub_rn(rq, res) : __fdiv_rn(rq, res);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- contiguous table writes: a warp writes the nq values of one point ---------------------------
+  for (int item = tid; item < 32 * nqp; item += kFastThreads) {
+    const int c = item / nqp, k = item % nqp;
+    if (k >= nq || n0 + c >= n_pts) continue;
+    const long long o = (n0 + c) * out_stride + (long long)g * nq + k;
+    af[o] = outa[k * 33 + c];
+    if (mode == 0) hist_q[o] = outh[k * 33 + c];
+  }
+  if (normalize && mode == 0 && scaling && tid < 32 && n0 + tid < n_pts) {
+    const float mr = mu[tid], mh = mu[32 + tid];  // scaling = get_correction(mu_hist, mu_ref)
+    scaling[(n0 + tid) * n_groups + g] = kind == XSDBA_KIND_ADD ? __fsub_rn(mr, mh) : __fdiv_rn(mr, mh);
   }
 }
 
@@ -397,9 +565,28 @@ int launch_train_c(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64
   return cuda_status(cudaGetLastError());
 }
 
+// float32 / time-major / <= 1024-slot segments take the register-blocked kernel; returns false otherwise
+bool launch_train_fast(const float* ref, const float* hist, int64_t n_pts, int64_t sp, int64_t st,
+                       const xsdba_grouping* grp, const float* q, int nq, int kind, int normalize, int mode, float* af,
+                       float* hq, float* scaling, cudaStream_t s, int* rc) {
+  if (sp != 1 || grp->segments.max_len > 1024 || nq > kFastMaxNq || getenv("XSDBA_B200_NO_FAST")) return false;
+  const size_t smem = FastSmem::total(nq);
+  *rc = set_smem(train_fast_kernel, smem);
+  if (*rc) return true;
+  dim3 grid((unsigned)((n_pts + 31) / 32), (unsigned)grp->n_groups);
+  train_fast_kernel<<<grid, kFastThreads, smem, s>>>(ref, hist, n_pts, st, grp->segments.off, grp->segments.rows,
+                                                     grp->n_groups, q, nq, kind, normalize, mode, af, hq, scaling);
+  ++g_launches;
+  *rc = cuda_status(cudaGetLastError());
+  return true;
+}
+bool launch_train_fast(const double*, const double*, int64_t, int64_t, int64_t, const xsdba_grouping*, const double*,
+                       int, int, int, int, double*, double*, double*, cudaStream_t, int*) { return false; }
+
 template <typename T>
 int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
                  const T* q, int nq, int kind, int normalize, int mode, T* af, T* hq, T* scaling, void* stream) {
+  int fast_rc = 0;
   if (!ref || !grp || !q || !af || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (mode == 0 && (!hist || !hq)) return XSDBA_ERR_INVALID_ARGUMENT;
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
@@ -409,6 +596,8 @@ int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t
   const int n_pad = std::max(2, next_pow2(grp->segments.max_len));
   const int C = pick_cols<T>(n_pad);
   cudaStream_t s = (cudaStream_t)stream;
+  if (launch_train_fast(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, s, &fast_rc))
+    return fast_rc;
 #define XS_CASE(CC) case CC: return launch_train_c<T, CC>(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, n_pad, s)
   switch (C) {
     XS_CASE(32); XS_CASE(16); XS_CASE(8); XS_CASE(4); XS_CASE(2); XS_CASE(1);
