@@ -112,6 +112,7 @@ struct Tables {
   T* clo;
   T* chi;
   int nq;
+  int top;   // largest power of two <= nq (first step of the branch-free searches)
   // global fallbacks for rows further than +-1 (rare): raw tables of this tile's points
   const T* gx;      // hist_q (per point) or q (shared, x_shared = true)
   const T* gy;      // af
@@ -200,17 +201,22 @@ __device__ __forceinline__ void nearest_in_row(const T* xs, const T* ys, int n, 
   if (d2 < best_d2) { best_d2 = d2; best_y = ys[(size_t)ibest * C]; }
 }
 
-// 2-D rule = scipy griddata(method="nearest") on points (hist_q, group coordinate) in raw units
-// + _extrapolate_on_quantiles (utils.py:380-400, 477-513; nbutils.py:392-416).  r is the group of
-// the sample (0-based); rows are the cyclically padded table rows r-1..r+1 (+ global fallback).
+// branch-free searchsorted(side='left') over a compacted column: #nodes < x.  top = tb.top.
 template <typename TX, typename T, int C>
-__device__ T lookup_2d_nearest(const Tables<T, C>& tb, int c, long long pt, int r, TX x, int extrap) {
-  if (is_nan(x)) return Num<T>::nan();
+__device__ __forceinline__ int lower_bound_bf(const T* xs, int n, TX x, int top) {
+  int pos = 0;
+  for (int step = top; step > 0; step >>= 1) {
+    const int p2 = pos + step;
+    if (p2 <= n && (TX)xs[(size_t)(p2 - 1) * C] < x) pos = p2;
+  }
+  return pos;
+}
+
+// Cross-row part of the 2-D nearest rule (rare: only when the in-row nearest node is >= 1 away).
+template <typename TX, typename T, int C>
+__device__ __noinline__ T nearest_cross_rows(const Tables<T, C>& tb, int c, long long pt, int r, TX x, double best_d2,
+                                             T best_y) {
   const int nq = tb.nq;
-  double best_d2 = __longlong_as_double(0x7ff0000000000000LL);
-  T best_y = Num<T>::nan();
-  nearest_in_row<TX, T, C>(tb.xs + (size_t)1 * nq * C + c, tb.ys + (size_t)1 * nq * C + c, tb.nv[1 * C + c], x, 0.0,
-                           best_d2, best_y);
   // padded row coordinate of the sample is r+1 in [1, G]; padded rows exist for 0..G+1
   for (int dist = 1; dist <= tb.G + 1; ++dist) {
     const double dg2 = (double)dist * (double)dist;
@@ -223,7 +229,7 @@ __device__ T lookup_2d_nearest(const Tables<T, C>& tb, int c, long long pt, int 
         nearest_in_row<TX, T, C>(tb.xs + (size_t)slot * nq * C + c, tb.ys + (size_t)slot * nq * C + c,
                                  tb.nv[slot * C + c], x, dg2, best_d2, best_y);
       } else {
-        // rare: scan the raw row in global memory (padded row pr is group (pr-1) mod G)
+        // scan the raw row in global memory (padded row pr is group (pr-1) mod G)
         const int g = (pr - 1 + tb.G) % tb.G;
         const T* gx = tb.x_shared ? tb.gx : tb.gx + pt * tb.pt_stride + (long long)g * nq;
         const T* gy = tb.gy + pt * tb.pt_stride + (long long)g * nq;
@@ -237,12 +243,66 @@ __device__ T lookup_2d_nearest(const Tables<T, C>& tb, int c, long long pt, int 
       }
     }
   }
-  T out = best_y;
-  // _extrapolate_on_quantiles: integer group coordinate -> np.interp returns the row's own bound
-  const double xd = (double)x;
-  if (xd < (double)tb.blo[c]) out = extrap == 0 ? tb.clo[c] : Num<T>::nan();
-  if (xd > (double)tb.bhi[c]) out = extrap == 0 ? tb.chi[c] : Num<T>::nan();
-  return out;
+  return best_y;
+}
+
+// 2-D rule = scipy griddata(method="nearest") on points (hist_q, group coordinate) in raw units
+// + _extrapolate_on_quantiles (utils.py:380-400, 477-513; nbutils.py:392-416), for N samples of the
+// same point and group at once (independent searches interleave).  r is the 0-based group; rows are
+// the cyclically padded table rows r-1..r+1 (+ global fallback).  The extrapolation override of the
+// reference is unconditional, so it is tested first and the search skipped for out-of-range samples
+// (_extrapolate_on_quantiles with an integer group coordinate: np.interp returns the row's own bound).
+template <typename TX, typename T, int C, int N>
+__device__ __forceinline__ void lookup_2d_nearest_n(const Tables<T, C>& tb, int c, long long pt, int r,
+                                                    const TX (&x)[N], T (&out)[N], int extrap) {
+  const int nq = tb.nq;
+  const T* xs = tb.xs + (size_t)1 * nq * C + c;
+  const T* ys = tb.ys + (size_t)1 * nq * C + c;
+  const int n = tb.nv[1 * C + c];
+  const double blo = (double)tb.blo[c], bhi = (double)tb.bhi[c];
+  int pos[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) pos[j] = 0;
+  for (int step = tb.top; step > 0; step >>= 1) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const int p2 = pos[j] + step;
+      if (p2 <= n && (TX)xs[(size_t)(p2 - 1) * C] < x[j]) pos[j] = p2;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const double xd = (double)x[j];
+    T res;
+    if (is_nan(x[j])) {
+      res = Num<T>::nan();
+    } else if (xd < blo) {
+      res = extrap == 0 ? tb.clo[c] : Num<T>::nan();
+    } else if (xd > bhi) {
+      res = extrap == 0 ? tb.chi[c] : Num<T>::nan();
+    } else {
+      const int i = pos[j];
+      double dbest = __longlong_as_double(0x7ff0000000000000LL);
+      T ybest = Num<T>::nan();
+      if (i > 0) { dbest = fabs(xd - (double)xs[(size_t)(i - 1) * C]); ybest = ys[(size_t)(i - 1) * C]; }
+      if (i < n) {
+        const double d = fabs((double)xs[(size_t)i * C] - xd);
+        if (d < dbest) { dbest = d; ybest = ys[(size_t)i * C]; }
+      }
+      res = ybest;
+      if (!(dbest < 1.0))  // a node of a neighbouring row (>= 1 away in the group coordinate) may be nearer
+        res = nearest_cross_rows<TX, T, C>(tb, c, pt, r, x[j], __dmul_rn(dbest, dbest), ybest);
+    }
+    out[j] = res;
+  }
+}
+
+template <typename TX, typename T, int C>
+__device__ __forceinline__ T lookup_2d_nearest(const Tables<T, C>& tb, int c, long long pt, int r, TX x, int extrap) {
+  const TX xa[1] = {x};
+  T o[1];
+  lookup_2d_nearest_n<TX, T, C, 1>(tb, c, pt, r, xa, o, extrap);
+  return o[0];
 }
 
 template <typename T> __device__ __forceinline__ T apply_corr(T x, T f, int kind) {

@@ -347,48 +347,66 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
 
 // =============================================================================================
 // Table staging shared by the adjust kernels: rows r-1, r, r+1 (cyclic) of the tile's tables into
-// shared memory, NaN nodes dropped, bounds / constants of the centre row recorded.
+// shared memory as xs/ys[slot][k][C] (column = point), NaN nodes dropped, bounds / constants of the
+// centre row recorded.  Global reads are contiguous (a point's nq nodes are adjacent in memory); the
+// transposition goes through a small padded staging buffer so that both sides are conflict free.
 // =============================================================================================
 template <typename T, int C>
-__device__ void stage_tables(Tables<T, C>& tb, long long n0, long long n_pts, int r, bool grouped) {
+__device__ void stage_tables(Tables<T, C>& tb, T* stage /*[2][C][nq|1]*/, long long n0, long long n_pts, int r,
+                             bool grouped) {
   const int nq = tb.nq;
-  const int n_slots = grouped ? 3 : 1;
-  // raw copy: lane -> point, so shared-memory writes are conflict free
-  for (int idx = threadIdx.x; idx < n_slots * nq * C; idx += blockDim.x) {
-    const int c = idx % C;
-    const int k = (idx / C) % nq;
-    const int s = idx / (C * nq);
+  const int pitch = nq | 1;
+  T* sx = stage;
+  T* sy = stage + (size_t)C * pitch;
+  for (int s = 0; s < (grouped ? 3 : 1); ++s) {
     const int slot = grouped ? s : 1;
     const int g = grouped ? (r + slot - 1 + tb.G) % tb.G : 0;
-    T xv = Num<T>::nan(), yv = Num<T>::nan();
-    if (n0 + c < n_pts) {
-      const long long o = (n0 + c) * tb.pt_stride + (long long)g * nq + k;
-      xv = tb.x_shared ? tb.gx[k] : tb.gx[o];
-      yv = tb.gy[o];
+    int has_nan = 0;
+    for (int idx = threadIdx.x; idx < C * nq; idx += blockDim.x) {
+      const int c = idx / nq, k = idx - c * nq;
+      T xv = Num<T>::nan(), yv = Num<T>::nan();
+      if (n0 + c < n_pts) {
+        const long long o = (n0 + c) * tb.pt_stride + (long long)g * nq + k;
+        xv = tb.x_shared ? tb.gx[k] : tb.gx[o];
+        yv = tb.gy[o];
+      }
+      has_nan |= (is_nan(xv) || is_nan(yv));
+      sx[c * pitch + k] = xv;
+      sy[c * pitch + k] = yv;
     }
-    tb.xs[((size_t)slot * nq + k) * C + c] = xv;
-    tb.ys[((size_t)slot * nq + k) * C + c] = yv;
-  }
-  __syncthreads();
-  // compaction: one thread per (slot, point)
-  for (int idx = threadIdx.x; idx < n_slots * C; idx += blockDim.x) {
-    const int c = idx % C;
-    const int slot = grouped ? idx / C : 1;
-    T* xs = tb.xs + (size_t)slot * nq * C + c;
-    T* ys = tb.ys + (size_t)slot * nq * C + c;
-    T blo = Num<T>::nan(), bhi = Num<T>::nan(), clo = Num<T>::nan(), chi = Num<T>::nan();
-    bool have_b = false, have_c = false;
-    int w = 0;
-    for (int k = 0; k < nq; ++k) {
-      const T xv = xs[(size_t)k * C], yv = ys[(size_t)k * C];
-      if (!is_nan(xv)) { if (!have_b) { blo = xv; have_b = true; } bhi = xv; }
-      if (!is_nan(yv)) { if (!have_c) { clo = yv; have_c = true; } chi = yv; }
-      if (!is_nan(xv) && !is_nan(yv)) { xs[(size_t)w * C] = xv; ys[(size_t)w * C] = yv; ++w; }
+    has_nan = __syncthreads_or(has_nan);
+    T* xs = tb.xs + (size_t)slot * nq * C;
+    T* ys = tb.ys + (size_t)slot * nq * C;
+    if (!has_nan) {  // common case: plain transposed copy by all threads
+      for (int idx = threadIdx.x; idx < C * nq; idx += blockDim.x) {
+        const int c = idx % C, k = idx / C;
+        xs[(size_t)k * C + c] = sx[c * pitch + k];
+        ys[(size_t)k * C + c] = sy[c * pitch + k];
+      }
+      if (threadIdx.x < C) {
+        const int c = threadIdx.x;
+        tb.nv[slot * C + c] = nq;
+        if (slot == 1) {
+          tb.blo[c] = sx[c * pitch]; tb.bhi[c] = sx[c * pitch + nq - 1];
+          tb.clo[c] = sy[c * pitch]; tb.chi[c] = sy[c * pitch + nq - 1];
+        }
+      }
+    } else if (threadIdx.x < C) {  // compaction: one thread per point
+      const int c = threadIdx.x;
+      T blo = Num<T>::nan(), bhi = Num<T>::nan(), clo = Num<T>::nan(), chi = Num<T>::nan();
+      bool have_b = false, have_c = false;
+      int w = 0;
+      for (int k = 0; k < nq; ++k) {
+        const T xv = sx[c * pitch + k], yv = sy[c * pitch + k];
+        if (!is_nan(xv)) { if (!have_b) { blo = xv; have_b = true; } bhi = xv; }
+        if (!is_nan(yv)) { if (!have_c) { clo = yv; have_c = true; } chi = yv; }
+        if (!is_nan(xv) && !is_nan(yv)) { xs[(size_t)w * C + c] = xv; ys[(size_t)w * C + c] = yv; ++w; }
+      }
+      tb.nv[slot * C + c] = w;
+      if (slot == 1) { tb.blo[c] = blo; tb.bhi[c] = bhi; tb.clo[c] = clo; tb.chi[c] = chi; }
     }
-    tb.nv[slot * C + c] = w;
-    if (slot == 1) { tb.blo[c] = blo; tb.bhi[c] = bhi; tb.clo[c] = clo; tb.chi[c] = chi; }
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 template <typename T, int C>
@@ -402,15 +420,20 @@ __device__ Tables<T, C> carve_tables(unsigned char* base, int nq) {
   tb.clo = tb.bhi + C;
   tb.chi = tb.clo + C;
   tb.nv = reinterpret_cast<int*>(tb.chi + C);
+  int top = 1;
+  while (top * 2 <= nq) top *= 2;
+  tb.top = top;
   return tb;
 }
 template <typename T, int C>
-constexpr size_t tables_bytes(int nq) { return ((size_t)6 * nq * C + 4 * C) * sizeof(T) + 3 * C * sizeof(int); }
+__host__ __device__ constexpr size_t tables_bytes(int nq) { return ((size_t)6 * nq * C + 4 * C) * sizeof(T) + 3 * C * sizeof(int); }
+template <typename T, int C>
+__host__ __device__ constexpr size_t stage_bytes(int nq) { return (size_t)2 * C * (nq | 1) * sizeof(T); }
 
 // =============================================================================================
 // K2: streaming adjust, EQM / DQM flavour.  grid = (ceil(n_pts/32), n_groups); each warp walks the
-// time steps of its group, lane = point: read sim (coalesced for time-major), look the factor up,
-// apply, write scen.
+// time steps of its group four at a time, lane = point: read sim (coalesced for time-major), look
+// the factor up (branch-free binary search in the staged table), apply, write scen.
 // =============================================================================================
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -419,8 +442,10 @@ adjust_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long lon
               const T* __restrict__ af, const T* __restrict__ hist_q, int nq, int interp, int extrap, int kind,
               T* __restrict__ scen) {
   constexpr int C = 32;
+  constexpr int U = 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Tables<T, C> tb = carve_tables<T, C>(smem_raw, nq);
+  T* stage = reinterpret_cast<T*>(smem_raw + ((tables_bytes<T, C>(nq) + 15) & ~(size_t)15));
   tb.gx = hist_q; tb.gy = af; tb.x_shared = false; tb.G = n_groups; tb.pt_stride = (long long)n_groups * nq;
 
   const int g = blockIdx.y;
@@ -428,17 +453,27 @@ adjust_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long lon
   const int m0 = mem_off[g], m1 = mem_off[g + 1];
   if (m0 == m1) return;
   const bool grouped = n_groups > 1;
-  stage_tables<T, C>(tb, n0, n_pts, g, grouped);
+  stage_tables<T, C>(tb, stage, n0, n_pts, g, grouped);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const long long pt = n0 + lane;
   if (pt >= n_pts) return;
-  for (int m = m0 + warp; m < m1; m += n_warps) {
-    const long long o = pt * sp + (long long)mem_rows[m] * st;
-    const T x = sim[o];
-    const T f = grouped ? lookup_2d_nearest<T, T, C>(tb, lane, pt, g, x, extrap)
-                        : lookup_1d<T, T, C>(tb, lane, x, interp, extrap);
-    scen[o] = apply_corr<T>(x, f, kind);
+  const T* __restrict__ src = sim + pt * sp;
+  T* __restrict__ dst = scen + pt * sp;
+  for (int m = m0 + warp * U; m < m1; m += n_warps * U) {
+    long long o[U];
+    T x[U], f[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) o[j] = (long long)mem_rows[min(m + j, m1 - 1)] * st;
+#pragma unroll
+    for (int j = 0; j < U; ++j) x[j] = src[o[j]];
+    if (grouped) lookup_2d_nearest_n<T, T, C, U>(tb, lane, pt, g, x, f, extrap);
+    else {
+#pragma unroll
+      for (int j = 0; j < U; ++j) f[j] = lookup_1d<T, T, C>(tb, lane, x[j], interp, extrap);
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) if (m + j < m1) dst[o[j]] = apply_corr<T>(x[j], f[j], kind);
   }
 }
 
@@ -463,6 +498,7 @@ rank_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long 
   unsigned char* p = smem_raw + C * 28 + ((C * 28) % 8 ? 4 : 0);
   T* sm = reinterpret_cast<T*>(p);                         // [n_pad][C]
   Tables<T, C> tb = carve_tables<T, C>(p + (size_t)n_pad * C * sizeof(T), nq);
+  T* stage = reinterpret_cast<T*>(p + (size_t)n_pad * C * sizeof(T) + ((tables_bytes<T, C>(nq) + 15) & ~(size_t)15));
 
   const int g = blockIdx.y;
   const long long n0 = (long long)blockIdx.x * C;
@@ -478,7 +514,7 @@ rank_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long 
   sort_columns<T, C>(sm, n_pad);
   if (do_adjust) {
     tb.gx = q; tb.gy = af; tb.x_shared = true; tb.G = n_groups; tb.pt_stride = (long long)n_groups * nq;
-    stage_tables<T, C>(tb, n0, n_pts, g, grouped);
+    stage_tables<T, C>(tb, stage, n0, n_pts, g, grouped);
   }
   if (threadIdx.x < C) {
     const int c = threadIdx.x, n = cnt[c];
@@ -616,7 +652,7 @@ int launch_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsd
   if (grp->n_groups > 1 && interp != XSDBA_INTERP_NEAREST) return XSDBA_ERR_UNSUPPORTED;
   if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
   if (n_pts == 0) return XSDBA_OK;
-  const size_t smem = tables_bytes<T, 32>(nq);
+  const size_t smem = ((tables_bytes<T, 32>(nq) + 15) & ~(size_t)15) + stage_bytes<T, 32>(nq);
   if (smem > 200 * 1024) return XSDBA_ERR_UNSUPPORTED;
   auto kern = adjust_kernel<T>;
   int rc = set_smem(kern, smem);
@@ -633,7 +669,8 @@ int launch_rank_c(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsd
                   const DevTable& seg, const T* af, const T* q, int nq, int interp, int extrap, int kind,
                   int do_adjust, T* scen, double* sim_q, int n_pad, cudaStream_t s) {
   const size_t head = (size_t)C * 28 + (((size_t)C * 28) % 8 ? 4 : 0);
-  const size_t smem = head + (size_t)n_pad * C * sizeof(T) + tables_bytes<T, C>(do_adjust ? nq : 0);
+  const size_t smem = head + (size_t)n_pad * C * sizeof(T) +
+                      (do_adjust ? ((tables_bytes<T, C>(nq) + 15) & ~(size_t)15) + stage_bytes<T, C>(nq) : tables_bytes<T, C>(0));
   if (smem > 220 * 1024) return XSDBA_ERR_SEGMENT_TOO_LONG;
   auto kern = rank_kernel<T, C>;
   int rc = set_smem(kern, smem);
