@@ -478,6 +478,88 @@ adjust_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long lon
 }
 
 // =============================================================================================
+// K2f: lean adjust kernel for the headline case -- float32, grouped (month / dayofyear) 2-D nearest
+// rule.  Same staging as K2; the per-sample work is branch-free float32: 6-step binary search on the
+// staged centre row, nearest of the two bracketing nodes, extrapolation override.  A sample goes to
+// the exact float64 / cross-row routine (lookup_2d_nearest_n) only when float32 cannot decide:
+// the two candidate distances agree to ~1e-5 relative (possible tie), the nearest in-row node is
+// >= ~1 away (a neighbouring row may win), or the sample is NaN.
+// =============================================================================================
+__global__ void __launch_bounds__(kThreads)
+adjust_fast_kernel(const float* __restrict__ sim, long long n_pts, long long sp, long long st,
+                   const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows, int n_groups,
+                   const float* __restrict__ af, const float* __restrict__ hist_q, int nq, int extrap, int kind,
+                   float* __restrict__ scen) {
+  constexpr int C = 32;
+  constexpr int U = 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Tables<float, C> tb = carve_tables<float, C>(smem_raw, nq);
+  float* stage = reinterpret_cast<float*>(smem_raw + ((tables_bytes<float, C>(nq) + 15) & ~(size_t)15));
+  tb.gx = hist_q; tb.gy = af; tb.x_shared = false; tb.G = n_groups; tb.pt_stride = (long long)n_groups * nq;
+
+  const int g = blockIdx.y;
+  const long long n0 = (long long)blockIdx.x * C;
+  const int m0 = mem_off[g], m1 = mem_off[g + 1];
+  if (m0 == m1) return;
+  stage_tables<float, C>(tb, stage, n0, n_pts, g, true);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const long long pt = n0 + lane;
+  if (pt >= n_pts) return;
+  const float* __restrict__ src = sim + pt * sp;
+  float* __restrict__ dst = scen + pt * sp;
+  // centre row of this lane's point, as shared-memory pointers (column = lane)
+  const float* xs = reinterpret_cast<const float*>(smem_raw) + (size_t)1 * nq * C + lane;
+  const float* ys = xs + (size_t)3 * nq * C;
+  const int n = tb.nv[C + lane];
+  const float blo = tb.blo[lane], bhi = tb.bhi[lane];
+  const float fnan = Num<float>::nan(), finf = Num<float>::inf();
+  const float clo = extrap == 0 ? tb.clo[lane] : fnan, chi = extrap == 0 ? tb.chi[lane] : fnan;
+  const int top = tb.top;
+
+  for (int m = m0 + warp * U; m < m1; m += n_warps * U) {
+    long long o[U];
+    float x[U];
+    int pos[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) o[j] = (long long)mem_rows[min(m + j, m1 - 1)] * st;
+#pragma unroll
+    for (int j = 0; j < U; ++j) { x[j] = src[o[j]]; pos[j] = 0; }
+    for (int step = top; step > 0; step >>= 1) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int p2 = pos[j] + step;
+        const float v = xs[(size_t)(p2 - 1) * C];  // p2-1 < 2*top-1 <= 2*nq: inside the staged tables
+        if (p2 <= n && v < x[j]) pos[j] = p2;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int i = pos[j];
+      const int il = i > 0 ? i - 1 : 0, ih = i < n ? i : (n > 0 ? n - 1 : 0);
+      const float xl = xs[(size_t)il * C], xh = xs[(size_t)ih * C];
+      const float yl = ys[(size_t)il * C], yh = ys[(size_t)ih * C];
+      const float dl = i > 0 ? x[j] - xl : finf;
+      const float dh = i < n ? xh - x[j] : finf;
+      const float dmin = fminf(dl, dh);
+      float f = dh < dl ? yh : yl;
+      const bool below = x[j] < blo, above = x[j] > bhi;
+      // float32 is decisive unless: near-tie, far node (cross-row candidates), NaN sample / empty row
+      const bool sure = (fabsf(dl - dh) > 1e-5f * dmin) && (dmin < 0.99f);
+      if (below) f = clo;
+      if (above) f = chi;
+      if (!(sure || below || above)) {
+        const float xa[1] = {x[j]};
+        float fo[1];
+        lookup_2d_nearest_n<float, float, C, 1>(tb, lane, pt, g, xa, fo, extrap);
+        f = fo[0];
+      }
+      if (m + j < m1) dst[o[j]] = kind == XSDBA_KIND_ADD ? __fadd_rn(x[j], f) : __fmul_rn(x[j], f);
+    }
+  }
+}
+
+// =============================================================================================
 // K3: per-group percentile ranks (+ QDM factor lookup).  grid = (ceil(n_pts / C), n_groups).
 // The segment (exact members, or members x window when rank_window) of C points is sorted in shared
 // memory; every member then finds its average-tie rank by two binary searches in its sorted column.
@@ -642,6 +724,19 @@ int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t
 #undef XS_CASE
 }
 
+bool launch_adjust_fast(const float* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
+                        const float* af, const float* hq, int nq, int interp, int extrap, int kind, float* scen,
+                        size_t smem, dim3 grid, cudaStream_t s) {
+  if (grp->n_groups <= 1 || interp != XSDBA_INTERP_NEAREST || getenv("XSDBA_B200_NO_FAST")) return false;
+  if (set_smem(adjust_fast_kernel, smem)) return false;
+  adjust_fast_kernel<<<grid, kThreads, smem, s>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows,
+                                                  grp->n_groups, af, hq, nq, extrap, kind, scen);
+  ++g_launches;
+  return true;
+}
+bool launch_adjust_fast(const double*, int64_t, int64_t, int64_t, const xsdba_grouping*, const double*, const double*,
+                        int, int, int, int, double*, size_t, dim3, cudaStream_t) { return false; }
+
 template <typename T>
 int launch_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* af,
                   const T* hq, int nq, int interp, int extrap, int kind, T* scen, void* stream) {
@@ -654,10 +749,12 @@ int launch_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsd
   if (n_pts == 0) return XSDBA_OK;
   const size_t smem = ((tables_bytes<T, 32>(nq) + 15) & ~(size_t)15) + stage_bytes<T, 32>(nq);
   if (smem > 200 * 1024) return XSDBA_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)((n_pts + 31) / 32), (unsigned)grp->n_groups);
+  if (launch_adjust_fast(sim, n_pts, sp, st, grp, af, hq, nq, interp, extrap, kind, scen, smem, grid, (cudaStream_t)stream))
+    return cuda_status(cudaGetLastError());
   auto kern = adjust_kernel<T>;
   int rc = set_smem(kern, smem);
   if (rc) return rc;
-  dim3 grid((unsigned)((n_pts + 31) / 32), (unsigned)grp->n_groups);
   kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows,
                                                        grp->n_groups, af, hq, nq, interp, extrap, kind, scen);
   ++g_launches;
