@@ -159,6 +159,11 @@ int xsdba_qm_train_adjust_host_f32(const float* ref_host, const float* hist_host
                                    float* scen_host, float* af_host, float* hist_q_host,
                                    int64_t slab_pts);
 
+/* Microbenchmark only (profiles/microbench_rows.py): copy every group's member rows with the tiling
+ * of the adjust kernel, v in {1,2,4} floats per lane.  Not part of the reference-facing surface. */
+int xsdba_debug_copy_rows_f32(const float* src_dev, int64_t n_pts, int64_t stride_time,
+                              const xsdba_grouping_t* grp, float* dst_dev, int32_t v, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

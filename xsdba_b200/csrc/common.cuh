@@ -113,6 +113,7 @@ struct Tables {
   T* chi;
   int nq;
   int top;   // largest power of two <= nq (first step of the branch-free searches)
+  int ld;    // rows per slot = 2*top >= nq+1; rows [nv, ld) of xs hold +inf so searches need no bound check
   // global fallbacks for rows further than +-1 (rare): raw tables of this tile's points
   const T* gx;      // hist_q (per point) or q (shared, x_shared = true)
   const T* gy;      // af
@@ -138,8 +139,8 @@ __device__ T lookup_1d(const Tables<T, C>& tb, int c, TX x, int interp, int extr
   if (is_nan(x)) return Num<T>::nan();
   const int n = tb.nv[1 * C + c];
   if (n == 0) return Num<T>::nan();
-  const T* xs = tb.xs + (size_t)1 * tb.nq * C + c;
-  const T* ys = tb.ys + (size_t)1 * tb.nq * C + c;
+  const T* xs = tb.xs + (size_t)1 * tb.ld * C + c;
+  const T* ys = tb.ys + (size_t)1 * tb.ld * C + c;
   // _check_bounds / fill_value (scipy _interpolate.py: interp1d._evaluate)
   if (x < (TX)xs[0]) return extrap == 0 ? tb.clo[c] : Num<T>::nan();
   if (x > (TX)xs[(size_t)(n - 1) * C]) return extrap == 0 ? tb.chi[c] : Num<T>::nan();
@@ -226,7 +227,7 @@ __device__ __noinline__ T nearest_cross_rows(const Tables<T, C>& tb, int c, long
       if (pr < 0 || pr > tb.G + 1) continue;
       if (dist == 1) {
         const int slot = 1 + sgn;
-        nearest_in_row<TX, T, C>(tb.xs + (size_t)slot * nq * C + c, tb.ys + (size_t)slot * nq * C + c,
+        nearest_in_row<TX, T, C>(tb.xs + (size_t)slot * tb.ld * C + c, tb.ys + (size_t)slot * tb.ld * C + c,
                                  tb.nv[slot * C + c], x, dg2, best_d2, best_y);
       } else {
         // scan the raw row in global memory (padded row pr is group (pr-1) mod G)
@@ -256,8 +257,8 @@ template <typename TX, typename T, int C, int N>
 __device__ __forceinline__ void lookup_2d_nearest_n(const Tables<T, C>& tb, int c, long long pt, int r,
                                                     const TX (&x)[N], T (&out)[N], int extrap) {
   const int nq = tb.nq;
-  const T* xs = tb.xs + (size_t)1 * nq * C + c;
-  const T* ys = tb.ys + (size_t)1 * nq * C + c;
+  const T* xs = tb.xs + (size_t)1 * tb.ld * C + c;
+  const T* ys = tb.ys + (size_t)1 * tb.ld * C + c;
   const int n = tb.nv[1 * C + c];
   const double blo = (double)tb.blo[c], bhi = (double)tb.bhi[c];
   int pos[N];
@@ -267,7 +268,7 @@ __device__ __forceinline__ void lookup_2d_nearest_n(const Tables<T, C>& tb, int 
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       const int p2 = pos[j] + step;
-      if (p2 <= n && (TX)xs[(size_t)(p2 - 1) * C] < x[j]) pos[j] = p2;
+      if ((TX)xs[(size_t)(p2 - 1) * C] < x[j]) pos[j] = p2;  // rows >= n hold +inf
     }
   }
 #pragma unroll

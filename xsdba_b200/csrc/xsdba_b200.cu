@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 using namespace xsdba;
@@ -375,13 +376,13 @@ __device__ void stage_tables(Tables<T, C>& tb, T* stage /*[2][C][nq|1]*/, long l
       sy[c * pitch + k] = yv;
     }
     has_nan = __syncthreads_or(has_nan);
-    T* xs = tb.xs + (size_t)slot * nq * C;
-    T* ys = tb.ys + (size_t)slot * nq * C;
-    if (!has_nan) {  // common case: plain transposed copy by all threads
-      for (int idx = threadIdx.x; idx < C * nq; idx += blockDim.x) {
+    T* xs = tb.xs + (size_t)slot * tb.ld * C;
+    T* ys = tb.ys + (size_t)slot * tb.ld * C;
+    if (!has_nan) {  // common case: plain transposed copy by all threads (+inf padding rows)
+      for (int idx = threadIdx.x; idx < C * tb.ld; idx += blockDim.x) {
         const int c = idx % C, k = idx / C;
-        xs[(size_t)k * C + c] = sx[c * pitch + k];
-        ys[(size_t)k * C + c] = sy[c * pitch + k];
+        xs[(size_t)k * C + c] = k < nq ? sx[c * pitch + k] : Num<T>::inf();
+        if (k < nq) ys[(size_t)k * C + c] = sy[c * pitch + k];
       }
       if (threadIdx.x < C) {
         const int c = threadIdx.x;
@@ -402,6 +403,7 @@ __device__ void stage_tables(Tables<T, C>& tb, T* stage /*[2][C][nq|1]*/, long l
         if (!is_nan(yv)) { if (!have_c) { clo = yv; have_c = true; } chi = yv; }
         if (!is_nan(xv) && !is_nan(yv)) { xs[(size_t)w * C + c] = xv; ys[(size_t)w * C + c] = yv; ++w; }
       }
+      for (int k = w; k < tb.ld; ++k) xs[(size_t)k * C + c] = Num<T>::inf();
       tb.nv[slot * C + c] = w;
       if (slot == 1) { tb.blo[c] = blo; tb.bhi[c] = bhi; tb.clo[c] = clo; tb.chi[c] = chi; }
     }
@@ -413,20 +415,25 @@ template <typename T, int C>
 __device__ Tables<T, C> carve_tables(unsigned char* base, int nq) {
   Tables<T, C> tb;
   tb.nq = nq;
+  int top = 1;
+  while (top * 2 <= nq) top *= 2;
+  tb.top = top;
+  tb.ld = 2 * top;
   tb.xs = reinterpret_cast<T*>(base);
-  tb.ys = tb.xs + (size_t)3 * nq * C;
-  tb.blo = tb.ys + (size_t)3 * nq * C;
+  tb.ys = tb.xs + (size_t)3 * tb.ld * C;
+  tb.blo = tb.ys + (size_t)3 * tb.ld * C;
   tb.bhi = tb.blo + C;
   tb.clo = tb.bhi + C;
   tb.chi = tb.clo + C;
   tb.nv = reinterpret_cast<int*>(tb.chi + C);
-  int top = 1;
-  while (top * 2 <= nq) top *= 2;
-  tb.top = top;
   return tb;
 }
 template <typename T, int C>
-__host__ __device__ constexpr size_t tables_bytes(int nq) { return ((size_t)6 * nq * C + 4 * C) * sizeof(T) + 3 * C * sizeof(int); }
+__host__ __device__ constexpr size_t tables_bytes(int nq) {
+  int top = 1;
+  while (top * 2 <= nq) top *= 2;
+  return ((size_t)6 * (nq > 0 ? 2 * top : 0) * C + 4 * C) * sizeof(T) + 3 * C * sizeof(int);
+}
 template <typename T, int C>
 __host__ __device__ constexpr size_t stage_bytes(int nq) { return (size_t)2 * C * (nq | 1) * sizeof(T); }
 
@@ -485,76 +492,90 @@ adjust_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long lon
 // the two candidate distances agree to ~1e-5 relative (possible tie), the nearest in-row node is
 // >= ~1 away (a neighbouring row may win), or the sample is NaN.
 // =============================================================================================
-__global__ void __launch_bounds__(kThreads)
+constexpr int kAdjMaxRows = 2048;  // member rows of one group kept in shared memory by K2f
+
+template <int TOP>
+__global__ void __launch_bounds__(kThreads, 3)
 adjust_fast_kernel(const float* __restrict__ sim, long long n_pts, long long sp, long long st,
                    const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows, int n_groups,
                    const float* __restrict__ af, const float* __restrict__ hist_q, int nq, int extrap, int kind,
                    float* __restrict__ scen) {
   constexpr int C = 32;
-  constexpr int U = 4;
+  constexpr int U = 8;         // rows per batch; two batches in flight per warp (software pipeline)
+  constexpr int LD = 2 * TOP;  // rows per staged slot (tb.ld)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Tables<float, C> tb = carve_tables<float, C>(smem_raw, nq);
   float* stage = reinterpret_cast<float*>(smem_raw + ((tables_bytes<float, C>(nq) + 15) & ~(size_t)15));
+  int* rows_sm = reinterpret_cast<int*>(stage + 2 * C * (nq | 1));
   tb.gx = hist_q; tb.gy = af; tb.x_shared = false; tb.G = n_groups; tb.pt_stride = (long long)n_groups * nq;
 
   const int g = blockIdx.y;
   const long long n0 = (long long)blockIdx.x * C;
-  const int m0 = mem_off[g], m1 = mem_off[g + 1];
-  if (m0 == m1) return;
-  stage_tables<float, C>(tb, stage, n0, n_pts, g, true);
+  const int m0 = mem_off[g], n_rows = mem_off[g + 1] - m0;
+  if (n_rows == 0) return;
+  for (int i = threadIdx.x; i < n_rows; i += blockDim.x) rows_sm[i] = mem_rows[m0 + i];
+  stage_tables<float, C>(tb, stage, n0, n_pts, g, true);  // (syncs)
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const long long pt = n0 + lane;
   if (pt >= n_pts) return;
   const float* __restrict__ src = sim + pt * sp;
   float* __restrict__ dst = scen + pt * sp;
-  // centre row of this lane's point, as shared-memory pointers (column = lane)
-  const float* xs = reinterpret_cast<const float*>(smem_raw) + (size_t)1 * nq * C + lane;
-  const float* ys = xs + (size_t)3 * nq * C;
+  // centre row of this lane's point (column = lane); rows [n, LD) of xs hold +inf
+  const float* xs = reinterpret_cast<const float*>(smem_raw) + (size_t)LD * C + lane;
+  const float* ys = xs + (size_t)3 * LD * C;
   const int n = tb.nv[C + lane];
   const float blo = tb.blo[lane], bhi = tb.bhi[lane];
   const float fnan = Num<float>::nan(), finf = Num<float>::inf();
   const float clo = extrap == 0 ? tb.clo[lane] : fnan, chi = extrap == 0 ? tb.chi[lane] : fnan;
-  const int top = tb.top;
 
-  for (int m = m0 + warp * U; m < m1; m += n_warps * U) {
-    long long o[U];
+  float xn[U];
+  int m = warp * U;
+  if (m < n_rows) {
+#pragma unroll
+    for (int j = 0; j < U; ++j) xn[j] = src[(long long)rows_sm[min(m + j, n_rows - 1)] * st];
+  }
+  for (; m < n_rows; m += n_warps * U) {
     float x[U];
     int pos[U];
 #pragma unroll
-    for (int j = 0; j < U; ++j) o[j] = (long long)mem_rows[min(m + j, m1 - 1)] * st;
+    for (int j = 0; j < U; ++j) { x[j] = xn[j]; pos[j] = 0; }
+    const int mn = m + n_warps * U;  // prefetch the next batch before working on this one
+    if (mn < n_rows) {
 #pragma unroll
-    for (int j = 0; j < U; ++j) { x[j] = src[o[j]]; pos[j] = 0; }
-    for (int step = top; step > 0; step >>= 1) {
+      for (int j = 0; j < U; ++j) xn[j] = src[(long long)rows_sm[min(mn + j, n_rows - 1)] * st];
+    }
+#pragma unroll
+    for (int step = TOP; step > 0; step >>= 1) {
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        const int p2 = pos[j] + step;
-        const float v = xs[(size_t)(p2 - 1) * C];  // p2-1 < 2*top-1 <= 2*nq: inside the staged tables
-        if (p2 <= n && v < x[j]) pos[j] = p2;
+        const float v = xs[(size_t)(pos[j] + step - 1) * C];
+        pos[j] = v < x[j] ? pos[j] + step : pos[j];
       }
     }
 #pragma unroll
     for (int j = 0; j < U; ++j) {
-      const int i = pos[j];
-      const int il = i > 0 ? i - 1 : 0, ih = i < n ? i : (n > 0 ? n - 1 : 0);
-      const float xl = xs[(size_t)il * C], xh = xs[(size_t)ih * C];
-      const float yl = ys[(size_t)il * C], yh = ys[(size_t)ih * C];
+      const int i = pos[j];  // #nodes < x  (<= n)
+      const int il = i > 0 ? i - 1 : 0;
+      const float xl = xs[(size_t)il * C], xh = xs[(size_t)i * C];   // xs[n] = +inf
+      const float yl = ys[(size_t)il * C], yh = ys[(size_t)(i < n ? i : il) * C];
       const float dl = i > 0 ? x[j] - xl : finf;
-      const float dh = i < n ? xh - x[j] : finf;
+      const float dh = xh - x[j];
       const float dmin = fminf(dl, dh);
       float f = dh < dl ? yh : yl;
       const bool below = x[j] < blo, above = x[j] > bhi;
       // float32 is decisive unless: near-tie, far node (cross-row candidates), NaN sample / empty row
       const bool sure = (fabsf(dl - dh) > 1e-5f * dmin) && (dmin < 0.99f);
-      if (below) f = clo;
-      if (above) f = chi;
+      f = below ? clo : f;
+      f = above ? chi : f;
       if (!(sure || below || above)) {
         const float xa[1] = {x[j]};
         float fo[1];
         lookup_2d_nearest_n<float, float, C, 1>(tb, lane, pt, g, xa, fo, extrap);
         f = fo[0];
       }
-      if (m + j < m1) dst[o[j]] = kind == XSDBA_KIND_ADD ? __fadd_rn(x[j], f) : __fmul_rn(x[j], f);
+      if (m + j < n_rows)
+        dst[(long long)rows_sm[m + j] * st] = kind == XSDBA_KIND_ADD ? __fadd_rn(x[j], f) : __fmul_rn(x[j], f);
     }
   }
 }
@@ -645,6 +666,33 @@ rank_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long 
 }
 
 // =============================================================================================
+// Microbenchmark (not on the product path): copy the member rows of every group with the same
+// (point tile x group) decomposition as K2f, V floats per lane (tile = 32*V points, 128*V-byte row
+// pieces).  profiles/ uses it to measure what HBM gives this access pattern.
+// =============================================================================================
+template <int V>
+__global__ void __launch_bounds__(kThreads)
+copy_rows_kernel(const float* __restrict__ src, long long n_pts, long long st, const int32_t* __restrict__ mem_off,
+                 const int32_t* __restrict__ mem_rows, float* __restrict__ dst) {
+  constexpr int U = 8;
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const long long pt = ((long long)blockIdx.x * 32 + lane) * V;
+  const int m0 = mem_off[g], n_rows = mem_off[g + 1] - m0;
+  if (pt >= n_pts) return;
+  typedef typename std::conditional<V == 1, float, typename std::conditional<V == 2, float2, float4>::type>::type vec;
+  for (int m = warp * U; m < n_rows; m += n_warps * U) {
+    vec x[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j)
+      x[j] = *reinterpret_cast<const vec*>(src + (long long)mem_rows[m0 + min(m + j, n_rows - 1)] * st + pt);
+#pragma unroll
+    for (int j = 0; j < U; ++j)
+      if (m + j < n_rows) *reinterpret_cast<vec*>(dst + (long long)mem_rows[m0 + m + j] * st + pt) = x[j];
+  }
+}
+
+// =============================================================================================
 // host side
 // =============================================================================================
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? XSDBA_OK : (int)e; }
@@ -728,9 +776,21 @@ bool launch_adjust_fast(const float* sim, int64_t n_pts, int64_t sp, int64_t st,
                         const float* af, const float* hq, int nq, int interp, int extrap, int kind, float* scen,
                         size_t smem, dim3 grid, cudaStream_t s) {
   if (grp->n_groups <= 1 || interp != XSDBA_INTERP_NEAREST || getenv("XSDBA_B200_NO_FAST")) return false;
-  if (set_smem(adjust_fast_kernel, smem)) return false;
-  adjust_fast_kernel<<<grid, kThreads, smem, s>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows,
-                                                  grp->n_groups, af, hq, nq, extrap, kind, scen);
+  if (grp->members.max_len > kAdjMaxRows) return false;
+  smem += (size_t)grp->members.max_len * sizeof(int);
+  int top = 1;
+  while (top * 2 <= nq) top *= 2;
+#define XS_LAUNCH(TOP)                                                                                          \
+  case TOP:                                                                                                     \
+    if (set_smem(adjust_fast_kernel<TOP>, smem)) return false;                                                  \
+    adjust_fast_kernel<TOP><<<grid, kThreads, smem, s>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows, \
+                                                         grp->n_groups, af, hq, nq, extrap, kind, scen);        \
+    break;
+  switch (top) {
+    XS_LAUNCH(4) XS_LAUNCH(8) XS_LAUNCH(16) XS_LAUNCH(32) XS_LAUNCH(64) XS_LAUNCH(128)
+    default: return false;
+  }
+#undef XS_LAUNCH
   ++g_launches;
   return true;
 }
@@ -951,6 +1011,19 @@ int xsdba_group_rank_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, 
 int xsdba_group_rank_f64(const double* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
                          int32_t rank_window, double* rank, void* stream) {
   return launch_rank<double>(x, n_pts, sp, st, grp, nullptr, nullptr, 0, 0, 0, XSDBA_KIND_ADD, rank_window, 0, nullptr, rank, stream);
+}
+
+// microbenchmark entry (see copy_rows_kernel); time-major float32 only, n_pts % (32*v) == 0 expected
+int xsdba_debug_copy_rows_f32(const float* src, int64_t n_pts, int64_t st, const xsdba_grouping_t* grp, float* dst,
+                              int32_t v, void* stream) {
+  if (!src || !dst || !grp) return XSDBA_ERR_INVALID_ARGUMENT;
+  dim3 grid((unsigned)((n_pts + 32 * v - 1) / (32 * v)), (unsigned)grp->n_groups);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (v == 1) copy_rows_kernel<1><<<grid, kThreads, 0, s>>>(src, n_pts, st, grp->members.off, grp->members.rows, dst);
+  else if (v == 2) copy_rows_kernel<2><<<grid, kThreads, 0, s>>>(src, n_pts, st, grp->members.off, grp->members.rows, dst);
+  else if (v == 4) copy_rows_kernel<4><<<grid, kThreads, 0, s>>>(src, n_pts, st, grp->members.off, grp->members.rows, dst);
+  else return XSDBA_ERR_INVALID_ARGUMENT;
+  return cuda_status(cudaGetLastError());
 }
 
 }  // extern "C"
