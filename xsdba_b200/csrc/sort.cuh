@@ -21,7 +21,13 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#ifndef XS_CE_IMAD
+#define XS_CE_IMAD 1
+#endif
+
 namespace xsdba {
+
+__constant__ unsigned xs_ce_consts[2] = {1u, 0xffffffffu};
 
 template <int B0, int B1, int B2, int B3, int B4>
 struct BitSet {
@@ -50,7 +56,7 @@ struct BitSet {
 
 // one stage (phase, exchange bit) on the 32 registers of a thread
 template <class S, bool DESC, int TOP, int PHASE, int BIT>
-__device__ __forceinline__ void sort_stage(float (&r)[32]) {
+__device__ __forceinline__ void sort_stage(float (&r)[32], unsigned ce_one, unsigned ce_mone) {
   constexpr int pos = S::pos(BIT);
   constexpr int ppos = S::pos(PHASE);
   static_assert(pos >= 0, "exchange bit must be in the pass's bit set");
@@ -60,7 +66,21 @@ __device__ __forceinline__ void sort_stage(float (&r)[32]) {
     const int j = i | (1 << pos);
     const bool desc = (PHASE >= TOP) ? false : (ppos >= 0 ? (((i >> ppos) & 1) != 0) : DESC);
     const float lo = fminf(r[i], r[j]);
-    const float hi = fmaxf(r[i], r[j]);
+    float hi;
+#if XS_CE_IMAD
+    // Pipe balancing (profiles/microbench_ce.cu): FMNMX runs on the half-rate ALU pipe, which bounds the
+    // sorter.  For two CEs out of three the max is rebuilt on the FMA pipe instead: lo is bit-identical
+    // to one of the inputs, so hi = a + b - lo in integer arithmetic is the other one, exactly.  The
+    // multipliers (1, -1) come from constant memory so that ptxas keeps two IMADs (an IADD3 would go
+    // back to the ALU pipe).
+    if ((i + (i >> pos)) % 3 != 0) {
+      unsigned s_, h_;
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(s_) : "r"(__float_as_uint(r[i])), "r"(ce_one), "r"(__float_as_uint(r[j])));
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(h_) : "r"(__float_as_uint(lo)), "r"(ce_mone), "r"(s_));
+      hi = __uint_as_float(h_);
+    } else
+#endif
+    hi = fmaxf(r[i], r[j]);
     r[i] = desc ? hi : lo;
     r[j] = desc ? lo : hi;
   }
@@ -68,8 +88,8 @@ __device__ __forceinline__ void sort_stage(float (&r)[32]) {
 
 // stage lists are encoded as ints PHASE*16 + BIT
 template <class S, bool DESC, int TOP, int... ST>
-__device__ __forceinline__ void sort_stages(float (&r)[32]) {
-  (sort_stage<S, DESC, TOP, ST / 16, ST % 16>(r), ...);
+__device__ __forceinline__ void sort_stages(float (&r)[32], unsigned ce_one, unsigned ce_mone) {
+  (sort_stage<S, DESC, TOP, ST / 16, ST % 16>(r, ce_one, ce_mone), ...);
 }
 
 // One pass.  NB = log2(rows per half); RT_PHASE = the phase whose direction bit is warp-uniform in this
@@ -83,8 +103,9 @@ __device__ __forceinline__ void sort_pass(float* __restrict__ half_col, int bloc
   for (int i = 0; i < 32; ++i) r[i] = p[S::off(i) * 32];
   bool desc = false;
   if (RT_PHASE >= 0 && RT_PHASE < NB) desc = ((ebase >> (RT_PHASE < 0 ? 0 : RT_PHASE)) & 1) != 0;
-  if (desc) sort_stages<S, true, NB, ST...>(r);
-  else sort_stages<S, false, NB, ST...>(r);
+  const unsigned ce_one = xs_ce_consts[0], ce_mone = xs_ce_consts[1];
+  if (desc) sort_stages<S, true, NB, ST...>(r, ce_one, ce_mone);
+  else sort_stages<S, false, NB, ST...>(r, ce_one, ce_mone);
 #pragma unroll
   for (int i = 0; i < 32; ++i) p[S::off(i) * 32] = r[i];
 }
@@ -92,31 +113,38 @@ __device__ __forceinline__ void sort_pass(float* __restrict__ half_col, int bloc
 #define XS_ST(p, b) ((p) * 16 + (b))
 
 // Sort both 512-row halves of buf[1024][32] ascending.  blockDim.x == 1024; ends with __syncthreads.
+__device__ __forceinline__ void half_barrier(int half) {
+  // the two 512-row halves are independent sorts: a named barrier per half (16 warps) lets them drift
+  // apart so that one half's shared-memory phase overlaps the other's FMNMX phase
+  asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "r"(512) : "memory");
+}
+
 __device__ __forceinline__ void sort_halves_512(float* buf) {
   constexpr int NB = 9;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hb = warp >> 4;
   float* hc = buf + (size_t)(warp >> 4) * (1 << NB) * 32 + lane;
   const int blk = warp & 15;
   // pass 1: phases 1..5 on bits {0..4}; phase-5 direction (bit 5) is warp-uniform
   sort_pass<BitSet<0, 1, 2, 3, 4>, NB, 5,
             XS_ST(1, 0), XS_ST(2, 1), XS_ST(2, 0), XS_ST(3, 2), XS_ST(3, 1), XS_ST(3, 0), XS_ST(4, 3), XS_ST(4, 2),
             XS_ST(4, 1), XS_ST(4, 0), XS_ST(5, 4), XS_ST(5, 3), XS_ST(5, 2), XS_ST(5, 1), XS_ST(5, 0)>(hc, blk);
-  __syncthreads();
+  half_barrier(hb);
   // pass 2: phase 6 bits 5..1 (direction bit 6 warp-uniform)
   sort_pass<BitSet<1, 2, 3, 4, 5>, NB, 6, XS_ST(6, 5), XS_ST(6, 4), XS_ST(6, 3), XS_ST(6, 2), XS_ST(6, 1)>(hc, blk);
-  __syncthreads();
+  half_barrier(hb);
   // pass 3: phase 6 bit 0 (direction bit 6 in S), phase 7 bits 6..3 (direction bit 7 warp-uniform)
   sort_pass<BitSet<0, 3, 4, 5, 6>, NB, 7, XS_ST(6, 0), XS_ST(7, 6), XS_ST(7, 5), XS_ST(7, 4), XS_ST(7, 3)>(hc, blk);
-  __syncthreads();
+  half_barrier(hb);
   // pass 4: phase 7 bits 2..0 (direction bit 7 in S), phase 8 bits 7,6 (direction bit 8 warp-uniform)
   sort_pass<BitSet<0, 1, 2, 6, 7>, NB, 8, XS_ST(7, 2), XS_ST(7, 1), XS_ST(7, 0), XS_ST(8, 7), XS_ST(8, 6)>(hc, blk);
-  __syncthreads();
+  half_barrier(hb);
   // pass 5: phase 8 bits 5..1 (direction bit 8 warp-uniform)
   sort_pass<BitSet<1, 2, 3, 4, 5>, NB, 8, XS_ST(8, 5), XS_ST(8, 4), XS_ST(8, 3), XS_ST(8, 2), XS_ST(8, 1)>(hc, blk);
-  __syncthreads();
+  half_barrier(hb);
   // pass 6: phase 8 bit 0 (direction bit 8 in S), phase 9 bits 8..5 (ascending)
   sort_pass<BitSet<0, 5, 6, 7, 8>, NB, -1, XS_ST(8, 0), XS_ST(9, 8), XS_ST(9, 7), XS_ST(9, 6), XS_ST(9, 5)>(hc, blk);
-  __syncthreads();
+  half_barrier(hb);
   // pass 7: phase 9 bits 4..0 (ascending)
   sort_pass<BitSet<0, 1, 2, 3, 4>, NB, -1, XS_ST(9, 4), XS_ST(9, 3), XS_ST(9, 2), XS_ST(9, 1), XS_ST(9, 0)>(hc, blk);
   __syncthreads();
