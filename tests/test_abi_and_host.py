@@ -1,0 +1,108 @@
+"""CPU-side checks (no GPU compute): the C ABI library builds for sm_100a, loads, and exports every
+symbol include/xsdba_b200.h declares; host logic (Grouper / TimeAxis / argument validation) mirrors
+the reference; the product never routes through the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from xsdba_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_header_symbols_are_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "xsdba_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(xsdba_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 18
+    raw = ctypes.CDLL(os.path.join(ROOT, "xsdba_b200", "libxsdba_b200.so"))
+    for n in sorted(names):
+        assert hasattr(raw, n), f"{n} declared in include/xsdba_b200.h but not exported"
+    from xsdba_b200 import _lib
+    assert names == set(_lib.SIGNATURES), names ^ set(_lib.SIGNATURES)
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "xsdba_b200", "libxsdba_b200.so")],
+                         capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_version_and_status_strings(lib):
+    assert lib.xsdba_version() >= 100
+    assert b"invalid" in lib.xsdba_status_string(-1)
+    assert b"segment" in lib.xsdba_status_string(-3)
+
+
+def test_no_device_is_a_loud_error_not_a_fallback(lib):
+    """Without a GPU the grouping handle cannot be created: the product raises, it never computes on CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import xsdba_b200 as xs
+    t = xs.TimeAxis.daily(2000, 2, "noleap")
+    x = np.zeros((len(t), 4), np.float32)
+    with pytest.raises((ValueError, RuntimeError)):
+        xs.eqm_train(xs.Dataset({"ref": x, "hist": x}, time=t), group="time.month", kind="+",
+                     quantiles=xs.equally_spaced_nodes(10))
+
+
+def test_product_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "xsdba_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".inc")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "qm_oracle" not in src and "oracle/" not in src and "import oracle" not in src, f
+
+
+def test_grouper_mirrors_reference_semantics():
+    import qm_oracle as o
+    import xsdba_b200 as xs
+    for cal in ("noleap", "standard", "360_day", "all_leap"):
+        tx = xs.TimeAxis.daily(1999, 3, cal)
+        to = o.daily_time_axis(1999, 3, cal)
+        assert len(tx) == len(to)
+        for group in ("time", "time.month", "time.dayofyear", "time.season"):
+            g = xs.Grouper(group)
+            gi, G, coord = o.group_index(to, group)
+            np.testing.assert_array_equal(g.zero_based_index(tx), gi)
+            assert g.n_groups(tx) == G
+        np.testing.assert_array_equal(xs.Grouper("time.month").get_index(tx, interp=True), o.group_index_interp(to, "time.month"))
+    # reference tests/test_base.py:46-65
+    t = xs.TimeAxis.daily(2000, 2, "noleap")
+    i = np.nonzero((t.year == 2001) & (t.month == 3) & (t.day == 31))[0][0]
+    assert xs.Grouper("time.month").get_index(t)[i] == 3
+    assert xs.Grouper("time.month").get_index(t, interp=True)[i] == 3.5
+    assert xs.Grouper("time.dayofyear").get_index(t)[i] == 90
+    with pytest.raises(ValueError):  # base.py:151-156
+        xs.Grouper("time", window=5)
+    with pytest.raises(NotImplementedError):
+        xs.Grouper("time.month", add_dims=["lon"])
+
+
+def test_time_axis_constructors_agree():
+    import xsdba_b200 as xs
+    a = xs.TimeAxis.daily(1999, 3, "standard")
+    d = np.arange("1999-01-01", "2002-01-01", dtype="datetime64[D]")
+    b = xs.TimeAxis.from_datetime64(d)
+    for f in ("year", "month", "day", "dayofyear", "days_in_month"):
+        np.testing.assert_array_equal(getattr(a, f), getattr(b, f))
+    c = xs.TimeAxis.from_fields(a.year, a.month, a.day, "standard")
+    np.testing.assert_array_equal(c.dayofyear, a.dayofyear)
+
+
+def test_equally_spaced_nodes_matches_reference(golden):
+    import xsdba_b200 as xs
+    assert (xs.equally_spaced_nodes(50) == golden["nodes_50"]).all()
+    assert (xs.equally_spaced_nodes(5, eps=1e-4) == golden["nodes_5_eps"]).all()

@@ -1,6 +1,6 @@
 // Shared device helpers for the xsdba_b200 kernels (sm_100a).
 //
-// Arithmetic notes (these pin bit-parity with the reference, see oracle/qm_oracle.py header):
+// Arithmetic notes (these pin bit-parity with the reference; measured facts are listed in DESIGN.md):
 //  * quantile virtual index  vi = (n-1)*q  rounded once in float64   (nbutils.py:131, LLVM-folded)
 //  * gamma cast to the data type; lerp branches are FMAs             (nbutils.py:101-104, contract)
 //  * SciPy interp1d / numpy.interp / cKDTree arithmetic is NOT contracted: every product / sum is
