@@ -104,10 +104,10 @@ __device__ __forceinline__ T quantile_sorted(const T* col, int n, int S, T qk) {
 // ---------------------------------------------------------------------------------------------
 template <typename T, int C>
 struct Tables {
-  T* xs;     // [3][nq][C]
-  T* ys;     // [3][nq][C]
-  int* nv;   // [3][C]
-  T* blo;    // [C]
+  T* xsl[3];   // per slot (rows g-1, g, g+1): [ld][C] compacted nodes, +inf padded
+  T* ysl[3];   // per slot: [ld][C] factors of the kept nodes
+  int* nvl[3]; // per slot: [C] number of kept nodes
+  T* blo;      // [C] centre row: first / last non-NaN hist_q, first / last non-NaN af
   T* bhi;
   T* clo;
   T* chi;
@@ -137,10 +137,10 @@ __device__ __forceinline__ int lower_bound_col(const T* xs, int n, TX x) {
 template <typename TX, typename T, int C>
 __device__ T lookup_1d(const Tables<T, C>& tb, int c, TX x, int interp, int extrap) {
   if (is_nan(x)) return Num<T>::nan();
-  const int n = tb.nv[1 * C + c];
+  const int n = tb.nvl[1][c];
   if (n == 0) return Num<T>::nan();
-  const T* xs = tb.xs + (size_t)1 * tb.ld * C + c;
-  const T* ys = tb.ys + (size_t)1 * tb.ld * C + c;
+  const T* xs = tb.xsl[1] + c;
+  const T* ys = tb.ysl[1] + c;
   // _check_bounds / fill_value (scipy _interpolate.py: interp1d._evaluate)
   if (x < (TX)xs[0]) return extrap == 0 ? tb.clo[c] : Num<T>::nan();
   if (x > (TX)xs[(size_t)(n - 1) * C]) return extrap == 0 ? tb.chi[c] : Num<T>::nan();
@@ -227,8 +227,8 @@ __device__ __noinline__ T nearest_cross_rows(const Tables<T, C>& tb, int c, long
       if (pr < 0 || pr > tb.G + 1) continue;
       if (dist == 1) {
         const int slot = 1 + sgn;
-        nearest_in_row<TX, T, C>(tb.xs + (size_t)slot * tb.ld * C + c, tb.ys + (size_t)slot * tb.ld * C + c,
-                                 tb.nv[slot * C + c], x, dg2, best_d2, best_y);
+        nearest_in_row<TX, T, C>(tb.xsl[slot] + c, tb.ysl[slot] + c,
+                                 tb.nvl[slot][c], x, dg2, best_d2, best_y);
       } else {
         // scan the raw row in global memory (padded row pr is group (pr-1) mod G)
         const int g = (pr - 1 + tb.G) % tb.G;
@@ -257,9 +257,9 @@ template <typename TX, typename T, int C, int N>
 __device__ __forceinline__ void lookup_2d_nearest_n(const Tables<T, C>& tb, int c, long long pt, int r,
                                                     const TX (&x)[N], T (&out)[N], int extrap) {
   const int nq = tb.nq;
-  const T* xs = tb.xs + (size_t)1 * tb.ld * C + c;
-  const T* ys = tb.ys + (size_t)1 * tb.ld * C + c;
-  const int n = tb.nv[1 * C + c];
+  const T* xs = tb.xsl[1] + c;
+  const T* ys = tb.ysl[1] + c;
+  const int n = tb.nvl[1][c];
   const double blo = (double)tb.blo[c], bhi = (double)tb.bhi[c];
   int pos[N];
 #pragma unroll

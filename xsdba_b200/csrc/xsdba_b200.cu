@@ -376,8 +376,8 @@ __device__ void stage_tables(Tables<T, C>& tb, T* stage /*[2][C][nq|1]*/, long l
       sy[c * pitch + k] = yv;
     }
     has_nan = __syncthreads_or(has_nan);
-    T* xs = tb.xs + (size_t)slot * tb.ld * C;
-    T* ys = tb.ys + (size_t)slot * tb.ld * C;
+    T* xs = tb.xsl[slot];
+    T* ys = tb.ysl[slot];
     if (!has_nan) {  // common case: plain transposed copy by all threads (+inf padding rows)
       for (int idx = threadIdx.x; idx < C * tb.ld; idx += blockDim.x) {
         const int c = idx % C, k = idx / C;
@@ -386,7 +386,7 @@ __device__ void stage_tables(Tables<T, C>& tb, T* stage /*[2][C][nq|1]*/, long l
       }
       if (threadIdx.x < C) {
         const int c = threadIdx.x;
-        tb.nv[slot * C + c] = nq;
+        tb.nvl[slot][c] = nq;
         if (slot == 1) {
           tb.blo[c] = sx[c * pitch]; tb.bhi[c] = sx[c * pitch + nq - 1];
           tb.clo[c] = sy[c * pitch]; tb.chi[c] = sy[c * pitch + nq - 1];
@@ -404,7 +404,7 @@ __device__ void stage_tables(Tables<T, C>& tb, T* stage /*[2][C][nq|1]*/, long l
         if (!is_nan(xv) && !is_nan(yv)) { xs[(size_t)w * C + c] = xv; ys[(size_t)w * C + c] = yv; ++w; }
       }
       for (int k = w; k < tb.ld; ++k) xs[(size_t)k * C + c] = Num<T>::inf();
-      tb.nv[slot * C + c] = w;
+      tb.nvl[slot][c] = w;
       if (slot == 1) { tb.blo[c] = blo; tb.bhi[c] = bhi; tb.clo[c] = clo; tb.chi[c] = chi; }
     }
     __syncthreads();
@@ -419,13 +419,18 @@ __device__ Tables<T, C> carve_tables(unsigned char* base, int nq) {
   while (top * 2 <= nq) top *= 2;
   tb.top = top;
   tb.ld = 2 * top;
-  tb.xs = reinterpret_cast<T*>(base);
-  tb.ys = tb.xs + (size_t)3 * tb.ld * C;
-  tb.blo = tb.ys + (size_t)3 * tb.ld * C;
+  T* xs = reinterpret_cast<T*>(base);
+  T* ys = xs + (size_t)3 * tb.ld * C;
+  tb.blo = ys + (size_t)3 * tb.ld * C;
   tb.bhi = tb.blo + C;
   tb.clo = tb.bhi + C;
   tb.chi = tb.clo + C;
-  tb.nv = reinterpret_cast<int*>(tb.chi + C);
+  int* nv = reinterpret_cast<int*>(tb.chi + C);
+  for (int sl = 0; sl < 3; ++sl) {
+    tb.xsl[sl] = xs + (size_t)sl * tb.ld * C;
+    tb.ysl[sl] = ys + (size_t)sl * tb.ld * C;
+    tb.nvl[sl] = nv + sl * C;
+  }
   return tb;
 }
 template <typename T, int C>
@@ -524,7 +529,7 @@ adjust_fast_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
   // centre row of this lane's point (column = lane); rows [n, LD) of xs hold +inf
   const float* xs = reinterpret_cast<const float*>(smem_raw) + (size_t)LD * C + lane;
   const float* ys = xs + (size_t)3 * LD * C;
-  const int n = tb.nv[C + lane];
+  const int n = tb.nvl[1][lane];
   const float blo = tb.blo[lane], bhi = tb.bhi[lane];
   const float fnan = Num<float>::nan(), finf = Num<float>::inf();
   const float clo = extrap == 0 ? tb.clo[lane] : fnan, chi = extrap == 0 ? tb.chi[lane] : fnan;
@@ -576,6 +581,220 @@ adjust_fast_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
       }
       if (m + j < n_rows)
         dst[(long long)rows_sm[m + j] * st] = kind == XSDBA_KIND_ADD ? __fadd_rn(x[j], f) : __fmul_rn(x[j], f);
+    }
+  }
+}
+
+// =============================================================================================
+// K2p + K2t: packed tables and the tile-persistent adjust kernel (float32, grouped nearest).
+//
+// K2p `pack_tables_kernel` turns the caller's point-major af / hist_q [N][G][nq] into per-(tile, group)
+// slots in the exact shared-memory image the lookup wants: xs[LD][32], ys[LD][32] (column = point, NaN
+// nodes dropped, +inf padding), bounds / constants and node counts.  One slot is one contiguous,
+// 16-byte aligned block, so K2t fetches it with a single bulk async copy (cp.async.bulk -> SASS UBLKCP,
+// completion on an mbarrier) -- no transposition, no per-element staging work in the hot kernel.
+//
+// K2t `adjust_tile_kernel`: one CTA per tile of 32 points walks ALL groups; a ring of four slots holds
+// rows g-1, g, g+1 while row g+2 is in flight, so table traffic is (G+2) slots per tile instead of 3G
+// and the staging latency is hidden behind the previous group's streaming.
+// =============================================================================================
+template <int LD>
+struct PackedSlot {
+  float xs[LD * 32];
+  float ys[LD * 32];
+  float blo[32], bhi[32], clo[32], chi[32];
+  int nv[32];
+};
+
+template <int TOP>
+__global__ void __launch_bounds__(kThreads)
+pack_tables_kernel(const float* __restrict__ af, const float* __restrict__ hist_q, long long n_pts, int n_groups,
+                   int nq, PackedSlot<2 * TOP>* __restrict__ packed) {
+  constexpr int C = 32, LD = 2 * TOP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PackedSlot<LD>* slot = reinterpret_cast<PackedSlot<LD>*>(smem_raw);
+  float* stage = reinterpret_cast<float*>(smem_raw + sizeof(PackedSlot<LD>));
+  Tables<float, C> tb;
+  tb.nq = nq; tb.top = TOP; tb.ld = LD;
+  // one-slot view: stage_tables(grouped = false) fills slot index 1
+  for (int sl = 0; sl < 3; ++sl) { tb.xsl[sl] = slot->xs; tb.ysl[sl] = slot->ys; tb.nvl[sl] = slot->nv; }
+  tb.blo = slot->blo; tb.bhi = slot->bhi; tb.clo = slot->clo; tb.chi = slot->chi;
+  const int g = blockIdx.y;
+  const long long n0 = (long long)blockIdx.x * C;
+  // present group g as the only group of a one-group table
+  tb.gx = hist_q + (long long)g * nq; tb.gy = af + (long long)g * nq; tb.x_shared = false; tb.G = 1;
+  tb.pt_stride = (long long)n_groups * nq;
+  stage_tables<float, C>(tb, stage, n0, n_pts, 0, false);
+  const float4* src = reinterpret_cast<const float4*>(slot);
+  float4* dst = reinterpret_cast<float4*>(packed + ((size_t)blockIdx.x * n_groups + g));
+  for (int i = threadIdx.x; i < (int)(sizeof(PackedSlot<LD>) / 16); i += blockDim.x) dst[i] = src[i];
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// exact (float64 / cross-row) lookup on three ring slots holding rows g-1, g, g+1
+template <int LD>
+__device__ __noinline__ float lookup_exact_slots(const PackedSlot<LD>* const (&s3)[3], Tables<float, 32> tb, int lane,
+                                                 long long pt, int g, float x, int extrap) {
+  for (int sl = 0; sl < 3; ++sl) {
+    tb.xsl[sl] = const_cast<float*>(s3[sl]->xs);
+    tb.ysl[sl] = const_cast<float*>(s3[sl]->ys);
+    tb.nvl[sl] = const_cast<int*>(s3[sl]->nv);
+  }
+  tb.blo = const_cast<float*>(s3[1]->blo); tb.bhi = const_cast<float*>(s3[1]->bhi);
+  tb.clo = const_cast<float*>(s3[1]->clo); tb.chi = const_cast<float*>(s3[1]->chi);
+  return lookup_2d_nearest<float, float, 32>(tb, lane, pt, g, x, extrap);
+}
+
+constexpr int kTileMaxRows = 1024;  // member rows of one group kept in shared memory by K2t (x2 buffers)
+
+template <int TOP>
+__global__ void __launch_bounds__(kThreads, 3)
+adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp, long long st,
+                   const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows, int n_groups,
+                   const float* __restrict__ af, const float* __restrict__ hist_q, int nq,
+                   const PackedSlot<2 * TOP>* __restrict__ packed, int extrap, int kind, float* __restrict__ scen) {
+  constexpr int C = 32, U = 8, LD = 2 * TOP, RING = 4;
+  typedef PackedSlot<LD> Slot;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Slot* ring = reinterpret_cast<Slot*>(smem_raw);
+  int* rows_sm = reinterpret_cast<int*>(smem_raw + RING * sizeof(Slot));     // [2][kTileMaxRows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rows_sm + 2 * kTileMaxRows);  // [RING]
+
+  const int tile = blockIdx.x;
+  const long long n0 = (long long)tile * C;
+  const int G = n_groups;
+  const Slot* my = packed + (size_t)tile * G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const long long pt = n0 + lane;
+  const bool pt_ok = pt < n_pts;
+  const float* __restrict__ src = sim + (pt_ok ? pt : n0) * sp;
+  float* __restrict__ dst = scen + (pt_ok ? pt : n0) * sp;
+  const float fnan = Num<float>::nan(), finf = Num<float>::inf();
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RING; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // extended row e in [-1, G] is group (e+G)%G and lives in ring slot (e+1)%RING
+  auto fetch = [&](int e) {
+    const int s = (e + 1) % RING;
+    mbar_expect_tx(&bars[s], (uint32_t)sizeof(Slot));
+    bulk_g2s(&ring[s], &my[(e + G) % G], (uint32_t)sizeof(Slot), &bars[s]);
+  };
+  if (threadIdx.x == 0) { fetch(-1); fetch(0); fetch(1 <= G ? 1 : 0); }
+  {
+    const int r0 = mem_off[0], nr = mem_off[1] - r0;
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) rows_sm[i] = mem_rows[r0 + i];
+  }
+  // fallback view for the exact routine (rows further than +-1 come from the raw tables)
+  Tables<float, C> tb;
+  tb.nq = nq; tb.top = TOP; tb.ld = LD; tb.gx = hist_q; tb.gy = af; tb.x_shared = false; tb.G = G;
+  tb.pt_stride = (long long)G * nq;
+
+  for (int g = 0; g < G; ++g) {
+    const int m0 = mem_off[g], n_rows = mem_off[g + 1] - m0;
+    const int* rows = rows_sm + (g & 1) * kTileMaxRows;
+    // rows of the next group: loads now, stores at the end of the step
+    int nxt[(kTileMaxRows + kThreads - 1) / kThreads];
+    int n_next = 0, r_next = 0;
+    if (g + 1 < G) { r_next = mem_off[g + 1]; n_next = mem_off[g + 2] - r_next; }
+#pragma unroll
+    for (int i = 0; i < (kTileMaxRows + kThreads - 1) / kThreads; ++i) {
+      const int idx = threadIdx.x + i * kThreads;
+      nxt[i] = idx < n_next ? mem_rows[r_next + idx] : 0;
+    }
+    // slots of rows g-1, g (already waited for in earlier steps except at g == 0) and g+1
+    if (g == 0) { mbar_wait(&bars[0], 0); mbar_wait(&bars[1], 0); }
+    {
+      const int e = g + 1, s = (e + 1) % RING;
+      mbar_wait(&bars[s], (uint32_t)(((e + 1) / RING) & 1));
+    }
+    __syncthreads();  // everyone is done with step g-1: slot of row g-2 is free, rows_sm[g&1] is complete
+    if (threadIdx.x == 0 && g + 2 <= G) fetch(g + 2);
+
+    const Slot& sc = ring[(g + 1) % RING];
+    // view of the three rows for the exact routine: slot index 0,1,2 <-> rows g-1, g, g+1.  The ring is not
+    // contiguous in row order, so the exact routine gets per-slot pointers through a small table.
+    const Slot* s3[3] = {&ring[g % RING], &ring[(g + 1) % RING], &ring[(g + 2) % RING]};
+    const float* xs = sc.xs + lane;
+    const float* ys = sc.ys + lane;
+    const int n = sc.nv[lane];
+    const float blo = sc.blo[lane], bhi = sc.bhi[lane];
+    const float clo = extrap == 0 ? sc.clo[lane] : fnan, chi = extrap == 0 ? sc.chi[lane] : fnan;
+
+    float xn[U];
+    int m = warp * U;
+    if (m < n_rows) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) xn[j] = src[(long long)rows[min(m + j, n_rows - 1)] * st];
+    }
+    for (; m < n_rows; m += n_warps * U) {
+      float x[U];
+      int po[U];  // byte offset of xs[pos] from xs: the search advances it by step rows (128 B each)
+#pragma unroll
+      for (int j = 0; j < U; ++j) { x[j] = xn[j]; po[j] = 0; }
+      const int mn = m + n_warps * U;
+      if (mn < n_rows) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) xn[j] = src[(long long)rows[min(mn + j, n_rows - 1)] * st];
+      }
+      const char* xb = reinterpret_cast<const char*>(xs);
+#pragma unroll
+      for (int step = TOP; step > 0; step >>= 1) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const float v = *reinterpret_cast<const float*>(xb + po[j] + (step - 1) * (C * 4));
+          po[j] = v < x[j] ? po[j] + step * (C * 4) : po[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        // po = offset of xs[i], i = #nodes < x (<= n); xs[n] = +inf.  ys sits LD rows after xs.
+        const bool first = po[j] == 0;
+        const int pl = first ? 0 : po[j] - C * 4;
+        const float xl = *reinterpret_cast<const float*>(xb + pl), xh = *reinterpret_cast<const float*>(xb + po[j]);
+        const float yl = *reinterpret_cast<const float*>(xb + pl + LD * C * 4);
+        const bool last = xh == finf;  // i == n (or a genuine +inf node: same treatment, dh = inf)
+        const float yh = *reinterpret_cast<const float*>(xb + (last ? pl : po[j]) + LD * C * 4);
+        const float dl = first ? finf : x[j] - xl;
+        const float dh = xh - x[j];
+        const float dmin = fminf(dl, dh);
+        float f = dh < dl ? yh : yl;
+        const bool below = x[j] < blo, above = x[j] > bhi;
+        // NaN samples need no lookup at all: x (+|*) anything = NaN
+        const bool sure = ((fabsf(dl - dh) > 1e-5f * dmin) && (dmin < 0.99f)) || (x[j] != x[j]);
+        f = below ? clo : f;
+        f = above ? chi : f;
+        if (!(sure || below || above)) f = lookup_exact_slots<LD>(s3, tb, lane, pt, g, x[j], extrap);
+        if (m + j < n_rows && pt_ok)
+          dst[(long long)rows[m + j] * st] = kind == XSDBA_KIND_ADD ? __fadd_rn(x[j], f) : __fmul_rn(x[j], f);
+      }
+    }
+    {
+      int* rn = rows_sm + ((g + 1) & 1) * kTileMaxRows;
+#pragma unroll
+      for (int i = 0; i < (kTileMaxRows + kThreads - 1) / kThreads; ++i) {
+        const int idx = threadIdx.x + i * kThreads;
+        if (idx < n_next) rn[idx] = nxt[i];
+      }
     }
   }
 }
@@ -772,14 +991,69 @@ int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t
 #undef XS_CASE
 }
 
+template <int TOP>
+bool launch_adjust_tile_t(const float* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
+                          const float* af, const float* hq, int nq, int extrap, int kind, float* scen, cudaStream_t s) {
+  typedef PackedSlot<2 * TOP> Slot;
+  const size_t smem_t = 4 * sizeof(Slot) + 2 * kTileMaxRows * sizeof(int) + 4 * sizeof(uint64_t) + 128;
+  const size_t smem_p = sizeof(Slot) + stage_bytes<float, 32>(nq);
+  if (smem_t > 220 * 1024 || smem_p > 220 * 1024) return false;
+  const int64_t tiles = (n_pts + 31) / 32;
+  Slot* packed = nullptr;
+  {
+    // keep the stream-ordered pool's memory across calls (default threshold 0 returns it to the driver at
+    // every synchronisation, which costs milliseconds per call)
+    static std::atomic<int> pool_ready{0};
+    if (!pool_ready.exchange(1)) {
+      int dev = 0;
+      cudaMemPool_t pool;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+    }
+  }
+  if (cudaMallocAsync(&packed, (size_t)tiles * grp->n_groups * sizeof(Slot), s) != cudaSuccess) {
+    cudaGetLastError();
+    return false;  // not enough memory for the packed image: the caller falls back to the staging kernel
+  }
+  if (set_smem(pack_tables_kernel<TOP>, smem_p) || set_smem(adjust_tile_kernel<TOP>, smem_t)) {
+    cudaFreeAsync(packed, s);
+    return false;
+  }
+  pack_tables_kernel<TOP><<<dim3((unsigned)tiles, (unsigned)grp->n_groups), kThreads, smem_p, s>>>(af, hq, n_pts,
+                                                                                                   grp->n_groups, nq, packed);
+  adjust_tile_kernel<TOP><<<(unsigned)tiles, kThreads, smem_t, s>>>(sim, n_pts, sp, st, grp->members.off,
+                                                                    grp->members.rows, grp->n_groups, af, hq, nq, packed,
+                                                                    extrap, kind, scen);
+  g_launches += 2;
+  cudaFreeAsync(packed, s);
+  return true;
+}
+
+bool launch_adjust_tile(const float* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
+                        const float* af, const float* hq, int nq, int top, int extrap, int kind, float* scen,
+                        cudaStream_t s) {
+  switch (top) {
+    case 8: return launch_adjust_tile_t<8>(sim, n_pts, sp, st, grp, af, hq, nq, extrap, kind, scen, s);
+    case 16: return launch_adjust_tile_t<16>(sim, n_pts, sp, st, grp, af, hq, nq, extrap, kind, scen, s);
+    case 32: return launch_adjust_tile_t<32>(sim, n_pts, sp, st, grp, af, hq, nq, extrap, kind, scen, s);
+    case 64: return launch_adjust_tile_t<64>(sim, n_pts, sp, st, grp, af, hq, nq, extrap, kind, scen, s);
+    default: return false;
+  }
+}
+
 bool launch_adjust_fast(const float* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
                         const float* af, const float* hq, int nq, int interp, int extrap, int kind, float* scen,
                         size_t smem, dim3 grid, cudaStream_t s) {
   if (grp->n_groups <= 1 || interp != XSDBA_INTERP_NEAREST || getenv("XSDBA_B200_NO_FAST")) return false;
   if (grp->members.max_len > kAdjMaxRows) return false;
-  smem += (size_t)grp->members.max_len * sizeof(int);
   int top = 1;
   while (top * 2 <= nq) top *= 2;
+  if (grp->members.max_len <= kTileMaxRows && !getenv("XSDBA_B200_NO_TILE") &&
+      launch_adjust_tile(sim, n_pts, sp, st, grp, af, hq, nq, top, extrap, kind, scen, s))
+    return true;
+  smem += (size_t)grp->members.max_len * sizeof(int);
 #define XS_LAUNCH(TOP)                                                                                          \
   case TOP:                                                                                                     \
     if (set_smem(adjust_fast_kernel<TOP>, smem)) return false;                                                  \
