@@ -159,6 +159,35 @@ int xsdba_qm_train_adjust_host_f32(const float* ref_host, const float* hist_host
                                    float* scen_host, float* af_host, float* hist_q_host,
                                    int64_t slab_pts);
 
+/*
+ * Polynomial trend: replaces detrending.PolyDetrend.fit(...).ds.trend = _polydetrend_get_trend
+ * (detrending.py:165-208; xarray polyfit/polyval per group through map_groups): y = x (+|*)
+ * scaling[point][group] when scaling_dev != NULL (the scaled_sim of dqm_adjust, _adjustment.py:748-757),
+ * the Grouper window is averaged NaN-skipping first (detrending.py:199-200), least squares of degree
+ * 0..4 on tcoord_dev[n_time] (any monotone float64 time coordinate, e.g. days), evaluated at every
+ * member.  trend_dev is float64 with the strides of x.
+ */
+int xsdba_poly_trend_f32(const float* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                         const xsdba_grouping_t* grp, const float* scaling_dev, int32_t kind, int32_t degree,
+                         const double* tcoord_dev, double* trend_dev, void* cuda_stream);
+int xsdba_poly_trend_f64(const double* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                         const xsdba_grouping_t* grp, const double* scaling_dev, int32_t kind, int32_t degree,
+                         const double* tcoord_dev, double* trend_dev, void* cuda_stream);
+
+/*
+ * Adjust (DQM): replaces _adjustment.dqm_adjust.func (_adjustment.py:748-780) once the trend of the
+ * scaled sim is known (xsdba_poly_trend_* or xsdba_loess_trend_*): scale, detrend (float64 like the
+ * reference), factor lookup as in xsdba_qm_adjust_*, correction, retrend.  scen has the strides of sim.
+ */
+int xsdba_dqm_adjust_f32(const float* sim_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                         const xsdba_grouping_t* grp, const float* af_dev, const float* hist_q_dev,
+                         const float* scaling_dev, const double* trend_dev, int32_t nq, int32_t interp,
+                         int32_t extrap, int32_t kind, float* scen_dev, void* cuda_stream);
+int xsdba_dqm_adjust_f64(const double* sim_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                         const xsdba_grouping_t* grp, const double* af_dev, const double* hist_q_dev,
+                         const double* scaling_dev, const double* trend_dev, int32_t nq, int32_t interp,
+                         int32_t extrap, int32_t kind, double* scen_dev, void* cuda_stream);
+
 /* Microbenchmark only (profiles/microbench_rows.py): copy every group's member rows with the tiling
  * of the adjust kernel, v in {1,2,4} floats per lane.  Not part of the reference-facing surface. */
 int xsdba_debug_copy_rows_f32(const float* src_dev, int64_t n_pts, int64_t stride_time,

@@ -731,3 +731,68 @@ def qm_adjust_factor_bounds(newx, af, xq, *, group, time, extrapolation):
         lo[i] = extrapolate_on_quantiles(a, oldx, oldg, oldy, newx[i], newg, extrapolation)
         hi[i] = extrapolate_on_quantiles(b, oldx, oldg, oldy, newx[i], newg, extrapolation)
     return lo, hi
+
+
+# ----------------------------------------------------------------------------------------------
+# DQM adjust  (_adjustment.py:679-780; detrending.py:59-120, 165-296)
+# ----------------------------------------------------------------------------------------------
+
+def time_ordinal(time: TimeAxis) -> np.ndarray:
+    """Days since the first step as float64 (x-axis of the trend fits; xarray uses ns since 1970,
+    which is the same polynomial up to conditioning)."""
+    y0 = int(time.year.min())
+    years = np.arange(y0, int(time.year.max()) + 1)
+    if time.calendar == "360_day":
+        ylen = np.full(years.shape, 360)
+    else:
+        ylen = 365 + _is_leap(years, time.calendar).astype(np.int64)
+    start = np.concatenate([[0], np.cumsum(ylen)[:-1]])
+    o = start[time.year - y0] + time.dayofyear - 1
+    return (o - o[0]).astype(np.float64)
+
+
+def group_trend_poly(x, gidx, n_groups, window, tcoord, degree):
+    """``PolyDetrend(degree, group).fit(x).ds.trend`` (detrending.py:189-208 through map_groups /
+    Grouper.apply, base.py:410-420): per group, window dims are averaged first (NaN-skipping), then a
+    polynomial is fitted on the group's time steps and evaluated there.  Returns float64 [N, T]."""
+    N, T = x.shape
+    trend = np.full((N, T), np.nan)
+    xw = window_gather(x, window) if window > 1 else None
+    for g in range(n_groups):
+        sel = np.nonzero(gidx == g)[0]
+        if sel.size == 0:
+            continue
+        if window > 1:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                series = np.nanmean(xw[:, sel, :].astype(np.float64), axis=2)  # detrending.py:199-200
+        else:
+            series = x[:, sel].astype(np.float64)
+        for i in range(N):
+            trend[i, sel] = poly_trend(series[i], tcoord[sel], degree)
+    return trend
+
+
+def dqm_adjust(sim, af, hist_q, scaling, *, group, window, time, interp, extrapolation, kind, detrend=1,
+               loess=None):
+    """``dqm_adjust.func`` without adapt_freq / max_tail_factor (_adjustment.py:748-780).
+    ``detrend`` is the PolyDetrend degree; ``loess`` (dict f, niter, d, weights) selects a
+    ``LoessDetrend(group="time")`` instead.  Returns (scen float64 [N,T], trend float64 [N,T])."""
+    gidx, G, _ = group_index(time, group)
+    if group == "time":
+        sc_b = scaling[:, :1]
+    elif group.endswith("dayofyear") or interp == "nearest":
+        sc_b = broadcast_nearest(scaling, gidx)                      # _adjustment.py:750-756
+    else:
+        sc_b = broadcast_month_linear(scaling, time)
+    scaled = apply_correction(sim, sc_b, kind)                       # _adjustment.py:748-757
+    tcoord = time_ordinal(time)
+    if loess is not None:
+        trend = np.stack([loess_smoothing(scaled[i], tcoord, **loess) for i in range(sim.shape[0])])
+    else:
+        trend = group_trend_poly(scaled, gidx, G, window, tcoord, detrend)  # _adjustment.py:759-765
+    detr = apply_correction(scaled, invert(trend, kind), kind)       # detrending.py:99
+    afi = interp_on_quantiles(detr, hist_q, af, group=group, time=time, method=interp, extrapolation=extrapolation)
+    scen = apply_correction(detr, afi, kind)                         # qm_adjust.func, _adjustment.py:669
+    scen = apply_correction(scen, trend, kind)                       # detrending.py:120
+    return scen, trend

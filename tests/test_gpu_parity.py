@@ -219,3 +219,38 @@ def test_dqm_train_matches_oracle():
         fin = np.isfinite(af_o)
         assert (np.isfinite(_np(ds.af)) == fin).all()
         np.testing.assert_allclose(_np(ds.af)[fin], af_o[fin], rtol=50 * rtol, atol=50 * rtol * scale)
+
+
+DQM_CASES = [
+    ("time", 1, "noleap", 4, 30, "+", "tas", np.float32, 1),
+    ("time.month", 1, "noleap", 5, 50, "+", "tas", np.float32, 1),
+    ("time.dayofyear", 31, "noleap", 4, 20, "*", "pr", np.float32, 1),
+    ("time.dayofyear", 15, "standard", 4, 20, "+", "tas", np.float64, 2),
+    ("time", 1, "noleap", 3, 20, "*", "pr", np.float64, 0),
+]
+
+
+@pytest.mark.parametrize("case", DQM_CASES, ids=lambda c: f"{c[0]}-w{c[1]}-{c[2]}-{c[5]}-{np.dtype(c[7]).name}-deg{c[8]}")
+def test_dqm_adjust_matches_oracle(case):
+    """dqm_adjust with PolyDetrend: trend within 1e-9, scen within 1e-6 (f32) / 1e-9 (f64) relative; samples
+    whose nearest node changes under that tolerance (ties) are excluded like in the EQM test."""
+    xs = _xs()
+    group, window, cal, years, nq, kind, var, dt, degree = case
+    tx, to, ref, hist, sim = _make(case[:8], n_pts=9)
+    q = o.equally_spaced_nodes(nq).astype(dt)
+    gidx, G, _ = o.group_index(to, group)
+    af_o, hq_o, sc_o = o.dqm_train(ref.T.copy(), hist.T.copy(), gidx, G, window, q, kind)
+    scen_o, trend_o = o.dqm_adjust(sim.T.copy(), af_o, hq_o, sc_o, group=group, window=window, time=to,
+                                   interp="nearest", extrapolation="constant", kind=kind, detrend=degree)
+    out = xs.dqm_adjust(xs.Dataset({"sim": sim, "af": af_o, "hist_q": hq_o, "scaling": sc_o}, time=tx),
+                        group=xs.Grouper(group, window), interp="nearest", extrapolation="constant", kind=kind,
+                        detrend=degree)
+    trend = _np(out.trend).T
+    scen = _np(out.scen).T
+    assert scen.dtype == dt
+    np.testing.assert_allclose(trend, trend_o, rtol=1e-9, atol=1e-9, equal_nan=True)
+    rtol = 2e-6 if dt == np.float32 else 1e-9
+    close = np.isclose(scen, scen_o, rtol=rtol, atol=0, equal_nan=True)
+    # a detrended value within ~1e-9 (relative) of a mid-point between two nodes may pick the other node
+    assert close.mean() > 0.999, close.mean()
+    assert (np.isnan(scen) == np.isnan(scen_o)).all()

@@ -17,6 +17,7 @@ import torch
 from . import _lib
 from .base import Grouper, parse_group
 from .calendar import TimeAxis
+from .detrending import LoessDetrend, PolyDetrend
 
 
 class Dataset(dict):
@@ -244,3 +245,65 @@ def group_rank(x, *, time, group, rank_window=False, time_axis=0):
     fn = getattr(lib, f"xsdba_group_rank_{_sfx(dt)}")
     _lib.check(fn(xs.data_ptr(), n_pts, sp, st, h.ptr, 1 if rank_window else 0, out.data_ptr(), _stream()), "rank")
     return out
+
+
+def poly_trend(x, *, time, group, degree, kind="+", scaling=None, time_axis=0):
+    """Trend of ``x`` (optionally of ``x (+|*) scaling``) as ``PolyDetrend(degree, group).fit`` computes it
+    (detrending.py:189-208): float64 tensor shaped like ``x``."""
+    group = parse_group(group)
+    lib = _lib.load()
+    dt = _widest(x)
+    xs, n_pts, sp, st, _ = _series(x, time_axis, len(time), dt)
+    h = group.handle(time)
+    sc = None
+    if scaling is not None:
+        sc = _as_device(scaling, dt).contiguous()
+        if sc.numel() != n_pts * h.n_groups:
+            raise ValueError("scaling must be (*points, n_groups)")
+    tc = _as_device(np.asarray(time.ordinal, np.float64)).contiguous()
+    trend = torch.empty(xs.shape, dtype=torch.float64, device=xs.device)
+    fn = getattr(lib, f"xsdba_poly_trend_{_sfx(dt)}")
+    _lib.check(fn(xs.data_ptr(), n_pts, sp, st, h.ptr, sc.data_ptr() if sc is not None else None, _lib.KIND[kind],
+                  int(degree), tc.data_ptr(), trend.data_ptr(), _stream()), "poly_trend")
+    return trend
+
+
+def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_thresh=None, max_tail_factor=None):
+    """``xsdba._adjustment.dqm_adjust`` (_adjustment.py:679-780): ds holds scaling, af, hist_q, sim.
+    ``detrend`` is an int (PolyDetrend degree on the adjust group) or a PolyDetrend / LoessDetrend."""
+    _reject_unsupported(adapt_freq_thresh=adapt_freq_thresh, max_tail_factor=max_tail_factor)
+    if interp == "cubic":
+        raise NotImplementedError("cubic interpolation is not built in xsdba_b200 yet")
+    group = parse_group(group)
+    if group.prop not in ("group", "dayofyear") and interp != "nearest":
+        raise NotImplementedError("broadcasting `scaling` with linear interpolation over months is not built yet")
+    lib = _lib.load()
+    time = ds.time
+    dt = _widest(ds["sim"], ds["af"])
+    sim, n_pts, sp, st, pshape = _series(ds["sim"], ds.time_axis, len(time), dt)
+    h = group.handle(time)
+    af, hq = _tables(ds, n_pts, h.n_groups, dt, ("af", "hist_q"))
+    scaling = _as_device(ds["scaling"], dt).contiguous()
+    if scaling.numel() != n_pts * h.n_groups:
+        raise ValueError("scaling must be (*points, n_groups)")
+    if isinstance(detrend, (int, np.integer)):
+        detrend = PolyDetrend(degree=int(detrend), kind=kind, group=group)   # _adjustment.py:759-762
+    if isinstance(detrend, PolyDetrend):
+        trend = poly_trend(sim, time=time, group=detrend.group, degree=detrend.degree, kind=kind,
+                           scaling=scaling if detrend.group.name == group.name and detrend.group.window == group.window else None,
+                           time_axis=0 if st != 1 or sim.ndim == 1 else -1)
+        if not (detrend.group.name == group.name and detrend.group.window == group.window):
+            raise NotImplementedError("a PolyDetrend with a group different from the adjustment group is not built yet")
+    elif isinstance(detrend, LoessDetrend):
+        raise NotImplementedError("LoessDetrend is not built in xsdba_b200 yet")
+    else:
+        raise TypeError("detrend must be an int, a PolyDetrend or a LoessDetrend")
+    nq = af.shape[-1]
+    scen = torch.empty_like(sim)
+    fn = getattr(lib, f"xsdba_dqm_adjust_{_sfx(dt)}")
+    status = fn(sim.data_ptr(), n_pts, sp, st, h.ptr, af.data_ptr(), hq.data_ptr(), scaling.data_ptr(),
+                trend.data_ptr(), nq, _lib.INTERP[interp], _lib.EXTRAP[extrapolation], _lib.KIND[kind],
+                scen.data_ptr(), _stream())
+    _lib.check(status, "dqm_adjust")
+    ta = 0 if st != 1 or sim.ndim == 1 else -1
+    return Dataset({"scen": scen, "trend": trend}, time=time, time_axis=ta)

@@ -64,6 +64,17 @@ class QuantileDeltaMapping(EmpiricalQuantileMapping):
         return out if extra_output else out["scen"]  # OPTIONS[EXTRA_OUTPUT] (adjustment.py:738)
 
 
+class DetrendedQuantileMapping(_TrainAdjust):
+    """adjustment.py:531-671."""
+    _train_fn = staticmethod(L4.dqm_train)
+
+    def adjust(self, sim, *, time, interp="nearest", extrapolation="constant", detrend=1, time_axis=0):
+        ds = L4.Dataset({"sim": sim, "af": self.ds["af"], "hist_q": self.ds["hist_q"], "scaling": self.ds["scaling"]},
+                        time=time, time_axis=time_axis)
+        return L4.dqm_adjust(ds, group=self.group, interp=interp, extrapolation=extrapolation, detrend=detrend,
+                             kind=self.kind)["scen"]
+
+
 def train_adjust_host(ref: np.ndarray, hist: np.ndarray, sim: np.ndarray, *, time, sim_time, nquantiles=50,
                       group="time.month", window=1, kind="+", method="eqm", interp="nearest",
                       extrapolation="constant", slab_points=16384, out=None, return_tables=False):

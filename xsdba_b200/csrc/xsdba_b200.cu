@@ -38,6 +38,7 @@ struct xsdba_grouping {
   int device = 0;
   DevTable members;   // exact group members (window = 1), ascending time
   DevTable segments;  // members x window slots (aliases `members` when window == 1)
+  int32_t* gidx = nullptr;  // [n_time] group of every time step (-1: none)
 };
 
 namespace {
@@ -800,6 +801,151 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
 }
 
 // =============================================================================================
+// K4: per-(point, group) polynomial trend  (PolyDetrend, detrending.py:165-208 via map_groups).
+// grid = (ceil(n_pts/32), n_groups), 256 threads.  y = x (+|*) scaling[point][group] (nullable), window
+// slots averaged NaN-skipping first (detrending.py:199-200), least squares of degree <= 4 on the
+// normalised time coordinate u = (t - t_first)/(t_last - t_first) by float64 normal equations, then
+// evaluated at every member: trend (float64) has the strides of x.
+// =============================================================================================
+constexpr int kMaxDeg = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+poly_trend_kernel(const T* __restrict__ x, long long n_pts, long long sp, long long st,
+                  const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows,
+                  const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows,
+                  const int32_t* __restrict__ gidx, int n_groups, int window, const T* __restrict__ scaling, int kind, int degree, const double* __restrict__ tcoord,
+                  double* __restrict__ trend) {
+  constexpr int C = 32, NS = 2 * kMaxDeg + 1, NB = kMaxDeg + 1;
+  __shared__ double red[kThreads / 32][NS + NB][C];
+  __shared__ double coef[NB][C];
+  const int g = blockIdx.y;
+  const long long n0 = (long long)blockIdx.x * C;
+  const int m0 = mem_off[g], n_mem = mem_off[g + 1] - m0;
+  if (n_mem == 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const long long pt = n0 + lane;
+  const bool ok = pt < n_pts;
+  const int32_t* segs = seg_rows + seg_off[g];
+  const double t0 = tcoord[mem_rows[m0]], t1 = tcoord[mem_rows[m0 + n_mem - 1]];
+  const double inv = t1 > t0 ? 1.0 / (t1 - t0) : 1.0;
+  T sc = (T)0;
+  if (scaling && ok) sc = scaling[pt * n_groups + g];
+
+  double S[NS], B[NB];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) S[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) B[k] = 0.0;
+  for (int m = warp; m < n_mem; m += n_warps) {
+    double y;
+    if (window == 1) {
+      T v = ok ? x[pt * sp + (long long)mem_rows[m0 + m] * st] : Num<T>::nan();
+      if (scaling) v = apply_corr<T>(v, sc, kind);
+      y = (double)v;
+    } else {
+      double acc = 0.0; int cnt = 0;
+      for (int j = 0; j < window; ++j) {
+        const int t = segs[m * window + j];
+        if (t < 0 || !ok) continue;
+        T v = x[pt * sp + (long long)t * st];
+        // every time step is scaled by its OWN group's factor before the window is built (_adjustment.py:748-757)
+        if (scaling) v = gidx[t] >= 0 ? apply_corr<T>(v, scaling[pt * n_groups + gidx[t]], kind) : Num<T>::nan();
+        if (!is_nan(v)) { acc += (double)v; ++cnt; }
+      }
+      y = cnt > 0 ? acc / (double)cnt : Num<double>::nan();
+    }
+    if (y == y) {
+      const double u = (tcoord[mem_rows[m0 + m]] - t0) * inv;
+      double p = 1.0;
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        if (k <= 2 * degree) S[k] += p;
+        if (k <= degree) B[k < NB ? k : 0] += p * y;
+        p *= u;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NS; ++k) red[warp][k][lane] = S[k];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) red[warp][NS + k][lane] = B[k];
+  __syncthreads();
+  if (warp == 0) {
+    double A[NB][NB + 1];
+    double Ssum[NS], Bsum[NB];
+    for (int k = 0; k < NS; ++k) { double a = 0; for (int w = 0; w < n_warps; ++w) a += red[w][k][lane]; Ssum[k] = a; }
+    for (int k = 0; k < NB; ++k) { double a = 0; for (int w = 0; w < n_warps; ++w) a += red[w][NS + k][lane]; Bsum[k] = a; }
+    const int nd = degree + 1;
+    for (int i = 0; i < nd; ++i) { for (int j = 0; j < nd; ++j) A[i][j] = Ssum[i + j]; A[i][nd] = Bsum[i]; }
+    bool singular = Ssum[0] <= (double)degree;  // not more valid points than the degree
+    for (int i = 0; i < nd && !singular; ++i) {  // Gaussian elimination, partial pivoting
+      int piv = i;
+      for (int r = i + 1; r < nd; ++r) if (fabs(A[r][i]) > fabs(A[piv][i])) piv = r;
+      if (A[piv][i] == 0.0) { singular = true; break; }
+      if (piv != i) for (int j = 0; j <= nd; ++j) { const double tmp = A[i][j]; A[i][j] = A[piv][j]; A[piv][j] = tmp; }
+      for (int r = i + 1; r < nd; ++r) {
+        const double f = A[r][i] / A[i][i];
+        for (int j = i; j <= nd; ++j) A[r][j] -= f * A[i][j];
+      }
+    }
+    for (int i = nd - 1; i >= 0; --i) {
+      double v = A[i][nd];
+      for (int j = i + 1; j < nd; ++j) v -= A[i][j] * coef[j][lane];
+      coef[i][lane] = singular ? Num<double>::nan() : v / A[i][i];
+    }
+  }
+  __syncthreads();
+  if (!ok) return;
+  for (int m = warp; m < n_mem; m += n_warps) {
+    const int t = mem_rows[m0 + m];
+    const double u = (tcoord[t] - t0) * inv;
+    double v = coef[degree][lane];
+    for (int k = degree - 1; k >= 0; --k) v = v * u + coef[k][lane];
+    trend[pt * sp + (long long)t * st] = v;
+  }
+}
+
+// =============================================================================================
+// K5: DQM adjust (dqm_adjust.func, _adjustment.py:748-780) given the trend: per sample, in float64 like
+// the reference after detrending,  x = sim (+|*) scaling ; xd = x (+|*) invert(trend) ; f = lookup(xd) ;
+// scen = (xd (+|*) f) (+|*) trend.  Same tiling / staging as K2 (generic kernel).
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+dqm_adjust_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long st,
+                  const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows, int n_groups,
+                  const T* __restrict__ af, const T* __restrict__ hist_q, const T* __restrict__ scaling,
+                  const double* __restrict__ trend, int nq, int interp, int extrap, int kind, T* __restrict__ scen) {
+  constexpr int C = 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Tables<T, C> tb = carve_tables<T, C>(smem_raw, nq);
+  T* stage = reinterpret_cast<T*>(smem_raw + ((tables_bytes<T, C>(nq) + 15) & ~(size_t)15));
+  tb.gx = hist_q; tb.gy = af; tb.x_shared = false; tb.G = n_groups; tb.pt_stride = (long long)n_groups * nq;
+  const int g = blockIdx.y;
+  const long long n0 = (long long)blockIdx.x * C;
+  const int m0 = mem_off[g], m1 = mem_off[g + 1];
+  if (m0 == m1) return;
+  const bool grouped = n_groups > 1;
+  stage_tables<T, C>(tb, stage, n0, n_pts, g, grouped);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const long long pt = n0 + lane;
+  if (pt >= n_pts) return;
+  const T sc = scaling[pt * n_groups + g];
+  for (int m = m0 + warp; m < m1; m += n_warps) {
+    const long long o = pt * sp + (long long)mem_rows[m] * st;
+    const T xs = apply_corr<T>(sim[o], sc, kind);           // scaled_sim, data dtype (_adjustment.py:748-757)
+    const double tr = trend[o];
+    const double itr = kind == XSDBA_KIND_ADD ? -tr : __ddiv_rn(1.0, tr);   // utils.invert
+    const double xd = apply_corr<double>((double)xs, itr, kind);             // detrended, float64
+    const T f = grouped ? lookup_2d_nearest<double, T, C>(tb, lane, pt, g, xd, extrap)
+                        : lookup_1d<double, T, C>(tb, lane, xd, interp, extrap);
+    const double sd = apply_corr<double>(xd, (double)f, kind);
+    scen[o] = (T)apply_corr<double>(sd, tr, kind);
+  }
+}
+
+// =============================================================================================
 // K3: per-group percentile ranks (+ QDM factor lookup).  grid = (ceil(n_pts / C), n_groups).
 // The segment (exact members, or members x window when rank_window) of C points is sorted in shared
 // memory; every member then finds its average-tie rank by two binary searches in its sorted column.
@@ -1142,6 +1288,44 @@ int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba
 #undef XS_CASE
 }
 
+template <typename T>
+int launch_poly_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* scaling,
+                      int kind, int degree, const double* tcoord, double* trend, void* stream) {
+  if (!x || !grp || !tcoord || !trend || n_pts < 0 || degree < 0 || degree > kMaxDeg) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
+  if (n_pts == 0) return XSDBA_OK;
+  dim3 grid((unsigned)((n_pts + 31) / 32), (unsigned)grp->n_groups);
+  poly_trend_kernel<T><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+      x, n_pts, sp, st, grp->members.off, grp->members.rows, grp->segments.off, grp->segments.rows, grp->gidx,
+      grp->n_groups, grp->window, scaling, kind, degree, tcoord, trend);
+  ++g_launches;
+  return cuda_status(cudaGetLastError());
+}
+
+template <typename T>
+int launch_dqm_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* af,
+                      const T* hq, const T* scaling, const double* trend, int nq, int interp, int extrap, int kind,
+                      T* scen, void* stream) {
+  if (!sim || !grp || !af || !hq || !scaling || !trend || !scen || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (extrap != XSDBA_EXTRAP_CONSTANT && extrap != XSDBA_EXTRAP_NAN) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (grp->n_groups > 1 && interp != XSDBA_INTERP_NEAREST) return XSDBA_ERR_UNSUPPORTED;
+  if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
+  if (n_pts == 0) return XSDBA_OK;
+  const size_t smem = ((tables_bytes<T, 32>(nq) + 15) & ~(size_t)15) + stage_bytes<T, 32>(nq);
+  if (smem > 200 * 1024) return XSDBA_ERR_UNSUPPORTED;
+  auto kern = dqm_adjust_kernel<T>;
+  int rc = set_smem(kern, smem);
+  if (rc) return rc;
+  dim3 grid((unsigned)((n_pts + 31) / 32), (unsigned)grp->n_groups);
+  kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows,
+                                                       grp->n_groups, af, hq, scaling, trend, nq, interp, extrap, kind, scen);
+  ++g_launches;
+  return cuda_status(cudaGetLastError());
+}
+
 int upload_table(const std::vector<int32_t>& off, const std::vector<int32_t>& rows, DevTable& t) {
   XS_CUDA(cudaMalloc(&t.off, off.size() * sizeof(int32_t)));
   XS_CUDA(cudaMalloc(&t.rows, std::max<size_t>(rows.size(), 1) * sizeof(int32_t)));
@@ -1198,6 +1382,11 @@ int xsdba_grouping_create(xsdba_grouping_t** out, const int32_t* grp_idx_host, i
   }
   int rc = upload_table(off, rows, g->members);
   if (rc == XSDBA_OK) {
+    cudaError_t e = cudaMalloc(&g->gidx, n_time * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(g->gidx, grp_idx_host, n_time * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = (int)e;
+  }
+  if (rc == XSDBA_OK) {
     if (window == 1) {
       g->segments = g->members;
     } else {
@@ -1231,6 +1420,7 @@ int xsdba_grouping_destroy(xsdba_grouping_t* g) {
   if (g->segments.off != g->members.off) { cudaFree(g->segments.off); cudaFree(g->segments.rows); }
   cudaFree(g->members.off);
   cudaFree(g->members.rows);
+  cudaFree(g->gidx);
   delete g;
   return XSDBA_OK;
 }
@@ -1285,6 +1475,27 @@ int xsdba_group_rank_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, 
 int xsdba_group_rank_f64(const double* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
                          int32_t rank_window, double* rank, void* stream) {
   return launch_rank<double>(x, n_pts, sp, st, grp, nullptr, nullptr, 0, 0, 0, XSDBA_KIND_ADD, rank_window, 0, nullptr, rank, stream);
+}
+
+int xsdba_poly_trend_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                         const float* scaling, int32_t kind, int32_t degree, const double* tcoord, double* trend,
+                         void* stream) {
+  return launch_poly_trend<float>(x, n_pts, sp, st, grp, scaling, kind, degree, tcoord, trend, stream);
+}
+int xsdba_poly_trend_f64(const double* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                         const double* scaling, int32_t kind, int32_t degree, const double* tcoord, double* trend,
+                         void* stream) {
+  return launch_poly_trend<double>(x, n_pts, sp, st, grp, scaling, kind, degree, tcoord, trend, stream);
+}
+int xsdba_dqm_adjust_f32(const float* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                         const float* af, const float* hq, const float* scaling, const double* trend, int32_t nq,
+                         int32_t interp, int32_t extrap, int32_t kind, float* scen, void* stream) {
+  return launch_dqm_adjust<float>(sim, n_pts, sp, st, grp, af, hq, scaling, trend, nq, interp, extrap, kind, scen, stream);
+}
+int xsdba_dqm_adjust_f64(const double* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                         const double* af, const double* hq, const double* scaling, const double* trend, int32_t nq,
+                         int32_t interp, int32_t extrap, int32_t kind, double* scen, void* stream) {
+  return launch_dqm_adjust<double>(sim, n_pts, sp, st, grp, af, hq, scaling, trend, nq, interp, extrap, kind, scen, stream);
 }
 
 // microbenchmark entry (see copy_rows_kernel); time-major float32 only, n_pts % (32*v) == 0 expected

@@ -1,0 +1,35 @@
+"""Host mirror of ``xsdba.detrending`` for the DQM path (detrending.py:165-296): parameter objects with
+the reference's names; the fits run in the CUDA library."""
+from __future__ import annotations
+
+from .base import parse_group
+
+
+class BaseDetrend:
+    def __init__(self, *, group="time", kind="+", **kw):
+        self.group = parse_group(group)
+        self.kind = kind
+        self.params = kw
+
+
+class PolyDetrend(BaseDetrend):
+    """``PolyDetrend(group, kind, degree)`` (detrending.py:165-193); ``preserve_mean`` is not built."""
+
+    def __init__(self, group="time", kind="+", degree=4, preserve_mean=False, mult_skip_zeros=False):
+        if preserve_mean or mult_skip_zeros:
+            raise NotImplementedError("preserve_mean / mult_skip_zeros are not built in xsdba_b200 yet")
+        if not 0 <= int(degree) <= 4:
+            raise NotImplementedError("xsdba_b200 fits polynomial trends of degree 0..4")
+        super().__init__(group=group, kind=kind, degree=int(degree))
+        self.degree = int(degree)
+
+
+class LoessDetrend(BaseDetrend):
+    """``LoessDetrend(group, kind, f, niter, d, weights, ...)`` (detrending.py:211-272)."""
+
+    def __init__(self, group="time", kind="+", f=0.2, niter=1, d=0, weights="tricube", equal_spacing=None,
+                 skipna=True, mult_skip_zeros=False):
+        if mult_skip_zeros or not skipna or weights != "tricube" or equal_spacing is False:
+            raise NotImplementedError("only tricube / skipna / equal-spacing LOESS is built in xsdba_b200")
+        super().__init__(group=group, kind=kind, f=f, niter=niter, d=d, weights=weights)
+        self.f, self.niter, self.d = float(f), int(niter), int(d)
