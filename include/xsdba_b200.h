@@ -175,6 +175,23 @@ int xsdba_poly_trend_f64(const double* x_dev, int64_t n_pts, int64_t stride_pt, 
                          const double* tcoord_dev, double* trend_dev, void* cuda_stream);
 
 /*
+ * LOESS trend over the whole series: replaces detrending.LoessDetrend(group="time").fit(...).ds.trend =
+ * loess.loess_smoothing -> numba _loess_nb (loess.py:49-179, 182-279; detrending.py:211-296) in its
+ * equal-spacing, tricube, skipna form with local degree d in {0, 1}; niter = 1 (robustness iterations
+ * return XSDBA_ERR_UNSUPPORTED).  y = x (+|*) scaling[point][group(t)] when scaling_dev != NULL (grp
+ * supplies group(t); pass a single-group handle otherwise).  xn_dev[n_time] is the time coordinate
+ * rescaled to [0, 1] (loess.py:244-245).  trend_dev is float64 with the strides of x; NaN where x is NaN.
+ */
+int xsdba_loess_trend_f32(const float* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                          const xsdba_grouping_t* grp, const float* scaling_dev, int32_t kind, double f,
+                          int32_t niter, int32_t degree, const double* xn_dev, double* trend_dev,
+                          void* cuda_stream);
+int xsdba_loess_trend_f64(const double* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                          const xsdba_grouping_t* grp, const double* scaling_dev, int32_t kind, double f,
+                          int32_t niter, int32_t degree, const double* xn_dev, double* trend_dev,
+                          void* cuda_stream);
+
+/*
  * Adjust (DQM): replaces _adjustment.dqm_adjust.func (_adjustment.py:748-780) once the trend of the
  * scaled sim is known (xsdba_poly_trend_* or xsdba_loess_trend_*): scale, detrend (float64 like the
  * reference), factor lookup as in xsdba_qm_adjust_*, correction, retrend.  scen has the strides of sim.

@@ -254,3 +254,41 @@ def test_dqm_adjust_matches_oracle(case):
     # a detrended value within ~1e-9 (relative) of a mid-point between two nodes may pick the other node
     assert close.mean() > 0.999, close.mean()
     assert (np.isnan(scen) == np.isnan(scen_o)).all()
+
+
+@pytest.mark.parametrize("d,f", [(0, 0.2), (1, 0.3)])
+def test_loess_trend_reference_golden(golden, d, f):
+    """CUDA LOESS against the reference's own numba _loess_nb on the golden series (equal spacing, NaNs)."""
+    xs = _xs()
+    x, y = golden["loess_x"], golden["loess_y"]
+    n = x.size
+    t = xs.TimeAxis.daily(2001, 1, "noleap")[:n]
+    if d == 0:  # golden case 0 is exactly (d=0, f=0.2, niter=1, equal spacing)
+        assert tuple(golden["loess_case0_params"][:3]) == (0, 0.2, 1)
+        want = golden["loess_case0_out"]
+    else:
+        want = o.loess_nb(x, y, f=f, niter=1, d=1, dx=float(x[1] - x[0]))
+    series = np.stack([y, y[::-1].copy(), np.where(np.arange(n) < 30, np.nan, y)], axis=1)  # (time, 3 points)
+    got = _np(xs.loess_trend(series, time=t, f=f, niter=1, d=d))
+    np.testing.assert_allclose(got[:, 0], want, rtol=1e-11, atol=1e-12, equal_nan=True)
+    for j in (1, 2):
+        wj = o.loess_nb(x, series[:, j], f=f, niter=1, d=d, dx=float(x[1] - x[0]))
+        np.testing.assert_allclose(got[:, j], wj, rtol=1e-11, atol=1e-12, equal_nan=True)
+
+
+def test_dqm_adjust_loess_matches_oracle():
+    xs = _xs()
+    case = ("time.month", 1, "noleap", 3, 20, "+", "tas", np.float32)
+    group, window, cal, years, nq, kind, var, dt = case
+    tx, to, ref, hist, sim = _make(case, n_pts=5)
+    q = o.equally_spaced_nodes(nq).astype(dt)
+    gidx, G, _ = o.group_index(to, group)
+    af_o, hq_o, sc_o = o.dqm_train(ref.T.copy(), hist.T.copy(), gidx, G, window, q, kind)
+    scen_o, trend_o = o.dqm_adjust(sim.T.copy(), af_o, hq_o, sc_o, group=group, window=window, time=to, interp="nearest",
+                                   extrapolation="constant", kind=kind, loess=dict(f=0.2, niter=1, d=0))
+    out = xs.dqm_adjust(xs.Dataset({"sim": sim, "af": af_o, "hist_q": hq_o, "scaling": sc_o}, time=tx), group=group,
+                        interp="nearest", extrapolation="constant", kind=kind,
+                        detrend=xs.LoessDetrend(group="time", kind=kind, f=0.2, niter=1, d=0))
+    np.testing.assert_allclose(_np(out.trend).T, trend_o, rtol=1e-10, atol=1e-10, equal_nan=True)
+    close = np.isclose(_np(out.scen).T, scen_o, rtol=2e-6, atol=0, equal_nan=True)
+    assert close.mean() > 0.999

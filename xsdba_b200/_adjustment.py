@@ -268,6 +268,34 @@ def poly_trend(x, *, time, group, degree, kind="+", scaling=None, time_axis=0):
     return trend
 
 
+def loess_trend(x, *, time, f=0.2, niter=1, d=0, kind="+", scaling=None, scaling_group=None, loess_group="time",
+                time_axis=0):
+    """``LoessDetrend(group="time", f, niter, d).fit(x (+|*) scaling).ds.trend`` (detrending.py:274-296 ->
+    loess.loess_smoothing, loess.py:182-279): float64 tensor shaped like ``x``."""
+    loess_group = parse_group(loess_group)
+    if loess_group.prop != "group":
+        raise NotImplementedError("grouped LoessDetrend is not built in xsdba_b200 yet (group='time' only)")
+    lib = _lib.load()
+    dt = _widest(x)
+    xs, n_pts, sp, st, _ = _series(x, time_axis, len(time), dt)
+    o = np.asarray(time.ordinal, np.float64)
+    if len(o) < 3 or not np.all(np.diff(o) == np.diff(o)[0]):
+        raise NotImplementedError("only the equal-spacing LOESS branch is built (loess.py:251-263)")
+    xn = _as_device((o - o[0]) / (o[-1] - o[0])).contiguous()   # loess.py:244-245
+    g = parse_group(scaling_group) if scaling is not None else parse_group("time")
+    h = g.handle(time, with_window=False)
+    sc = None
+    if scaling is not None:
+        sc = _as_device(scaling, dt).contiguous()
+        if sc.numel() != n_pts * h.n_groups:
+            raise ValueError("scaling must be (*points, n_groups)")
+    trend = torch.empty(xs.shape, dtype=torch.float64, device=xs.device)
+    fn = getattr(lib, f"xsdba_loess_trend_{_sfx(dt)}")
+    _lib.check(fn(xs.data_ptr(), n_pts, sp, st, h.ptr, sc.data_ptr() if sc is not None else None, _lib.KIND[kind],
+                  float(f), int(niter), int(d), xn.data_ptr(), trend.data_ptr(), _stream()), "loess_trend")
+    return trend
+
+
 def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_thresh=None, max_tail_factor=None):
     """``xsdba._adjustment.dqm_adjust`` (_adjustment.py:679-780): ds holds scaling, af, hist_q, sim.
     ``detrend`` is an int (PolyDetrend degree on the adjust group) or a PolyDetrend / LoessDetrend."""
@@ -295,7 +323,9 @@ def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_
         if not (detrend.group.name == group.name and detrend.group.window == group.window):
             raise NotImplementedError("a PolyDetrend with a group different from the adjustment group is not built yet")
     elif isinstance(detrend, LoessDetrend):
-        raise NotImplementedError("LoessDetrend is not built in xsdba_b200 yet")
+        trend = loess_trend(sim, time=time, f=detrend.f, niter=detrend.niter, d=detrend.d, kind=kind, scaling=scaling,
+                            scaling_group=group, loess_group=detrend.group,
+                            time_axis=0 if st != 1 or sim.ndim == 1 else -1)
     else:
         raise TypeError("detrend must be an int, a PolyDetrend or a LoessDetrend")
     nq = af.shape[-1]

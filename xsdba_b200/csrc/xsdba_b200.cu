@@ -946,6 +946,104 @@ dqm_adjust_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long
 }
 
 // =============================================================================================
+// K6: LOESS trend of a whole series (LoessDetrend(group="time"), detrending.py:211-296 ->
+// loess.loess_smoothing / _loess_nb, loess.py:49-179, 244-278), equal-spacing branch, tricube
+// weights, niter = 1, local degree d in {0, 1}.
+//   K6a loess_compact_kernel: one thread per point walks its series, applies the optional per-group
+//       scaling, drops NaNs (loess.py:94-100) and writes the compacted values / time indices
+//       time-major into the workspace (lanes = neighbouring points, so rows stay coalesced).
+//   K6b loess_smooth_kernel: thread = (point, output index i); the window, bandwidth h and the
+//       "weights are only recomputed near the edges" rule follow loess.py:122-150 literally: away from
+//       the edges the weights are those computed at i = HW from the first 2*HW+1 valid samples.
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+loess_compact_kernel(const T* __restrict__ x, long long n_pts, long long sp, long long st, int n_time,
+                     const int32_t* __restrict__ gidx, int n_groups, const T* __restrict__ scaling, int kind,
+                     T* __restrict__ yc, int32_t* __restrict__ tc, int32_t* __restrict__ nvalid,
+                     double* __restrict__ trend) {
+  const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pt >= n_pts) return;
+  int n = 0;
+  for (int t = 0; t < n_time; ++t) {
+    T v = x[pt * sp + (long long)t * st];
+    if (scaling) v = gidx[t] >= 0 ? apply_corr<T>(v, scaling[pt * n_groups + gidx[t]], kind) : Num<T>::nan();
+    trend[pt * sp + (long long)t * st] = Num<double>::nan();
+    if (!is_nan(v)) {
+      yc[(long long)n * n_pts + pt] = v;
+      tc[(long long)n * n_pts + pt] = t;
+      ++n;
+    }
+  }
+  nvalid[pt] = n;
+}
+
+__device__ __forceinline__ double tricube_w(double u) {  // loess.py:31-35
+  const double c = 1.0 - u * u * u;
+  return u >= 1.0 ? 0.0 : c * c * c;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, const int32_t* __restrict__ nvalid,
+                    long long n_pts, long long sp, long long st, int n_time, const double* __restrict__ xn,
+                    double f, int degree, double* __restrict__ trend) {
+  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5, rows_per_cta = blockDim.x >> 5;
+  const long long pt = (long long)blockIdx.x * 32 + lane;
+  if (pt >= n_pts) return;
+  const int n = nvalid[pt];
+  if (n == 0) return;
+  const double dx = xn[1] - xn[0];                              // loess.py:262-263
+  const int r = (int)(2.0 * floor(f * (double)n / 2.0) + 1.0);  // loess.py:113
+  const int hw = (r - 1) / 2;
+  const int R = r + 4 < n ? r + 4 : n;
+  const int HW = hw + 2;
+  const T* y = yc + pt;
+  const int32_t* tcp = tc + pt;
+  for (int i = blockIdx.y * rows_per_cta + row; i < n; i += gridDim.y * rows_per_cta) {
+    int lo, hi;                                                 // loess.py:124-135
+    if (i < HW) { lo = 0; hi = R; }
+    else if (i >= n - HW - 1) { lo = n - R; hi = n; }
+    else { lo = i - HW; hi = i + HW + 1; }
+    // weights: recomputed for i <= HW or i >= n-HW, otherwise those of the last recomputation (i = HW),
+    // i.e. taken from the samples [0, 2HW+1) around sample HW                    (loess.py:136-150)
+    const bool edge = (i <= HW) || (i >= n - HW);
+    const int ic = edge ? i : HW;          // centre the weights are computed for
+    const int wlo = edge ? lo : 0;         // first sample of the window the weights are computed on
+    double h;
+    if (ic < hw) h = (double)(r - ic) * dx;
+    else if (ic >= n - hw) h = (double)(ic - (n - r) + 1) * dx;
+    else h = (double)(hw + 1) * dx;
+    const double xc = xn[tcp[(long long)ic * n_pts]];
+    const double xi = xn[tcp[(long long)i * n_pts]];
+    double sw = 0, swy = 0, swx = 0, swxx = 0, swxy = 0;
+    for (int j = lo; j < hi; ++j) {
+      const int k = wlo + (j - lo);        // sample whose distance defines the weight of window slot j-lo
+      const double w = k < n ? tricube_w(fabs(xn[tcp[(long long)k * n_pts]] - xc) / h) : 0.0;
+      const double yj = (double)y[(long long)j * n_pts];
+      sw += w; swy += w * yj;
+      if (degree == 1) {
+        const double xj = xn[tcp[(long long)j * n_pts]];
+        swx += w * xj; swxx += w * xj * xj; swxy += w * yj * xj;
+      }
+    }
+    double est;
+    if (degree == 0) {
+      est = swy / sw;                                           // loess.py:38-39
+    } else {                                                    // loess.py:42-46 (2x2 solve, partial pivoting)
+      double a00 = sw, a01 = swx, a10 = swx, a11 = swxx, b0 = swy, b1 = swxy;
+      if (fabs(a10) > fabs(a00)) { double t_; t_ = a00; a00 = a10; a10 = t_; t_ = a01; a01 = a11; a11 = t_; t_ = b0; b0 = b1; b1 = t_; }
+      const double m = a10 / a00;
+      a11 -= m * a01; b1 -= m * b0;
+      const double beta1 = b1 / a11;
+      const double beta0 = (b0 - a01 * beta1) / a00;
+      est = beta0 + beta1 * xi;
+    }
+    trend[pt * sp + (long long)tcp[(long long)i * n_pts] * st] = est;
+  }
+}
+
+// =============================================================================================
 // K3: per-group percentile ranks (+ QDM factor lookup).  grid = (ceil(n_pts / C), n_groups).
 // The segment (exact members, or members x window when rank_window) of C points is sorted in shared
 // memory; every member then finds its average-tie rank by two binary searches in its sorted column.
@@ -1326,6 +1424,34 @@ int launch_dqm_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const
   return cuda_status(cudaGetLastError());
 }
 
+template <typename T>
+int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* scaling,
+                       int kind, double f, int niter, int degree, const double* xn, double* trend, void* stream) {
+  if (!x || !grp || !xn || !trend || n_pts < 0 || !(f > 0.0) || degree < 0 || degree > 1) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (niter != 1) return XSDBA_ERR_UNSUPPORTED;  // robustness iterations (median of residuals) not built yet
+  if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (n_pts == 0) return XSDBA_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n_time = (int)grp->n_time;
+  T* yc = nullptr; int32_t* tc = nullptr; int32_t* nv = nullptr;
+  if (cudaMallocAsync(&yc, sizeof(T) * n_pts * n_time, s) != cudaSuccess ||
+      cudaMallocAsync(&tc, sizeof(int32_t) * n_pts * n_time, s) != cudaSuccess ||
+      cudaMallocAsync(&nv, sizeof(int32_t) * n_pts, s) != cudaSuccess) {
+    cudaGetLastError();
+    if (yc) cudaFreeAsync(yc, s);
+    if (tc) cudaFreeAsync(tc, s);
+    return XSDBA_ERR_OUT_OF_MEMORY;
+  }
+  loess_compact_kernel<T><<<(unsigned)((n_pts + kThreads - 1) / kThreads), kThreads, 0, s>>>(
+      x, n_pts, sp, st, n_time, grp->gidx, grp->n_groups, scaling, kind, yc, tc, nv, trend);
+  const unsigned chunks = (unsigned)std::min<int64_t>(std::max<int64_t>(1, (n_time + 63) / 64), 1024);
+  loess_smooth_kernel<T><<<dim3((unsigned)((n_pts + 31) / 32), chunks), kThreads, 0, s>>>(yc, tc, nv, n_pts, sp, st, n_time,
+                                                                                          xn, f, degree, trend);
+  g_launches += 2;
+  cudaFreeAsync(yc, s); cudaFreeAsync(tc, s); cudaFreeAsync(nv, s);
+  return cuda_status(cudaGetLastError());
+}
+
 int upload_table(const std::vector<int32_t>& off, const std::vector<int32_t>& rows, DevTable& t) {
   XS_CUDA(cudaMalloc(&t.off, off.size() * sizeof(int32_t)));
   XS_CUDA(cudaMalloc(&t.rows, std::max<size_t>(rows.size(), 1) * sizeof(int32_t)));
@@ -1496,6 +1622,17 @@ int xsdba_dqm_adjust_f64(const double* sim, int64_t n_pts, int64_t sp, int64_t s
                          const double* af, const double* hq, const double* scaling, const double* trend, int32_t nq,
                          int32_t interp, int32_t extrap, int32_t kind, double* scen, void* stream) {
   return launch_dqm_adjust<double>(sim, n_pts, sp, st, grp, af, hq, scaling, trend, nq, interp, extrap, kind, scen, stream);
+}
+
+int xsdba_loess_trend_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                          const float* scaling, int32_t kind, double f, int32_t niter, int32_t degree, const double* xn,
+                          double* trend, void* stream) {
+  return launch_loess_trend<float>(x, n_pts, sp, st, grp, scaling, kind, f, niter, degree, xn, trend, stream);
+}
+int xsdba_loess_trend_f64(const double* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                          const double* scaling, int32_t kind, double f, int32_t niter, int32_t degree, const double* xn,
+                          double* trend, void* stream) {
+  return launch_loess_trend<double>(x, n_pts, sp, st, grp, scaling, kind, f, niter, degree, xn, trend, stream);
 }
 
 // microbenchmark entry (see copy_rows_kernel); time-major float32 only, n_pts % (32*v) == 0 expected
