@@ -91,6 +91,28 @@ int xsdba_qm_train_f64(const double* ref_dev, const double* hist_dev, int64_t n_
                        double* scaling_dev, void* cuda_stream);
 
 /*
+ * Train with the jitter pre-step of _preprocess_dataset (_adjustment.py:48-83): jitter4_host =
+ * {lower, minimum, upper, maximum} in the data's units (NaN lower / upper disables that side; minimum
+ * is the already next-after'ed lower bound, processing.py:222-224).  As in the reference the noise is
+ * applied to `hist` only, after the window gather, independently for every window slot.  The draws are a
+ * counter-based hash of (seed, element): reproducible per call, distributionally equal to the
+ * reference's numpy.random.uniform draws (which are not reproducible by design).
+ */
+int xsdba_qm_train_jitter_f32(const float* ref_dev, const float* hist_dev, int64_t n_pts, int64_t stride_pt,
+                              int64_t stride_time, const xsdba_grouping_t* grp, const float* q_dev, int32_t nq,
+                              int32_t kind, int32_t normalize, const double* jitter4_host, uint64_t seed,
+                              float* af_dev, float* hist_q_dev, float* scaling_dev, void* cuda_stream);
+int xsdba_qm_train_jitter_f64(const double* ref_dev, const double* hist_dev, int64_t n_pts, int64_t stride_pt,
+                              int64_t stride_time, const xsdba_grouping_t* grp, const double* q_dev, int32_t nq,
+                              int32_t kind, int32_t normalize, const double* jitter4_host, uint64_t seed,
+                              double* af_dev, double* hist_q_dev, double* scaling_dev, void* cuda_stream);
+/* Elementwise processing.jitter (processing.py:180-257) over n contiguous elements. */
+int xsdba_jitter_f32(const float* x_dev, int64_t n, const double* jitter4_host, uint64_t seed, float* out_dev,
+                     void* cuda_stream);
+int xsdba_jitter_f64(const double* x_dev, int64_t n, const double* jitter4_host, uint64_t seed, double* out_dev,
+                     void* cuda_stream);
+
+/*
  * Quantiles only: replaces nbutils.quantile over grouped segments (nbutils.py:224-271), used for
  * hist_q_raw (_adjustment.py:254-256) and by callers that want ref_q.  out is [n_pts][n_groups][nq].
  */

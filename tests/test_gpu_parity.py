@@ -292,3 +292,44 @@ def test_dqm_adjust_loess_matches_oracle():
     np.testing.assert_allclose(_np(out.trend).T, trend_o, rtol=1e-10, atol=1e-10, equal_nan=True)
     close = np.isclose(_np(out.scen).T, scen_o, rtol=2e-6, atol=0, equal_nan=True)
     assert close.mean() > 0.999
+
+
+def test_jitter_is_distributionally_the_reference(golden):
+    """processing.jitter (processing.py:180-257): the reference draws from numpy's global RNG, so parity is
+    distributional: untouched values bit-identical, replaced values uniform in the reference's
+    interval, NaNs kept."""
+    from scipy import stats
+    xs = _xs()
+    rng = np.random.default_rng(5)
+    x = synth.pr(rng, o.daily_time_axis(1981, 6, "noleap"), 40, "hist", jitter=False)
+    out = _np(xs.jitter_under_thresh(x, "0.01 mm/d", seed=3))
+    dry = (x < 0.01)
+    assert bits_equal(np.where(dry, 0, out), np.where(dry, 0, x))          # wet values and NaNs untouched
+    assert (np.isnan(out) == np.isnan(x)).all()
+    v = out[dry]
+    assert v.min() > 0 and v.max() <= np.float32(0.01)
+    assert stats.kstest(v.astype(np.float64), stats.uniform(0, 0.01).cdf).pvalue > 1e-3
+    out2 = _np(xs.jitter_under_thresh(x, 0.01, seed=3))
+    assert bits_equal(out, out2)                                            # reproducible for a given seed
+    hi = _np(xs.jitter_over_thresh(x, 30.0, 35.0, seed=1))
+    big = x >= 30
+    assert big.sum() > 10 and (hi[big] >= 30).all() and (hi[big] < 35).all() and bits_equal(np.where(big, 0, hi), np.where(big, 0, x))
+
+
+def test_train_with_jitter_matches_oracle_statistically():
+    """eqm_train(jitter_under_thresh_value=...) jitters hist inside each group after the window gather; like the
+    reference's own test (tests/test_adjustment.py:1097-1103) the comparison is to 2 decimals on the quantiles."""
+    xs = _xs()
+    rng = np.random.default_rng(11)
+    to = o.daily_time_axis(1981, 10, "noleap"); tx = xs.TimeAxis.daily(1981, 10, "noleap")
+    ref, hist = (synth.pr(rng, to, 6, w, jitter=False, nan_frac=0) for w in ("ref", "hist"))
+    q = o.equally_spaced_nodes(20).astype(np.float32)
+    ds = xs.eqm_train(xs.Dataset({"ref": ref, "hist": hist}, time=tx), group=xs.Grouper("time.month"), kind="*",
+                      quantiles=q, jitter_under_thresh_value="0.01 mm/d")
+    hq = _np(ds.hist_q)
+    hist_j = np.where(hist < 0.01, rng.uniform(1e-45, 0.01, hist.shape), hist).astype(np.float32)
+    gidx, G, _ = o.group_index(to, "time.month")
+    _, hq_o = o.eqm_train(ref.T.copy(), hist_j.T.copy(), gidx, G, 1, q, "*")
+    np.testing.assert_allclose(hq, hq_o, atol=2e-3, rtol=0.02)   # nodes inside the jittered range are random
+    wet = hq_o > 0.02
+    np.testing.assert_array_equal(hq[wet], hq_o[wet])            # above the threshold nothing changes

@@ -11,3 +11,4 @@ from .adjustment import (  # noqa: F401
 from .detrending import LoessDetrend, PolyDetrend  # noqa: F401
 
 __version__ = "0.1.0"
+from .processing import jitter, jitter_over_thresh, jitter_under_thresh  # noqa: F401

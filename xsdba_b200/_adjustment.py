@@ -104,10 +104,11 @@ def _reject_unsupported(**kw):
 
 
 def _train(ds, *, group, kind, quantiles, normalize, adapt_freq_thresh=None, jitter_under_thresh_value=None,
-           jitter_over_thresh_value=None, jitter_over_thresh_upper_bnd=None, max_tail_factor=None):
-    _reject_unsupported(adapt_freq_thresh=adapt_freq_thresh, jitter_under_thresh_value=jitter_under_thresh_value,
-                        jitter_over_thresh_value=jitter_over_thresh_value,
-                        jitter_over_thresh_upper_bnd=jitter_over_thresh_upper_bnd, max_tail_factor=max_tail_factor)
+           jitter_over_thresh_value=None, jitter_over_thresh_upper_bnd=None, max_tail_factor=None, seed=0):
+    _reject_unsupported(adapt_freq_thresh=adapt_freq_thresh, max_tail_factor=max_tail_factor)
+    if (jitter_over_thresh_value is None) ^ (jitter_over_thresh_upper_bnd is None):
+        raise ValueError("`jitter_over_thresh_value` and `jitter_over_thresh_upper_bnd` must both be specified or both "
+                         "be `None` (default)")  # _adjustment.py:64-65
     if kind not in _lib.KIND:
         raise ValueError("kind must be + or *.")  # utils.py:139
     group = parse_group(group)
@@ -127,9 +128,19 @@ def _train(ds, *, group, kind, quantiles, normalize, adapt_freq_thresh=None, jit
     af = torch.empty((n_pts, G, nq), dtype=dt, device=ref.device)
     hq = torch.empty_like(af)
     sc = torch.empty((n_pts, G), dtype=dt, device=ref.device) if normalize else None
-    fn = getattr(lib, f"xsdba_qm_train_{_sfx(dt)}")
-    status = fn(ref.data_ptr(), hist.data_ptr(), n_pts, sp, st, h.ptr, q.data_ptr(), nq, _lib.KIND[kind],
-                1 if normalize else 0, af.data_ptr(), hq.data_ptr(), sc.data_ptr() if normalize else None, _stream())
+    if jitter_under_thresh_value is not None or jitter_over_thresh_value is not None:
+        import ctypes as C
+        from .processing import jitter_params
+        j4 = jitter_params(dt, lower=jitter_under_thresh_value, upper=jitter_over_thresh_value,
+                           maximum=jitter_over_thresh_upper_bnd)
+        fn = getattr(lib, f"xsdba_qm_train_jitter_{_sfx(dt)}")
+        status = fn(ref.data_ptr(), hist.data_ptr(), n_pts, sp, st, h.ptr, q.data_ptr(), nq, _lib.KIND[kind],
+                    1 if normalize else 0, j4.ctypes.data_as(_lib.c_f64p), C.c_uint64(seed), af.data_ptr(), hq.data_ptr(),
+                    sc.data_ptr() if normalize else None, _stream())
+    else:
+        fn = getattr(lib, f"xsdba_qm_train_{_sfx(dt)}")
+        status = fn(ref.data_ptr(), hist.data_ptr(), n_pts, sp, st, h.ptr, q.data_ptr(), nq, _lib.KIND[kind],
+                    1 if normalize else 0, af.data_ptr(), hq.data_ptr(), sc.data_ptr() if normalize else None, _stream())
     _lib.check(status, "dqm_train" if normalize else "eqm_train")
     nan_like = lambda t: torch.full_like(t, float("nan"))  # noqa: E731
     out = Dataset(time=None)

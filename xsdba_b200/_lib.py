@@ -38,6 +38,9 @@ SIGNATURES = {
 }
 for _t in ("f32", "f64"):
     SIGNATURES[f"xsdba_qm_train_{_t}"] = (C.c_int, [vp, vp, i64, i64, i64, vp, vp, i32, i32, i32, vp, vp, vp, vp])
+    SIGNATURES[f"xsdba_qm_train_jitter_{_t}"] = (
+        C.c_int, [vp, vp, i64, i64, i64, vp, vp, i32, i32, i32, c_f64p, C.c_uint64, vp, vp, vp, vp])
+    SIGNATURES[f"xsdba_jitter_{_t}"] = (C.c_int, [vp, i64, c_f64p, C.c_uint64, vp, vp])
     SIGNATURES[f"xsdba_group_quantile_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, i32, vp, vp])
     SIGNATURES[f"xsdba_qm_adjust_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, vp, i32, i32, i32, i32, vp, vp])
     SIGNATURES[f"xsdba_qdm_adjust_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp])

@@ -39,6 +39,34 @@ template <> struct Num<double> {
 template <typename T> __device__ __forceinline__ bool is_nan(T v) { return v != v; }
 
 // ---------------------------------------------------------------------------------------------
+// Jitter (processing.jitter, processing.py:180-257; used on `hist` inside the per-group train
+// function, _adjustment.py:58-67): non-NaN values < lower are REPLACED by U(minimum, lower), values
+// >= upper by U(upper, maximum).  The reference draws from numpy's global RNG (not reproducible by
+// design); here the draw is a counter-based hash of (seed, element id), so a call is
+// reproducible and every window slot gets its own draw like in the reference.
+// ---------------------------------------------------------------------------------------------
+struct JitterParams {
+  double lower, minimum, upper, maximum;  // lower / upper = NaN disables that side
+  unsigned long long seed;
+};
+
+__device__ __forceinline__ double hash_uniform(unsigned long long seed, unsigned long long id) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (id + 1);  // splitmix64
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z = z ^ (z >> 31);
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);  // [0, 1)
+}
+
+template <typename T>
+__device__ __forceinline__ T jitter_value(T v, const JitterParams& jp, unsigned long long id) {
+  if (v != v) return v;
+  if ((double)v < jp.lower) return (T)(jp.minimum + (jp.lower - jp.minimum) * hash_uniform(jp.seed, 2 * id));
+  if ((double)v >= jp.upper) return (T)(jp.upper + (jp.maximum - jp.upper) * hash_uniform(jp.seed, 2 * id + 1));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Column sort in shared memory.  sm is [n_pad][C] (column c of row r at sm[r*C + c]); n_pad is a
 // power of two; NaNs have been replaced by +inf by the caller.  Every column is sorted ascending.
 // v0: one compare-exchange per thread per step (bitonic network), __syncthreads between stages.

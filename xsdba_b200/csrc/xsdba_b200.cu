@@ -52,7 +52,8 @@ namespace {
 // =============================================================================================
 template <typename T, int C>
 __device__ void load_segment(T* sm, const T* __restrict__ src, long long n0, long long n_pts, long long sp,
-                             long long st, const int32_t* __restrict__ rows, int S, int n_pad) {
+                             long long st, const int32_t* __restrict__ rows, int S, int n_pad,
+                             const JitterParams* jp = nullptr, long long seg_base = 0) {
   const int total = n_pad * C;
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int r = idx / C;
@@ -61,6 +62,7 @@ __device__ void load_segment(T* sm, const T* __restrict__ src, long long n0, lon
     if (r < S && n0 + c < n_pts) {
       const int t = rows[r];
       if (t >= 0) v = src[(n0 + c) * sp + (long long)t * st];
+      if (jp) v = jitter_value<T>(v, *jp, (unsigned long long)((seg_base + r) * n_pts + n0 + c));
     }
     sm[idx] = v;
   }
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(kThreads)
 train_kernel(const T* __restrict__ ref, const T* __restrict__ hist, long long n_pts, long long sp, long long st,
              const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
              const T* __restrict__ q, int nq, int kind, int normalize, int mode, T* __restrict__ af,
-             T* __restrict__ hist_q, T* __restrict__ scaling, int n_pad) {
+             T* __restrict__ hist_q, T* __restrict__ scaling, int n_pad, JitterParams jp, int use_jitter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sum = reinterpret_cast<double*>(smem_raw);   // [C]
   double* mu_ref = sum + C;                            // [C]
@@ -147,7 +149,9 @@ train_kernel(const T* __restrict__ ref, const T* __restrict__ hist, long long n_
   const int n_pass = mode == 0 ? 2 : 1;
   for (int pass = 0; pass < n_pass; ++pass) {
     const T* src = pass == 0 ? ref : hist;
-    load_segment<T, C>(sm, src, n0, n_pts, sp, st, rows, S, n_pad);
+    // jitter applies to hist only, after the window gather (_adjustment.py:58-67, 80-81)
+    load_segment<T, C>(sm, src, n0, n_pts, sp, st, rows, S, n_pad, (use_jitter && pass == 1) ? &jp : nullptr,
+                       (long long)seg_off[g]);
     __syncthreads();
     count_columns<T, C>(sm, n_pad, cnt, sum, normalize != 0);
     make_keys<T, C>(sm, n_pad, cnt, sum, normalize, kind);
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(kFastThreads, 1)
 train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist, long long n_pts, long long st,
                   const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
                   const float* __restrict__ q, int nq, int kind, int normalize, int mode, float* __restrict__ af,
-                  float* __restrict__ hist_q, float* __restrict__ scaling) {
+                  float* __restrict__ hist_q, float* __restrict__ scaling, JitterParams jp, int use_jitter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* buf = reinterpret_cast<float*>(smem_raw + FastSmem::buf);
   int* rows_tab = reinterpret_cast<int*>(smem_raw + FastSmem::rows);
@@ -257,6 +261,12 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
     for (int i = 0; i < 32; ++i) {
       const int t = rows_tab[warp + 32 * i];
       v[i] = (t >= 0 && col_ok) ? src[(long long)t * st] : fnan;
+    }
+    if (use_jitter && pass == 1) {  // hist only, per window slot (_adjustment.py:58-67)
+      const long long seg_base = seg_off[g];
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        v[i] = jitter_value<float>(v[i], jp, (unsigned long long)((seg_base + warp + 32 * i) * n_pts + n0 + lane));
     }
     double my_sum = 0.0;
 #pragma unroll
@@ -1155,6 +1165,13 @@ copy_rows_kernel(const float* __restrict__ src, long long n_pts, long long st, c
   }
 }
 
+// elementwise jitter (processing.jitter / jitter_under_thresh / jitter_over_thresh, processing.py:124-257)
+template <typename T>
+__global__ void jitter_kernel(const T* __restrict__ x, long long n, JitterParams jp, T* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = jitter_value<T>(x[i], jp, (unsigned long long)i);
+}
+
 // =============================================================================================
 // host side
 // =============================================================================================
@@ -1182,14 +1199,14 @@ template <typename K> int set_smem(K kernel, size_t bytes) {
 template <typename T, int C>
 int launch_train_c(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
                    const T* q, int nq, int kind, int normalize, int mode, T* af, T* hq, T* scaling, int n_pad,
-                   cudaStream_t s) {
+                   cudaStream_t s, const JitterParams& jp, int use_jitter) {
   const size_t smem = (size_t)C * 24 + ((size_t)nq * C + (size_t)n_pad * C) * sizeof(T);
   auto kern = train_kernel<T, C>;
   int rc = set_smem(kern, smem);
   if (rc) return rc;
   dim3 grid((unsigned)((n_pts + C - 1) / C), (unsigned)grp->n_groups);
   kern<<<grid, kThreads, smem, s>>>(ref, hist, n_pts, sp, st, grp->segments.off, grp->segments.rows, grp->n_groups, q,
-                                    nq, kind, normalize, mode, af, hq, scaling, n_pad);
+                                    nq, kind, normalize, mode, af, hq, scaling, n_pad, jp, use_jitter);
   ++g_launches;
   return cuda_status(cudaGetLastError());
 }
@@ -1197,25 +1214,34 @@ int launch_train_c(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64
 // float32 / time-major / <= 1024-slot segments take the register-blocked kernel; returns false otherwise
 bool launch_train_fast(const float* ref, const float* hist, int64_t n_pts, int64_t sp, int64_t st,
                        const xsdba_grouping* grp, const float* q, int nq, int kind, int normalize, int mode, float* af,
-                       float* hq, float* scaling, cudaStream_t s, int* rc) {
+                       float* hq, float* scaling, cudaStream_t s, int* rc, const JitterParams& jp, int use_jitter) {
   if (sp != 1 || grp->segments.max_len > 1024 || nq > kFastMaxNq || getenv("XSDBA_B200_NO_FAST")) return false;
   const size_t smem = FastSmem::total(nq);
   *rc = set_smem(train_fast_kernel, smem);
   if (*rc) return true;
   dim3 grid((unsigned)((n_pts + 31) / 32), (unsigned)grp->n_groups);
   train_fast_kernel<<<grid, kFastThreads, smem, s>>>(ref, hist, n_pts, st, grp->segments.off, grp->segments.rows,
-                                                     grp->n_groups, q, nq, kind, normalize, mode, af, hq, scaling);
+                                                     grp->n_groups, q, nq, kind, normalize, mode, af, hq, scaling, jp,
+                                                     use_jitter);
   ++g_launches;
   *rc = cuda_status(cudaGetLastError());
   return true;
 }
 bool launch_train_fast(const double*, const double*, int64_t, int64_t, int64_t, const xsdba_grouping*, const double*,
-                       int, int, int, int, double*, double*, double*, cudaStream_t, int*) { return false; }
+                       int, int, int, int, double*, double*, double*, cudaStream_t, int*, const JitterParams&, int) {
+  return false;
+}
 
 template <typename T>
 int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
-                 const T* q, int nq, int kind, int normalize, int mode, T* af, T* hq, T* scaling, void* stream) {
+                 const T* q, int nq, int kind, int normalize, int mode, T* af, T* hq, T* scaling, void* stream,
+                 const double* jitter = nullptr, unsigned long long seed = 0) {
   int fast_rc = 0;
+  JitterParams jp;
+  const double dnan = __builtin_nan("");
+  jp.lower = jitter ? jitter[0] : dnan; jp.minimum = jitter ? jitter[1] : 0.0;
+  jp.upper = jitter ? jitter[2] : dnan; jp.maximum = jitter ? jitter[3] : 0.0; jp.seed = seed;
+  const int use_jitter = jitter && (jitter[0] == jitter[0] || jitter[2] == jitter[2]);
   if (!ref || !grp || !q || !af || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (mode == 0 && (!hist || !hq)) return XSDBA_ERR_INVALID_ARGUMENT;
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
@@ -1225,9 +1251,9 @@ int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t
   const int n_pad = std::max(2, next_pow2(grp->segments.max_len));
   const int C = pick_cols<T>(n_pad);
   cudaStream_t s = (cudaStream_t)stream;
-  if (launch_train_fast(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, s, &fast_rc))
+  if (launch_train_fast(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, s, &fast_rc, jp, use_jitter))
     return fast_rc;
-#define XS_CASE(CC) case CC: return launch_train_c<T, CC>(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, n_pad, s)
+#define XS_CASE(CC) case CC: return launch_train_c<T, CC>(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, n_pad, s, jp, use_jitter)
   switch (C) {
     XS_CASE(32); XS_CASE(16); XS_CASE(8); XS_CASE(4); XS_CASE(2); XS_CASE(1);
     default: return XSDBA_ERR_SEGMENT_TOO_LONG;
@@ -1452,6 +1478,16 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
   return cuda_status(cudaGetLastError());
 }
 
+template <typename T>
+int launch_jitter(const T* x, int64_t n, const double* j4, uint64_t seed, T* out, void* stream) {
+  if (!x || !out || !j4 || n < 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (n == 0) return XSDBA_OK;
+  JitterParams jp{j4[0], j4[1], j4[2], j4[3], seed};
+  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  jitter_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, jp, out);
+  ++g_launches;
+  return cuda_status(cudaGetLastError());
+}
 int upload_table(const std::vector<int32_t>& off, const std::vector<int32_t>& rows, DevTable& t) {
   XS_CUDA(cudaMalloc(&t.off, off.size() * sizeof(int32_t)));
   XS_CUDA(cudaMalloc(&t.rows, std::max<size_t>(rows.size(), 1) * sizeof(int32_t)));
@@ -1601,6 +1637,27 @@ int xsdba_group_rank_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, 
 int xsdba_group_rank_f64(const double* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
                          int32_t rank_window, double* rank, void* stream) {
   return launch_rank<double>(x, n_pts, sp, st, grp, nullptr, nullptr, 0, 0, 0, XSDBA_KIND_ADD, rank_window, 0, nullptr, rank, stream);
+}
+
+int xsdba_qm_train_jitter_f32(const float* ref, const float* hist, int64_t n_pts, int64_t sp, int64_t st,
+                              const xsdba_grouping_t* grp, const float* q, int32_t nq, int32_t kind, int32_t normalize,
+                              const double* jitter4_host, uint64_t seed, float* af, float* hq, float* scaling,
+                              void* stream) {
+  return launch_train<float>(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, 0, af, hq, scaling, stream,
+                             jitter4_host, seed);
+}
+int xsdba_qm_train_jitter_f64(const double* ref, const double* hist, int64_t n_pts, int64_t sp, int64_t st,
+                              const xsdba_grouping_t* grp, const double* q, int32_t nq, int32_t kind, int32_t normalize,
+                              const double* jitter4_host, uint64_t seed, double* af, double* hq, double* scaling,
+                              void* stream) {
+  return launch_train<double>(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, 0, af, hq, scaling, stream,
+                              jitter4_host, seed);
+}
+int xsdba_jitter_f32(const float* x, int64_t n, const double* j4, uint64_t seed, float* out, void* stream) {
+  return launch_jitter<float>(x, n, j4, seed, out, stream);
+}
+int xsdba_jitter_f64(const double* x, int64_t n, const double* j4, uint64_t seed, double* out, void* stream) {
+  return launch_jitter<double>(x, n, j4, seed, out, stream);
 }
 
 int xsdba_poly_trend_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
