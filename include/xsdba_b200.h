@@ -182,6 +182,46 @@ int xsdba_qm_train_adjust_host_f32(const float* ref_host, const float* hist_host
                                    int64_t slab_pts);
 
 /*
+ * MBCn / N-pdf transform building blocks (_npdft_train / _npdft_adjust / mbcn_adjust,
+ * _adjustment.py:289-328, 426-464, 467-591).  The per-iteration loop is host code
+ * (xsdba_b200/mbcn.py); every array op inside it is one of these kernels.
+ *  - xsdba_qm_train_q64_f32: eqm_train with float64 quantile nodes on float32 data -- _npdft_train calls
+ *    nbutils._quantile with the un-cast float64 nodes (_adjustment.py:315), so the virtual index uses them.
+ *  - xsdba_rank_lookup_*: xsdba_qdm_adjust_* with the rank normalisation selectable: rank_mode 0 =
+ *    utils.rank(pct=True) (utils.py:629-634), 1 = utils._rank_bn (utils.py:641-646), as used at
+ *    _adjustment.py:317-323, 453-459 (x + af looked up at the rank of x).
+ *  - xsdba_rotate_*: y[v] = sum_w rot[v][w] * x[w] over n_var stacked variables of n_elem elements each
+ *    (rot @ x, _adjustment.py:311, 449; rot_host is n_var x n_var float32 row-major, n_var <= 8; y != x).
+ *  - xsdba_standardize_*: (x - nanmean) / nanstd (ddof = 0) along time for every (variable, point)
+ *    (processing.standardize, processing.py:323-350; _adjustment.py:303-305); variables var_stride apart.
+ *  - xsdba_reorder_*: Schaake shuffle sort(sim)[argsort(argsort(ref))] per (point, group); with a window
+ *    the [time, window] segment is flattened and the centre column kept (_processing.py:204-211).
+ */
+int xsdba_qm_train_q64_f32(const float* ref_dev, const float* hist_dev, int64_t n_pts, int64_t stride_pt,
+                           int64_t stride_time, const xsdba_grouping_t* grp, const double* q64_dev, int32_t nq,
+                           int32_t kind, float* af_dev, float* hist_q_dev, void* cuda_stream);
+int xsdba_rank_lookup_f32(const float* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                          const xsdba_grouping_t* grp, const float* af_dev, const float* q_dev, int32_t nq,
+                          int32_t interp, int32_t extrap, int32_t kind, int32_t rank_window, int32_t rank_mode,
+                          float* out_dev, double* rank_dev, void* cuda_stream);
+int xsdba_rank_lookup_f64(const double* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                          const xsdba_grouping_t* grp, const double* af_dev, const double* q_dev, int32_t nq,
+                          int32_t interp, int32_t extrap, int32_t kind, int32_t rank_window, int32_t rank_mode,
+                          double* out_dev, double* rank_dev, void* cuda_stream);
+int xsdba_rotate_f32(const float* x_dev, int64_t n_elem, int32_t n_var, const float* rot_host, float* y_dev,
+                     void* cuda_stream);
+int xsdba_rotate_f64(const double* x_dev, int64_t n_elem, int32_t n_var, const float* rot_host, double* y_dev,
+                     void* cuda_stream);
+int xsdba_standardize_f32(const float* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                          int64_t n_time, int32_t n_var, int64_t var_stride, float* y_dev, void* cuda_stream);
+int xsdba_standardize_f64(const double* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                          int64_t n_time, int32_t n_var, int64_t var_stride, double* y_dev, void* cuda_stream);
+int xsdba_reorder_f32(const float* sim_dev, const float* ref_dev, int64_t n_pts, int64_t stride_pt,
+                      int64_t stride_time, const xsdba_grouping_t* grp, float* out_dev, void* cuda_stream);
+int xsdba_reorder_f64(const double* sim_dev, const double* ref_dev, int64_t n_pts, int64_t stride_pt,
+                      int64_t stride_time, const xsdba_grouping_t* grp, double* out_dev, void* cuda_stream);
+
+/*
  * Polynomial trend: replaces detrending.PolyDetrend.fit(...).ds.trend = _polydetrend_get_trend
  * (detrending.py:165-208; xarray polyfit/polyval per group through map_groups): y = x (+|*)
  * scaling[point][group] when scaling_dev != NULL (the scaled_sim of dqm_adjust, _adjustment.py:748-757),

@@ -136,6 +136,26 @@ def main():
                                                reg_func=rf, dx=dx, skipna=True)
         k += 1
 
+    # ---- N-pdf transform (_adjustment.py:289-328, 426-464): the two functions are pure numpy + nbutils +
+    # utils, so they are exec'ed from the reference's source text with the stub-loaded modules ------------
+    import ast
+    src = open(os.path.join(ref_loader.REF_SRC, "_adjustment.py")).read()
+    ns = {"np": np, "nbu": nbu, "u": u}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("_npdft_train", "_npdft_adjust"):
+            exec(compile(ast.Module([node], []), "_adjustment.py", "exec"), ns)
+    V, Tn, n_iter = 3, 500, 4
+    rots = np.stack([np.linalg.qr(rng.standard_normal((V, V)))[0] for _ in range(n_iter)]).astype(np.float32)
+    mk = lambda off: (rng.standard_normal((V, Tn)) * np.array([[3.0], [1.0], [7.0]]) + off).astype(np.float32)
+    ref, hist, sim = mk(0.0), mk(1.0), mk(1.5)
+    hist[1, 7] = np.nan
+    qn = u.equally_spaced_nodes(20)
+    af_q, _ = ns["_npdft_train"](ref.copy(), hist.copy(), rots, qn, "nearest", "constant", -1, True)
+    sim_std = ((sim - sim.mean(-1, keepdims=True)) / sim.std(-1, keepdims=True)).astype(np.float32)
+    adj = ns["_npdft_adjust"](sim_std.copy(), af_q, rots, qn, "nearest", "constant")
+    g["npdft_ref"], g["npdft_hist"], g["npdft_sim_std"], g["npdft_rots"], g["npdft_q"] = ref, hist, sim_std, rots, qn
+    g["npdft_af_q"], g["npdft_adjusted"] = af_q, adj
+
     np.savez_compressed(os.path.join(OUT, "reference_kernels.npz"), **g)
     sz = os.path.getsize(os.path.join(OUT, "reference_kernels.npz"))
     print(f"wrote {len(g)} arrays, {sz/1024:.0f} KiB")

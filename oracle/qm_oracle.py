@@ -217,7 +217,7 @@ def _fma(a, b, c, dtype):
     return _fma64(a, b, c)
 
 
-def nan_quantile(arr: np.ndarray, q: np.ndarray) -> np.ndarray:
+def nan_quantile(arr: np.ndarray, q: np.ndarray, cast_q: bool = True) -> np.ndarray:
     """Type-7 NaN-aware quantiles of each row of ``arr`` [rows, S] -> [rows, nq].
 
     Restates ``_nan_quantile_1d`` + ``_get_indexes`` + ``_linear_interpolation`` +
@@ -226,7 +226,9 @@ def nan_quantile(arr: np.ndarray, q: np.ndarray) -> np.ndarray:
     """
     arr = np.asarray(arr)
     dt = arr.dtype
-    q = np.asarray(q, dtype=dt)
+    # nbutils.quantile casts q to the data dtype (nbutils.py:253); direct _quantile callers
+    # (_npdft_train, _adjustment.py:315) pass float64 nodes un-cast
+    q = np.asarray(q, dtype=dt) if cast_q else np.asarray(q, dtype=np.float64)
     rows, S = arr.shape
     if S == 0:
         return np.full((rows, q.size), np.nan, dt)
@@ -796,3 +798,114 @@ def dqm_adjust(sim, af, hist_q, scaling, *, group, window, time, interp, extrapo
     scen = apply_correction(detr, afi, kind)                         # qm_adjust.func, _adjustment.py:669
     scen = apply_correction(scen, trend, kind)                       # detrending.py:120
     return scen, trend
+
+
+# ----------------------------------------------------------------------------------------------
+# MBCn / N-pdf transform  (_adjustment.py:289-591; processing.py:323-350, 829-918; _processing.py:184-247)
+# ----------------------------------------------------------------------------------------------
+
+def rand_rot_matrices(n_var: int, n_iter: int, seed: int) -> np.ndarray:
+    """``utils.rand_rot_matrix`` recipe (utils.py:961-973; Mezzadri 2007) with a seeded generator:
+    float32 [n_iter, V, V]."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((n_iter, n_var, n_var), np.float32)
+    for i in range(n_iter):
+        Z = rng.standard_normal((n_var, n_var))
+        Q, R = np.linalg.qr(Z)
+        num = np.diag(R)
+        out[i] = (Q @ np.diag(num / np.abs(num))).astype(np.float32)
+    return out
+
+
+def mbcn_blocks(time: TimeAxis, group: str, window: int):
+    """``grouped_time_indexes`` (processing.py:829-918) for "time" and "time.dayofyear": per block the
+    windowed time indices (sorted, out-of-range dropped) and the exact-group indices."""
+    T = len(time)
+    if group == "time":
+        return [(np.arange(T), np.arange(T))]
+    gidx, G, _ = group_index(time, group)
+    half = window // 2
+    out = []
+    for g in range(G):
+        sel = np.nonzero(gidx == g)[0]
+        if sel.size == 0:
+            continue
+        w = (sel[:, None] - half + np.arange(window)[None, :]).ravel()
+        w = w[(w >= 0) & (w < T)]
+        out.append((w, sel))
+    return out
+
+
+def _standardize(x):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return ((x - np.nanmean(x, axis=-1, keepdims=True)) / np.nanstd(x, axis=-1, keepdims=True)).astype(x.dtype)
+
+
+def npdft_train(ref, hist, rots, quantiles, method="nearest", extrap="constant"):
+    """``_npdft_train`` (_adjustment.py:289-328) without escores: ref, hist [V, T] -> af_q [n_iter, V, nq]."""
+    ref = _standardize(ref)
+    hist = _standardize(hist)
+    quantiles = np.asarray(quantiles, np.float64)
+    af_q = np.zeros((len(rots), ref.shape[0], len(quantiles)))
+    for ii, _rot in enumerate(rots):
+        rot = _rot if ii == 0 else _rot @ rots[ii - 1].T
+        ref, hist = rot @ ref, rot @ hist
+        for iv in range(ref.shape[0]):
+            ref_q = nan_quantile(ref[iv][None, :], quantiles, cast_q=False)[0]
+            hist_q = nan_quantile(hist[iv][None, :], quantiles, cast_q=False)[0]
+            af_q[ii, iv] = ref_q - hist_q
+            af = interp_on_quantiles_1d(rank_bn(hist[iv]), quantiles, af_q[ii, iv], method, extrap)
+            hist[iv] = hist[iv] + af
+    return af_q
+
+
+def npdft_adjust(sim, af_q, rots, quantiles, method="nearest", extrap="constant"):
+    """``_npdft_adjust`` (_adjustment.py:426-464): sim [V, T] (already standardized) -> [V, T]."""
+    sim = sim.copy()[:, np.newaxis, :]  # the reference adds a dummy period dim (_adjustment.py:441-442)
+    quantiles = np.asarray(quantiles, np.float64)
+    for ii, _rot in enumerate(rots):
+        rot = _rot if ii == 0 else _rot @ rots[ii - 1].T
+        sim = np.einsum("ij,j...->i...", rot, sim)  # (einsum, not matmul: the float32 summation order differs)
+        for iv in range(sim.shape[0]):
+            af = interp_on_quantiles_1d(rank_bn(sim[iv, 0]), quantiles, af_q[ii, iv], method, extrap)
+            sim[iv, 0] = sim[iv, 0] + af
+    return np.einsum("ij,j...->i...", rots[-1].T, sim)[:, 0, :]
+
+
+def reordering_1d(data, ordr):
+    """_processing.py:204-205."""
+    return np.sort(data)[np.argsort(np.argsort(ordr, kind="stable"), kind="stable")]
+
+
+def mbcn_train(ref, hist, rots, quantiles, blocks, method="nearest", extrap="constant"):
+    """``mbcn_train`` (_adjustment.py:385-421): ref, hist [V, N, T] -> af_q [n_blocks, N, n_iter, V, nq] (data dtype)."""
+    V, N, T = ref.shape
+    out = np.empty((len(blocks), N, len(rots), V, len(quantiles)), ref.dtype)
+    for ib, (gw, _) in enumerate(blocks):
+        for i in range(N):
+            out[ib, i] = npdft_train(ref[:, i, gw].copy(), hist[:, i, gw].copy(), rots, quantiles, method, extrap)
+    return out
+
+
+def mbcn_adjust(ref, hist, sim, af_q, rots, quantiles, blocks, kinds, method="nearest", extrap="constant"):
+    """``mbcn_adjust`` (_adjustment.py:528-591) with base = QuantileDeltaMapping(group="time"): [V, N, T]."""
+    V, N, T = sim.shape
+    dt = sim.dtype
+    q_dt = np.asarray(quantiles).astype(dt)   # QDM._train casts the nodes (adjustment.py:480-483)
+    scen = np.zeros_like(sim)
+    for ib, (gw, g) in enumerate(blocks):
+        keep = np.isin(gw, g)
+        for i in range(N):
+            scen_block = np.empty((V, gw.size), dt)
+            for v in range(V):
+                r, h, s_ = ref[v, i, gw][None], hist[v, i, gw][None], sim[v, i, gw][None]
+                af, _ = eqm_train(r, h, np.zeros(gw.size, np.int32), 1, 1, q_dt, kinds[v])
+                sq = rank_pct(s_)
+                afi = interp_on_quantiles_1d(sq[0], q_dt, af[0, 0], method, extrap)
+                scen_block[v] = apply_correction(s_[0], afi.astype(dt), kinds[v])
+            npdft_block = npdft_adjust(_standardize(sim[:, i, gw]), af_q[ib, i].astype(np.float64), rots, quantiles,
+                                       method, extrap)
+            for v in range(V):
+                scen[v, i, g] = reordering_1d(scen_block[v], npdft_block[v])[keep]
+    return scen

@@ -54,8 +54,9 @@ def load():
         raise NotImplementedError("xarray.apply_ufunc stub: call the raw kernel instead")
 
     def _nanrankdata(arr, axis=None):
-        # bottleneck.nanrankdata stand-in: average ties, NaN -> NaN
-        return rankdata(arr, method="average", axis=axis, nan_policy="omit")
+        # bottleneck.nanrankdata stand-in: average ties, NaN -> NaN, ALWAYS float64 (bottleneck's
+        # documented return dtype; scipy keeps float32 for float32 input with NaNs)
+        return np.asarray(rankdata(arr, method="average", axis=axis, nan_policy="omit"), dtype=np.float64)
 
     xr = _mod("xarray", DataArray=_DataArray, Dataset=_Dataset, apply_ufunc=_apply_ufunc)
     core = _mod("xarray.core")

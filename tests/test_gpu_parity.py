@@ -333,3 +333,49 @@ def test_train_with_jitter_matches_oracle_statistically():
     np.testing.assert_allclose(hq, hq_o, atol=2e-3, rtol=0.02)   # nodes inside the jittered range are random
     wet = hq_o > 0.02
     np.testing.assert_array_equal(hq[wet], hq_o[wet])            # above the threshold nothing changes
+
+
+def _mbcn_inputs(years, N, seed=0):
+    rng = np.random.default_rng(seed)
+    to = o.daily_time_axis(1981, years, "noleap")
+    mk = lambda w: np.stack([synth.tas(rng, to, N, w, nan_frac=0), synth.pr(rng, to, N, w, nan_frac=0),
+                             synth.tas(rng, to, N, w, nan_frac=0) + 2]).astype(np.float32)  # (V, T, N)
+    return to, mk("ref"), mk("hist"), mk("sim")
+
+
+def test_npdft_reference_golden(golden):
+    """The CUDA N-pdf training against the reference's own _npdft_train output (tests/golden): the float32
+    rotation (FMA chain here, BLAS sgemm there) is the only unpinned arithmetic -> 2e-5 absolute on O(1) factors."""
+    xs = _xs()
+    ref, hist, rots, q = golden["npdft_ref"], golden["npdft_hist"], golden["npdft_rots"], golden["npdft_q"]
+    t = xs.TimeAxis.daily(2001, 2, "noleap")[: ref.shape[1]]
+    af_q = _np(xs.mbcn_train(ref[:, :, None], hist[:, :, None], time=t, rot_matrices=rots, quantiles=q, group="time"))
+    np.testing.assert_allclose(af_q[0, 0], golden["npdft_af_q"], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("group,window,years,n_iter", [("time", 1, 2, 4), ("time.dayofyear", 5, 2, 2)])
+def test_mbcn_matches_oracle(group, window, years, n_iter):
+    xs = _xs()
+    N = 3
+    to, ref, hist, sim = _mbcn_inputs(years, N)
+    tx = xs.TimeAxis.daily(1981, years, "noleap")
+    rots = o.rand_rot_matrices(3, n_iter, 7)
+    q = o.equally_spaced_nodes(10)
+    kinds = ["+", "*", "+"]
+    blocks = o.mbcn_blocks(to, group, window)
+    tr = lambda a: np.ascontiguousarray(a.transpose(0, 2, 1))           # oracle layout (V, N, T)
+    afq_o = o.mbcn_train(tr(ref), tr(hist), rots, q, blocks)
+    scen_o = o.mbcn_adjust(tr(ref), tr(hist), tr(sim), afq_o, rots, q, blocks, kinds)
+    obj = xs.MBCn.train(ref, hist, time=tx, base_kws={"nquantiles": q, "group": xs.Grouper(group, window)}, n_iter=n_iter,
+                        rot_matrices=rots)
+    afq = _np(obj.ds["af_q"])                                           # (blocks, N, n_iter, V, nq)
+    assert afq.shape == afq_o.shape
+    close = np.isclose(afq, afq_o, rtol=0, atol=5e-5)
+    assert close.mean() > 0.995, close.mean()
+    scen = tr(_np(obj.adjust(sim, ref, hist, time=tx, kinds=kinds)))
+    # the shuffle only permutes univariate-QDM values: the multiset per (variable, point) must match the oracle's
+    # wherever blocks do not overlap, and most samples land on the same rank
+    same = np.isclose(scen, scen_o, rtol=1e-5, atol=1e-6)
+    assert same.mean() > 0.98, same.mean()
+    if group == "time":
+        np.testing.assert_allclose(np.sort(scen, axis=-1), np.sort(scen_o, axis=-1), rtol=1e-6, atol=1e-6)

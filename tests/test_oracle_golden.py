@@ -122,3 +122,19 @@ def test_window_gather_reference_kat():
     gidx = np.array([0, 1, 2, 3, 0, 1, 2, 3])
     seg = o.group_segment(y[None, :], gidx, 0, 3)[0]
     np.testing.assert_array_equal(seg, [np.nan, 8, 7, 5, 4, 3])
+
+
+def test_npdft_vs_reference(golden):
+    """oracle npdft_train / npdft_adjust against the reference's own _npdft_train / _npdft_adjust
+    (exec'ed from its source by oracle/gen_golden.py): bit-exact."""
+    af = o.npdft_train(golden["npdft_ref"].copy(), golden["npdft_hist"].copy(), golden["npdft_rots"], golden["npdft_q"])
+    assert np.array_equal(af, golden["npdft_af_q"], equal_nan=True)
+    adj = o.npdft_adjust(golden["npdft_sim_std"].copy(), golden["npdft_af_q"], golden["npdft_rots"], golden["npdft_q"])
+    assert bits_equal(adj, golden["npdft_adjusted"])
+
+
+def test_reordering_reference_kat():
+    # reference tests/test_processing.py:248-257: x = 1..8 reordered by the ranks of y = 8..1 -> reversed
+    x = np.arange(1, 9).astype(float)
+    y = np.arange(8, 0, -1).astype(float)
+    np.testing.assert_array_equal(o.reordering_1d(x, y), x[::-1])

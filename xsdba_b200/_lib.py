@@ -47,7 +47,12 @@ for _t in ("f32", "f64"):
     SIGNATURES[f"xsdba_poly_trend_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, i32, i32, vp, vp, vp])
     SIGNATURES[f"xsdba_loess_trend_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, i32, C.c_double, i32, i32, vp, vp, vp])
     SIGNATURES[f"xsdba_dqm_adjust_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp])
+    SIGNATURES[f"xsdba_rank_lookup_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp])
+    SIGNATURES[f"xsdba_rotate_{_t}"] = (C.c_int, [vp, i64, i32, c_f32p, vp, vp])
+    SIGNATURES[f"xsdba_standardize_{_t}"] = (C.c_int, [vp, i64, i64, i64, i64, i32, i64, vp, vp])
+    SIGNATURES[f"xsdba_reorder_{_t}"] = (C.c_int, [vp, vp, i64, i64, i64, vp, vp, vp])
     SIGNATURES[f"xsdba_group_rank_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, i32, vp, vp])
+SIGNATURES["xsdba_qm_train_q64_f32"] = (C.c_int, [vp, vp, i64, i64, i64, vp, vp, i32, i32, vp, vp, vp])
 SIGNATURES["xsdba_debug_copy_rows_f32"] = (C.c_int, [vp, i64, i64, vp, vp, i32, vp])
 SIGNATURES["xsdba_qm_train_adjust_host_f32"] = (
     C.c_int, [vp, vp, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, i64])

@@ -106,8 +106,8 @@ __device__ __forceinline__ T sorted_at(const T* col, long long i, int n, int S) 
 // Type-7 quantile of one sorted column: _nan_quantile_1d + _get_indexes + _linear_interpolation
 // (nbutils.py:24-148).  col points at sm[0*C + c]; n = number of valid values; S = segment length.
 template <typename T, int C>
-__device__ __forceinline__ T quantile_sorted(const T* col, int n, int S, T qk) {
-  const double vi = (double)(n - 1) * (double)qk;   // nbutils.py:131
+__device__ __forceinline__ T quantile_sorted(const T* col, int n, int S, double qk) {
+  const double vi = (double)(n - 1) * qk;   // nbutils.py:131
   long long prev = (long long)floor(vi);
   long long next = prev + 1;
   if (vi >= (double)(n - 1)) { prev = -1; next = -1; }  // nbutils.py:47-51

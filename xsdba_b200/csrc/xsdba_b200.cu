@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(kThreads)
 train_kernel(const T* __restrict__ ref, const T* __restrict__ hist, long long n_pts, long long sp, long long st,
              const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
              const T* __restrict__ q, int nq, int kind, int normalize, int mode, T* __restrict__ af,
-             T* __restrict__ hist_q, T* __restrict__ scaling, int n_pad, JitterParams jp, int use_jitter) {
+             T* __restrict__ hist_q, T* __restrict__ scaling, int n_pad, JitterParams jp, int use_jitter,
+             const double* __restrict__ q64) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sum = reinterpret_cast<double*>(smem_raw);   // [C]
   double* mu_ref = sum + C;                            // [C]
@@ -159,7 +160,7 @@ train_kernel(const T* __restrict__ ref, const T* __restrict__ hist, long long n_
     // quantiles: item -> (point c, node k), k fastest so that global writes are contiguous
     for (int item = threadIdx.x; item < C * nq; item += blockDim.x) {
       const int c = item / nq, k = item % nq;
-      const T v = quantile_sorted<T, C>(sm + c, cnt[c], S, q[k]);
+      const T v = quantile_sorted<T, C>(sm + c, cnt[c], S, q64 ? q64[k] : (double)q[k]);
       if (mode == 1) {
         if (n0 + c < n_pts) af[(n0 + c) * out_stride + (long long)g * nq + k] = v;
       } else if (pass == 0) {
@@ -201,8 +202,8 @@ struct FastSmem {
   static constexpr size_t psum = pcnt + 32 * 32 * 4;                // double[32][32]
   static constexpr size_t cnt = psum + 32 * 32 * 8;                 // int   [2][32]
   static constexpr size_t mu = cnt + 2 * 32 * 4;                    // float [2][32]  (ref, hist means)
-  static constexpr size_t q = mu + 2 * 32 * 4;                      // float [kFastMaxNq]
-  static constexpr size_t refq = q + kFastMaxNq * 4;                // float [nq][33]
+  static constexpr size_t q = mu + 2 * 32 * 4;                      // double[kFastMaxNq]
+  static constexpr size_t refq = q + kFastMaxNq * 8;                // float [nq][33]
   static __host__ __device__ constexpr size_t total(int nq) { return refq + (size_t)3 * nq * 33 * 4; }
 };
 
@@ -210,7 +211,8 @@ __global__ void __launch_bounds__(kFastThreads, 1)
 train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist, long long n_pts, long long st,
                   const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
                   const float* __restrict__ q, int nq, int kind, int normalize, int mode, float* __restrict__ af,
-                  float* __restrict__ hist_q, float* __restrict__ scaling, JitterParams jp, int use_jitter) {
+                  float* __restrict__ hist_q, float* __restrict__ scaling, JitterParams jp, int use_jitter,
+                  const double* __restrict__ q64) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* buf = reinterpret_cast<float*>(smem_raw + FastSmem::buf);
   int* rows_tab = reinterpret_cast<int*>(smem_raw + FastSmem::rows);
@@ -218,7 +220,7 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
   double* psum = reinterpret_cast<double*>(smem_raw + FastSmem::psum);
   int* cnt = reinterpret_cast<int*>(smem_raw + FastSmem::cnt);
   float* mu = reinterpret_cast<float*>(smem_raw + FastSmem::mu);
-  float* qs = reinterpret_cast<float*>(smem_raw + FastSmem::q);
+  double* qs = reinterpret_cast<double*>(smem_raw + FastSmem::q);
   float* refq = reinterpret_cast<float*>(smem_raw + FastSmem::refq);
   float* outh = refq + (size_t)nq * 33;
   float* outa = outh + (size_t)nq * 33;
@@ -245,7 +247,7 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
   {
     const int32_t* rows = seg_rows + seg_off[g];
     rows_tab[tid] = tid < S ? rows[tid] : -1;
-    if (tid < nq) qs[tid] = q[tid];
+    if (tid < nq) qs[tid] = q64 ? q64[tid] : (double)q[tid];
   }
   __syncthreads();
 
@@ -314,7 +316,7 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
         const float amax = nA > 0 ? A[(size_t)(nA - 1) * 32] : -finf;
         const float bmax = nB > 0 ? B[(size_t)(nB - 1) * 32] : -finf;
         const float vmax = fmaxf(amax, bmax);
-        const double vi = (double)(n - 1) * (double)qs[k];  // nbutils.py:131
+        const double vi = (double)(n - 1) * qs[k];  // nbutils.py:131
         float left, right, gamma;
         if (vi >= (double)(n - 1)) {  // nbutils.py:47-51: position -1 of the full-length sorted row
           left = right = (n < S) ? fnan : vmax;
@@ -1066,7 +1068,7 @@ rank_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long 
             const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows,
             const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
             const T* __restrict__ af, const T* __restrict__ q, int nq, int interp, int extrap, int kind,
-            int do_adjust, T* __restrict__ scen, double* __restrict__ sim_q, int n_pad) {
+            int do_adjust, T* __restrict__ scen, double* __restrict__ sim_q, int n_pad, int rank_mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* mnmx = reinterpret_cast<double*>(smem_raw);      // [2][C]
   double* sum = mnmx + 2 * C;                              // [C] (unused sum slot of count_columns)
@@ -1100,10 +1102,19 @@ rank_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long 
       const T vmin = col[0], vmax = col[(size_t)(n - 1) * C];
       int ub = 1; while (ub < n && col[(size_t)ub * C] == vmin) ++ub;          // multiplicity of the minimum
       int lb = n - 1; while (lb > 0 && col[(size_t)(lb - 1) * C] == vmax) --lb;  // first index of the maximum
-      mn = ((double)(ub + 1) * 0.5) / (double)n;          // avg rank of ranks 1..ub
-      mx = ((double)(lb + n + 1) * 0.5) / (double)n;      // avg rank of ranks lb+1..n
+      // rank_mode 0: utils.rank(pct=True): r = avgrank / n_valid        (utils.py:629-634)
+      // rank_mode 1: utils._rank_bn:          r = avgrank / max(avgrank)  (utils.py:641-646)
+      const double den = rank_mode == 0 ? (double)n : (double)(lb + n + 1) * 0.5;
+      mn = ((double)(ub + 1) * 0.5) / den;                // avg rank of ranks 1..ub
+      mx = ((double)(lb + n + 1) * 0.5) / den;            // avg rank of ranks lb+1..n
     }
     mnmx[c] = mn; mnmx[C + c] = mx;
+    if (n > 0) {  // (re-derive the maximum average rank for _rank_bn; sum[] is free after count_columns)
+      const T* col = sm + c;
+      const T vmax = col[(size_t)(n - 1) * C];
+      int lb = n - 1; while (lb > 0 && col[(size_t)(lb - 1) * C] == vmax) --lb;
+      sum[c] = (double)(lb + n + 1) * 0.5;
+    }
   }
   __syncthreads();
 
@@ -1125,9 +1136,14 @@ rank_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long 
       hi = n;              // upper bound: #values <= x
       while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[(size_t)mid * C] <= x) lo = mid + 1; else hi = mid; }
       const int ub = lo;
-      const double r = ((double)(lb + ub + 1) * 0.5) / (double)n;
       const double mn = mnmx[c], mx = mnmx[C + c];
-      sq = __ddiv_rn(__dmul_rn(mx, __dsub_rn(r, mn)), __dsub_rn(mx, mn));
+      if (rank_mode == 0) {
+        const double r = ((double)(lb + ub + 1) * 0.5) / (double)n;
+        sq = __ddiv_rn(__dmul_rn(mx, __dsub_rn(r, mn)), __dsub_rn(mx, mn));
+      } else {  // _rank_bn: rnk / nanmax(rnk), then 1 * (rnk - mn) / (1 - mn)
+        const double r = ((double)(lb + ub + 1) * 0.5) / sum[c];
+        sq = __ddiv_rn(__dsub_rn(r, mn), __dsub_rn(1.0, mn));
+      }
     }
     if (sim_q) sim_q[o] = sq;
     if (do_adjust) {
@@ -1165,6 +1181,120 @@ copy_rows_kernel(const float* __restrict__ src, long long n_pts, long long st, c
   }
 }
 
+// =============================================================================================
+// K7: MBCn / N-pdf transform helpers (_adjustment.py:289-328, 426-464; processing.py:323-350;
+// _processing.py:184-247).
+//   rotate_kernel      y[v][e] = sum_w R[v][w] x[w][e]   (rot @ x, _adjustment.py:311, 449; V <= 8)
+//   standardize_kernel (x - nanmean) / nanstd(ddof=0) along time per (variable, point)
+//   reorder_kernel     Schaake shuffle  sort(sim)[argsort(argsort(ref))]  per (point, group), window
+//                      segments flattened and the centre column kept (_processing.py:204-211)
+// =============================================================================================
+constexpr int kMaxVar = 8;
+struct RotMat { float r[kMaxVar * kMaxVar]; };
+
+template <typename T>
+__global__ void rotate_kernel(const T* __restrict__ x, long long n_elem, int n_var, RotMat R, T* __restrict__ y) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_elem; e += (long long)gridDim.x * blockDim.x) {
+    T in[kMaxVar];
+#pragma unroll
+    for (int w = 0; w < kMaxVar; ++w) if (w < n_var) in[w] = x[(long long)w * n_elem + e];
+#pragma unroll
+    for (int v = 0; v < kMaxVar; ++v) {
+      if (v >= n_var) break;
+      T acc = (T)0;
+#pragma unroll
+      for (int w = 0; w < kMaxVar; ++w) if (w < n_var) acc = Num<T>::fma((T)R.r[v * kMaxVar + w], in[w], acc);
+      y[(long long)v * n_elem + e] = acc;
+    }
+  }
+}
+
+// one thread per (variable, point): two passes over time (mean, then variance), float64 accumulation
+template <typename T>
+__global__ void standardize_kernel(const T* __restrict__ x, long long n_pts, long long sp, long long st, int n_time,
+                                   int n_var, long long var_stride, T* __restrict__ y) {
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_pts * n_var) return;
+  const long long pt = id % n_pts;
+  const int v = (int)(id / n_pts);
+  const T* xv = x + v * var_stride + pt * sp;
+  T* yv = y + v * var_stride + pt * sp;
+  double s = 0; int n = 0;
+  for (int t = 0; t < n_time; ++t) { const T a = xv[(long long)t * st]; if (!is_nan(a)) { s += (double)a; ++n; } }
+  const T mean = (T)(s / (double)n);
+  double ss = 0;
+  for (int t = 0; t < n_time; ++t) {
+    const T a = xv[(long long)t * st];
+    if (!is_nan(a)) { const double d = (double)(T)(a - mean); ss += d * d; }
+  }
+  const T sd = (T)sqrt(ss / (double)n);
+  for (int t = 0; t < n_time; ++t) yv[(long long)t * st] = Num<T>::div(Num<T>::sub(xv[(long long)t * st], mean), sd);
+}
+
+// ordinal rank of every segment slot of `ref` (ties by slot order, NaNs last) and the sorted `sim`
+// segment; member m (its centre slot) receives sorted_sim[rank(centre slot)].
+template <typename T, int C>
+__global__ void __launch_bounds__(kThreads)
+reorder_kernel(const T* __restrict__ sim, const T* __restrict__ ref, long long n_pts, long long sp, long long st,
+               const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows,
+               const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int window, int n_pad,
+               T* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sum = reinterpret_cast<double*>(smem_raw);
+  int* cnt = reinterpret_cast<int*>(sum + C);
+  T* sref = reinterpret_cast<T*>(smem_raw + C * 16);      // sorted ref keys [n_pad][C]
+  T* ssim = sref + (size_t)n_pad * C;                     // sorted sim keys [n_pad][C]
+  const int g = blockIdx.y;
+  const long long n0 = (long long)blockIdx.x * C;
+  const int m0 = mem_off[g], n_mem = mem_off[g + 1] - m0;
+  if (n_mem == 0) return;
+  const int S = seg_off[g + 1] - seg_off[g];
+  const int32_t* rows = seg_rows + seg_off[g];
+  load_segment<T, C>(sref, ref, n0, n_pts, sp, st, rows, S, n_pad);
+  load_segment<T, C>(ssim, sim, n0, n_pts, sp, st, rows, S, n_pad);
+  __syncthreads();
+  count_columns<T, C>(sref, n_pad, cnt, sum, false);
+  make_keys<T, C>(sref, n_pad, cnt, sum, 0, XSDBA_KIND_ADD);
+  make_keys<T, C>(ssim, n_pad, cnt, sum, 0, XSDBA_KIND_ADD);
+  sort_columns<T, C>(sref, n_pad);
+  sort_columns<T, C>(ssim, n_pad);
+  const int half = window / 2;
+  for (int item = threadIdx.x; item < n_mem * C; item += blockDim.x) {
+    const int c = item % C, m = item / C;
+    const long long pt = n0 + c;
+    if (pt >= n_pts) continue;
+    const int slot = m * window + half;                   // centre column of member m
+    const int t = mem_rows[m0 + m];
+    const long long o = pt * sp + (long long)t * st;
+    T key = ref[o];
+    const bool key_nan = is_nan(key);
+    if (key_nan) key = Num<T>::inf();
+    const T* col = sref + c;
+    int lo = 0, hi = S;  // #keys < key over the whole padded segment (NaN keys are +inf: sorted last)
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[(size_t)mid * C] < key) lo = mid + 1; else hi = mid; }
+    int rank = lo;
+    // ties (and NaNs): np.argsort orders equal keys by position -> count equal keys in earlier slots
+    if (lo + 1 < S && col[(size_t)(lo + 1) * C] == key) {
+      for (int s2 = 0; s2 < slot; ++s2) {
+        const int t2 = rows[s2];
+        T k2 = t2 >= 0 ? ref[pt * sp + (long long)t2 * st] : Num<T>::nan();
+        if (is_nan(k2)) k2 = Num<T>::inf();
+        if (k2 == key) ++rank;
+      }
+    }
+    const T v = ssim[(size_t)rank * C + c];
+    // np.sort puts NaNs last: sorted positions >= (#valid sim) are NaN
+    int n_sim = 0;  // (#valid sim values: keys below +inf; genuine +inf values are kept as they are)
+    {
+      int l2 = 0, h2 = S; const T inf = Num<T>::inf();
+      const T* cs = ssim + c;
+      while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (cs[(size_t)mid * C] < inf) l2 = mid + 1; else h2 = mid; }
+      n_sim = l2;
+    }
+    out[o] = (rank >= n_sim && v == Num<T>::inf()) ? Num<T>::nan() : v;
+  }
+}
+
 // elementwise jitter (processing.jitter / jitter_under_thresh / jitter_over_thresh, processing.py:124-257)
 template <typename T>
 __global__ void jitter_kernel(const T* __restrict__ x, long long n, JitterParams jp, T* __restrict__ out) {
@@ -1199,14 +1329,14 @@ template <typename K> int set_smem(K kernel, size_t bytes) {
 template <typename T, int C>
 int launch_train_c(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
                    const T* q, int nq, int kind, int normalize, int mode, T* af, T* hq, T* scaling, int n_pad,
-                   cudaStream_t s, const JitterParams& jp, int use_jitter) {
+                   cudaStream_t s, const JitterParams& jp, int use_jitter, const double* q64) {
   const size_t smem = (size_t)C * 24 + ((size_t)nq * C + (size_t)n_pad * C) * sizeof(T);
   auto kern = train_kernel<T, C>;
   int rc = set_smem(kern, smem);
   if (rc) return rc;
   dim3 grid((unsigned)((n_pts + C - 1) / C), (unsigned)grp->n_groups);
   kern<<<grid, kThreads, smem, s>>>(ref, hist, n_pts, sp, st, grp->segments.off, grp->segments.rows, grp->n_groups, q,
-                                    nq, kind, normalize, mode, af, hq, scaling, n_pad, jp, use_jitter);
+                                    nq, kind, normalize, mode, af, hq, scaling, n_pad, jp, use_jitter, q64);
   ++g_launches;
   return cuda_status(cudaGetLastError());
 }
@@ -1214,7 +1344,8 @@ int launch_train_c(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64
 // float32 / time-major / <= 1024-slot segments take the register-blocked kernel; returns false otherwise
 bool launch_train_fast(const float* ref, const float* hist, int64_t n_pts, int64_t sp, int64_t st,
                        const xsdba_grouping* grp, const float* q, int nq, int kind, int normalize, int mode, float* af,
-                       float* hq, float* scaling, cudaStream_t s, int* rc, const JitterParams& jp, int use_jitter) {
+                       float* hq, float* scaling, cudaStream_t s, int* rc, const JitterParams& jp, int use_jitter,
+                       const double* q64) {
   if (sp != 1 || grp->segments.max_len > 1024 || nq > kFastMaxNq || getenv("XSDBA_B200_NO_FAST")) return false;
   const size_t smem = FastSmem::total(nq);
   *rc = set_smem(train_fast_kernel, smem);
@@ -1222,20 +1353,21 @@ bool launch_train_fast(const float* ref, const float* hist, int64_t n_pts, int64
   dim3 grid((unsigned)((n_pts + 31) / 32), (unsigned)grp->n_groups);
   train_fast_kernel<<<grid, kFastThreads, smem, s>>>(ref, hist, n_pts, st, grp->segments.off, grp->segments.rows,
                                                      grp->n_groups, q, nq, kind, normalize, mode, af, hq, scaling, jp,
-                                                     use_jitter);
+                                                     use_jitter, q64);
   ++g_launches;
   *rc = cuda_status(cudaGetLastError());
   return true;
 }
 bool launch_train_fast(const double*, const double*, int64_t, int64_t, int64_t, const xsdba_grouping*, const double*,
-                       int, int, int, int, double*, double*, double*, cudaStream_t, int*, const JitterParams&, int) {
+                       int, int, int, int, double*, double*, double*, cudaStream_t, int*, const JitterParams&, int,
+                       const double*) {
   return false;
 }
 
 template <typename T>
 int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
                  const T* q, int nq, int kind, int normalize, int mode, T* af, T* hq, T* scaling, void* stream,
-                 const double* jitter = nullptr, unsigned long long seed = 0) {
+                 const double* jitter = nullptr, unsigned long long seed = 0, const double* q64 = nullptr) {
   int fast_rc = 0;
   JitterParams jp;
   const double dnan = __builtin_nan("");
@@ -1251,9 +1383,9 @@ int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t
   const int n_pad = std::max(2, next_pow2(grp->segments.max_len));
   const int C = pick_cols<T>(n_pad);
   cudaStream_t s = (cudaStream_t)stream;
-  if (launch_train_fast(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, s, &fast_rc, jp, use_jitter))
+  if (launch_train_fast(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, s, &fast_rc, jp, use_jitter, q64))
     return fast_rc;
-#define XS_CASE(CC) case CC: return launch_train_c<T, CC>(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, n_pad, s, jp, use_jitter)
+#define XS_CASE(CC) case CC: return launch_train_c<T, CC>(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, n_pad, s, jp, use_jitter, q64)
   switch (C) {
     XS_CASE(32); XS_CASE(16); XS_CASE(8); XS_CASE(4); XS_CASE(2); XS_CASE(1);
     default: return XSDBA_ERR_SEGMENT_TOO_LONG;
@@ -1368,7 +1500,7 @@ int launch_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsd
 template <typename T, int C>
 int launch_rank_c(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
                   const DevTable& seg, const T* af, const T* q, int nq, int interp, int extrap, int kind,
-                  int do_adjust, T* scen, double* sim_q, int n_pad, cudaStream_t s) {
+                  int do_adjust, T* scen, double* sim_q, int n_pad, cudaStream_t s, int rank_mode) {
   const size_t head = (size_t)C * 28 + (((size_t)C * 28) % 8 ? 4 : 0);
   const size_t smem = head + (size_t)n_pad * C * sizeof(T) +
                       (do_adjust ? ((tables_bytes<T, C>(nq) + 15) & ~(size_t)15) + stage_bytes<T, C>(nq) : tables_bytes<T, C>(0));
@@ -1379,7 +1511,7 @@ int launch_rank_c(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsd
   dim3 grid((unsigned)((n_pts + C - 1) / C), (unsigned)grp->n_groups);
   kern<<<grid, kThreads, smem, s>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows, seg.off, seg.rows,
                                     grp->n_groups, af, q, do_adjust ? nq : 0, interp, extrap, kind, do_adjust, scen,
-                                    sim_q, n_pad);
+                                    sim_q, n_pad, rank_mode);
   ++g_launches;
   return cuda_status(cudaGetLastError());
 }
@@ -1387,7 +1519,7 @@ int launch_rank_c(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsd
 template <typename T>
 int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* af,
                 const T* q, int nq, int interp, int extrap, int kind, int rank_window, int do_adjust, T* scen,
-                double* sim_q, void* stream) {
+                double* sim_q, void* stream, int rank_mode = 0) {
   if (!sim || !grp || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (do_adjust) {
     if (!af || !q || !scen || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
@@ -1404,7 +1536,7 @@ int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba
   const int n_pad = std::max(2, next_pow2(seg.max_len));
   int C = pick_cols<T>(n_pad);
   cudaStream_t s = (cudaStream_t)stream;
-#define XS_CASE(CC) case CC: return launch_rank_c<T, CC>(sim, n_pts, sp, st, grp, seg, af, q, nq, interp, extrap, kind, do_adjust, scen, sim_q, n_pad, s)
+#define XS_CASE(CC) case CC: return launch_rank_c<T, CC>(sim, n_pts, sp, st, grp, seg, af, q, nq, interp, extrap, kind, do_adjust, scen, sim_q, n_pad, s, rank_mode)
   switch (C) {
     XS_CASE(32); XS_CASE(16); XS_CASE(8); XS_CASE(4); XS_CASE(2); XS_CASE(1);
     default: return XSDBA_ERR_SEGMENT_TOO_LONG;
@@ -1488,6 +1620,62 @@ int launch_jitter(const T* x, int64_t n, const double* j4, uint64_t seed, T* out
   ++g_launches;
   return cuda_status(cudaGetLastError());
 }
+template <typename T, int C>
+int launch_reorder_c(const T* sim, const T* ref, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
+                     T* out, int n_pad, cudaStream_t s) {
+  const size_t smem = (size_t)C * 16 + (size_t)2 * n_pad * C * sizeof(T);
+  auto kern = reorder_kernel<T, C>;
+  int rc = set_smem(kern, smem);
+  if (rc) return rc;
+  dim3 grid((unsigned)((n_pts + C - 1) / C), (unsigned)grp->n_groups);
+  kern<<<grid, kThreads, smem, s>>>(sim, ref, n_pts, sp, st, grp->members.off, grp->members.rows, grp->segments.off,
+                                    grp->segments.rows, grp->window, n_pad, out);
+  ++g_launches;
+  return cuda_status(cudaGetLastError());
+}
+
+template <typename T>
+int launch_reorder(const T* sim, const T* ref, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, T* out,
+                   void* stream) {
+  if (!sim || !ref || !grp || !out || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
+  if (n_pts == 0) return XSDBA_OK;
+  const int n_pad = std::max(2, next_pow2(grp->segments.max_len));
+  int C = pick_cols<T>(2 * n_pad);  // two sorted arrays share the budget
+  cudaStream_t s = (cudaStream_t)stream;
+#define XS_CASE(CC) case CC: return launch_reorder_c<T, CC>(sim, ref, n_pts, sp, st, grp, out, n_pad, s)
+  switch (C) {
+    XS_CASE(32); XS_CASE(16); XS_CASE(8); XS_CASE(4); XS_CASE(2); XS_CASE(1);
+    default: return XSDBA_ERR_SEGMENT_TOO_LONG;
+  }
+#undef XS_CASE
+}
+
+template <typename T>
+int launch_rotate(const T* x, int64_t n_elem, int n_var, const float* rot_host, T* y, void* stream) {
+  if (!x || !y || !rot_host || n_var < 1 || n_var > kMaxVar || n_elem < 0 || x == y) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (n_elem == 0) return XSDBA_OK;
+  RotMat R;
+  for (int v = 0; v < kMaxVar; ++v) for (int w = 0; w < kMaxVar; ++w)
+    R.r[v * kMaxVar + w] = (v < n_var && w < n_var) ? rot_host[v * n_var + w] : 0.f;
+  const unsigned blocks = (unsigned)std::min<int64_t>((n_elem + 255) / 256, 148 * 32);
+  rotate_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n_elem, n_var, R, y);
+  ++g_launches;
+  return cuda_status(cudaGetLastError());
+}
+
+template <typename T>
+int launch_standardize(const T* x, int64_t n_pts, int64_t sp, int64_t st, int64_t n_time, int n_var, int64_t var_stride,
+                       T* y, void* stream) {
+  if (!x || !y || n_pts < 0 || n_time <= 0 || n_var < 1) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (n_pts == 0) return XSDBA_OK;
+  const int64_t n = n_pts * n_var;
+  standardize_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, n_pts, sp, st, (int)n_time,
+                                                                                       n_var, var_stride, y);
+  ++g_launches;
+  return cuda_status(cudaGetLastError());
+}
+
 int upload_table(const std::vector<int32_t>& off, const std::vector<int32_t>& rows, DevTable& t) {
   XS_CUDA(cudaMalloc(&t.off, off.size() * sizeof(int32_t)));
   XS_CUDA(cudaMalloc(&t.rows, std::max<size_t>(rows.size(), 1) * sizeof(int32_t)));
@@ -1658,6 +1846,48 @@ int xsdba_jitter_f32(const float* x, int64_t n, const double* j4, uint64_t seed,
 }
 int xsdba_jitter_f64(const double* x, int64_t n, const double* j4, uint64_t seed, double* out, void* stream) {
   return launch_jitter<double>(x, n, j4, seed, out, stream);
+}
+
+int xsdba_qm_train_q64_f32(const float* ref, const float* hist, int64_t n_pts, int64_t sp, int64_t st,
+                           const xsdba_grouping_t* grp, const double* q64, int32_t nq, int32_t kind, float* af,
+                           float* hq, void* stream) {
+  if (!q64) return XSDBA_ERR_INVALID_ARGUMENT;
+  return launch_train<float>(ref, hist, n_pts, sp, st, grp, reinterpret_cast<const float*>(q64), nq, kind, 0, 0, af, hq,
+                             nullptr, stream, nullptr, 0, q64);
+}
+int xsdba_rank_lookup_f32(const float* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                          const float* af, const float* q, int32_t nq, int32_t interp, int32_t extrap, int32_t kind,
+                          int32_t rank_window, int32_t rank_mode, float* scen, double* sim_q, void* stream) {
+  return launch_rank<float>(sim, n_pts, sp, st, grp, af, q, nq, interp, extrap, kind, rank_window, 1, scen, sim_q, stream,
+                            rank_mode);
+}
+int xsdba_rank_lookup_f64(const double* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                          const double* af, const double* q, int32_t nq, int32_t interp, int32_t extrap, int32_t kind,
+                          int32_t rank_window, int32_t rank_mode, double* scen, double* sim_q, void* stream) {
+  return launch_rank<double>(sim, n_pts, sp, st, grp, af, q, nq, interp, extrap, kind, rank_window, 1, scen, sim_q, stream,
+                             rank_mode);
+}
+int xsdba_rotate_f32(const float* x, int64_t n_elem, int32_t n_var, const float* rot_host, float* y, void* stream) {
+  return launch_rotate<float>(x, n_elem, n_var, rot_host, y, stream);
+}
+int xsdba_rotate_f64(const double* x, int64_t n_elem, int32_t n_var, const float* rot_host, double* y, void* stream) {
+  return launch_rotate<double>(x, n_elem, n_var, rot_host, y, stream);
+}
+int xsdba_standardize_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, int64_t n_time, int32_t n_var,
+                          int64_t var_stride, float* y, void* stream) {
+  return launch_standardize<float>(x, n_pts, sp, st, n_time, n_var, var_stride, y, stream);
+}
+int xsdba_standardize_f64(const double* x, int64_t n_pts, int64_t sp, int64_t st, int64_t n_time, int32_t n_var,
+                          int64_t var_stride, double* y, void* stream) {
+  return launch_standardize<double>(x, n_pts, sp, st, n_time, n_var, var_stride, y, stream);
+}
+int xsdba_reorder_f32(const float* sim, const float* ref, int64_t n_pts, int64_t sp, int64_t st,
+                      const xsdba_grouping_t* grp, float* out, void* stream) {
+  return launch_reorder<float>(sim, ref, n_pts, sp, st, grp, out, stream);
+}
+int xsdba_reorder_f64(const double* sim, const double* ref, int64_t n_pts, int64_t sp, int64_t st,
+                      const xsdba_grouping_t* grp, double* out, void* stream) {
+  return launch_reorder<double>(sim, ref, n_pts, sp, st, grp, out, stream);
 }
 
 int xsdba_poly_trend_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
