@@ -112,39 +112,45 @@ __device__ __forceinline__ void sort_pass(float* __restrict__ half_col, int bloc
 
 #define XS_ST(p, b) ((p) * 16 + (b))
 
-// Sort both 512-row halves of buf[1024][32] ascending.  blockDim.x == 1024; ends with __syncthreads.
-__device__ __forceinline__ void half_barrier(int half) {
-  // the two 512-row halves are independent sorts: a named barrier per half (16 warps) lets them drift
-  // apart so that one half's shared-memory phase overlaps the other's FMNMX phase
-  asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "r"(512) : "memory");
+__device__ __forceinline__ void group_barrier(int id, int n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
-__device__ __forceinline__ void sort_halves_512(float* buf) {
+// Sort both 512-row halves of buf[1024][32] ascending.  blockDim.x == 1024; ends with __syncthreads.
+// Synchronisation is as fine as the data flow allows: up to and including phase 8 every pass stays
+// inside a 256-row quarter (bit 8 of the in-half index is never an exchange bit), so the 8 warps of a
+// quarter only wait for each other (named barriers 1..4); the two passes that touch phase 9 need the
+// 16 warps of the half (barriers 5, 6).  Four independent groups per CTA drift apart, so the
+// shared-memory phase of one overlaps the FMNMX / IMAD phase of another.  stagger_ns > 0 delays group
+// k by k*stagger_ns at the start to force the phase offset.
+__device__ __forceinline__ void sort_halves_512(float* buf, int stagger_ns = 0) {
   constexpr int NB = 9;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hb = warp >> 4;
-  float* hc = buf + (size_t)(warp >> 4) * (1 << NB) * 32 + lane;
+  const int hb = warp >> 4;          // half (0, 1)
+  const int qb = warp >> 3;          // quarter group (0..3): half*2 + bit 8 of the block base
+  float* hc = buf + (size_t)hb * (1 << NB) * 32 + lane;
   const int blk = warp & 15;
+  if (stagger_ns > 0 && qb > 0) __nanosleep((unsigned)(stagger_ns * qb));
   // pass 1: phases 1..5 on bits {0..4}; phase-5 direction (bit 5) is warp-uniform
   sort_pass<BitSet<0, 1, 2, 3, 4>, NB, 5,
             XS_ST(1, 0), XS_ST(2, 1), XS_ST(2, 0), XS_ST(3, 2), XS_ST(3, 1), XS_ST(3, 0), XS_ST(4, 3), XS_ST(4, 2),
             XS_ST(4, 1), XS_ST(4, 0), XS_ST(5, 4), XS_ST(5, 3), XS_ST(5, 2), XS_ST(5, 1), XS_ST(5, 0)>(hc, blk);
-  half_barrier(hb);
+  group_barrier(1 + qb, 256);
   // pass 2: phase 6 bits 5..1 (direction bit 6 warp-uniform)
   sort_pass<BitSet<1, 2, 3, 4, 5>, NB, 6, XS_ST(6, 5), XS_ST(6, 4), XS_ST(6, 3), XS_ST(6, 2), XS_ST(6, 1)>(hc, blk);
-  half_barrier(hb);
+  group_barrier(1 + qb, 256);
   // pass 3: phase 6 bit 0 (direction bit 6 in S), phase 7 bits 6..3 (direction bit 7 warp-uniform)
   sort_pass<BitSet<0, 3, 4, 5, 6>, NB, 7, XS_ST(6, 0), XS_ST(7, 6), XS_ST(7, 5), XS_ST(7, 4), XS_ST(7, 3)>(hc, blk);
-  half_barrier(hb);
+  group_barrier(1 + qb, 256);
   // pass 4: phase 7 bits 2..0 (direction bit 7 in S), phase 8 bits 7,6 (direction bit 8 warp-uniform)
   sort_pass<BitSet<0, 1, 2, 6, 7>, NB, 8, XS_ST(7, 2), XS_ST(7, 1), XS_ST(7, 0), XS_ST(8, 7), XS_ST(8, 6)>(hc, blk);
-  half_barrier(hb);
+  group_barrier(1 + qb, 256);
   // pass 5: phase 8 bits 5..1 (direction bit 8 warp-uniform)
   sort_pass<BitSet<1, 2, 3, 4, 5>, NB, 8, XS_ST(8, 5), XS_ST(8, 4), XS_ST(8, 3), XS_ST(8, 2), XS_ST(8, 1)>(hc, blk);
-  half_barrier(hb);
+  group_barrier(5 + hb, 512);
   // pass 6: phase 8 bit 0 (direction bit 8 in S), phase 9 bits 8..5 (ascending)
   sort_pass<BitSet<0, 5, 6, 7, 8>, NB, -1, XS_ST(8, 0), XS_ST(9, 8), XS_ST(9, 7), XS_ST(9, 6), XS_ST(9, 5)>(hc, blk);
-  half_barrier(hb);
+  group_barrier(5 + hb, 512);
   // pass 7: phase 9 bits 4..0 (ascending)
   sort_pass<BitSet<0, 1, 2, 3, 4>, NB, -1, XS_ST(9, 4), XS_ST(9, 3), XS_ST(9, 2), XS_ST(9, 1), XS_ST(9, 0)>(hc, blk);
   __syncthreads();

@@ -207,12 +207,13 @@ struct FastSmem {
   static __host__ __device__ constexpr size_t total(int nq) { return refq + (size_t)3 * nq * 33 * 4; }
 };
 
+template <bool JITTER>
 __global__ void __launch_bounds__(kFastThreads, 1)
 train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist, long long n_pts, long long st,
                   const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
                   const float* __restrict__ q, int nq, int kind, int normalize, int mode, float* __restrict__ af,
                   float* __restrict__ hist_q, float* __restrict__ scaling, JitterParams jp, int use_jitter,
-                  const double* __restrict__ q64) {
+                  const double* __restrict__ q64, int stagger_ns) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* buf = reinterpret_cast<float*>(smem_raw + FastSmem::buf);
   int* rows_tab = reinterpret_cast<int*>(smem_raw + FastSmem::rows);
@@ -264,7 +265,7 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
       const int t = rows_tab[warp + 32 * i];
       v[i] = (t >= 0 && col_ok) ? src[(long long)t * st] : fnan;
     }
-    if (use_jitter && pass == 1) {  // hist only, per window slot (_adjustment.py:58-67)
+    if (JITTER && use_jitter && pass == 1) {  // hist only, per window slot (_adjustment.py:58-67)
       const long long seg_base = seg_off[g];
 #pragma unroll
       for (int i = 0; i < 32; ++i)
@@ -304,7 +305,7 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
       for (int i = 0; i < 32; ++i) dst[(size_t)i * 16 * 32] = (v[i] == v[i]) ? v[i] : finf;
     }
     __syncthreads();
-    sort_halves_512(buf);
+    sort_halves_512(buf, stagger_ns);
     // ---- quantiles from the two sorted runs -------------------------------------------------------
     for (int item = tid; item < nq * 32; item += kFastThreads) {
       const int k = item >> 5;  // warp-uniform node, lane = column
@@ -1348,12 +1349,21 @@ bool launch_train_fast(const float* ref, const float* hist, int64_t n_pts, int64
                        const double* q64) {
   if (sp != 1 || grp->segments.max_len > 1024 || nq > kFastMaxNq || getenv("XSDBA_B200_NO_FAST")) return false;
   const size_t smem = FastSmem::total(nq);
-  *rc = set_smem(train_fast_kernel, smem);
-  if (*rc) return true;
   dim3 grid((unsigned)((n_pts + 31) / 32), (unsigned)grp->n_groups);
-  train_fast_kernel<<<grid, kFastThreads, smem, s>>>(ref, hist, n_pts, st, grp->segments.off, grp->segments.rows,
-                                                     grp->n_groups, q, nq, kind, normalize, mode, af, hq, scaling, jp,
-                                                     use_jitter, q64);
+  static const int stagger_ns = getenv("XSDBA_B200_STAGGER_NS") ? atoi(getenv("XSDBA_B200_STAGGER_NS")) : 0;
+  if (use_jitter) {
+    *rc = set_smem(train_fast_kernel<true>, smem);
+    if (*rc) return true;
+    train_fast_kernel<true><<<grid, kFastThreads, smem, s>>>(ref, hist, n_pts, st, grp->segments.off, grp->segments.rows,
+                                                             grp->n_groups, q, nq, kind, normalize, mode, af, hq, scaling,
+                                                             jp, use_jitter, q64, stagger_ns);
+  } else {
+    *rc = set_smem(train_fast_kernel<false>, smem);
+    if (*rc) return true;
+    train_fast_kernel<false><<<grid, kFastThreads, smem, s>>>(ref, hist, n_pts, st, grp->segments.off, grp->segments.rows,
+                                                              grp->n_groups, q, nq, kind, normalize, mode, af, hq, scaling,
+                                                              jp, use_jitter, q64, stagger_ns);
+  }
   ++g_launches;
   *rc = cuda_status(cudaGetLastError());
   return true;
