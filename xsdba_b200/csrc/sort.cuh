@@ -54,6 +54,38 @@ struct BitSet {
   }
 };
 
+// one compare-exchange; `imad` selects the FMA-pipe reconstruction of the max (see sort_stage)
+template <bool DESC>
+__device__ __forceinline__ void constexpr_ce(float& a, float& b, bool imad, unsigned ce_one, unsigned ce_mone) {
+  const float lo = fminf(a, b);
+  float hi;
+#if XS_CE_IMAD
+  if (imad) {
+    unsigned s_, h_;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(s_) : "r"(__float_as_uint(a)), "r"(ce_one), "r"(__float_as_uint(b)));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(h_) : "r"(__float_as_uint(lo)), "r"(ce_mone), "r"(s_));
+    hi = __uint_as_float(h_);
+  } else
+#endif
+  hi = fmaxf(a, b);
+  a = DESC ? hi : lo;
+  b = DESC ? lo : hi;
+}
+
+// Batcher's odd-even merge sort of 32 inputs: 191 compare-exchanges (depth 15) against 240 for the
+// bitonic phases 1..5 -- used for the first pass, where a thread sorts its whole 32-element block.
+// (generated and 0-1 verified offline; pairs are (lo index, hi index), applied in this order)
+__device__ constexpr unsigned char kOem32A[191] = {0,2,0,1,1,4,6,4,5,5,0,2,2,1,3,3,1,3,5,8,10,8,9,9,12,14,12,13,13,8,10,10,9,11,11,9,11,13,0,4,4,2,6,6,2,6,10,1,5,5,3,7,7,3,7,11,1,3,5,7,9,11,13,16,18,16,17,17,20,22,20,21,21,16,18,18,17,19,19,17,19,21,24,26,24,25,25,28,30,28,29,29,24,26,26,25,27,27,25,27,29,16,20,20,18,22,22,18,22,26,17,21,21,19,23,23,19,23,27,17,19,21,23,25,27,29,0,8,8,4,12,12,4,12,20,2,10,10,6,14,14,6,14,22,2,6,10,14,18,22,26,1,9,9,5,13,13,5,13,21,3,11,11,7,15,15,7,15,23,3,7,11,15,19,23,27,1,3,5,7,9,11,13,15,17,19,21,23,25,27,29};
+__device__ constexpr unsigned char kOem32B[191] = {1,3,2,3,2,5,7,6,7,6,4,6,4,5,7,5,2,4,6,9,11,10,11,10,13,15,14,15,14,12,14,12,13,15,13,10,12,14,8,12,8,10,14,10,4,8,12,9,13,9,11,15,11,5,9,13,2,4,6,8,10,12,14,17,19,18,19,18,21,23,22,23,22,20,22,20,21,23,21,18,20,22,25,27,26,27,26,29,31,30,31,30,28,30,28,29,31,29,26,28,30,24,28,24,26,30,26,20,24,28,25,29,25,27,31,27,21,25,29,18,20,22,24,26,28,30,16,24,16,20,28,20,8,16,24,18,26,18,22,30,22,10,18,26,4,8,12,16,20,24,28,17,25,17,21,29,21,9,17,25,19,27,19,23,31,23,11,19,27,5,9,13,17,21,25,29,2,4,6,8,10,12,14,16,18,20,22,24,26,28,30};
+
+template <bool DESC>
+__device__ __forceinline__ void sort32_oem(float (&r)[32], unsigned ce_one, unsigned ce_mone) {
+#pragma unroll
+  for (int k = 0; k < 191; ++k) {
+    constexpr_ce<DESC>(r[kOem32A[k]], r[kOem32B[k]], (k % 3) != 0, ce_one, ce_mone);
+  }
+}
+
 // one stage (phase, exchange bit) on the 32 registers of a thread
 template <class S, bool DESC, int TOP, int PHASE, int BIT>
 __device__ __forceinline__ void sort_stage(float (&r)[32], unsigned ce_one, unsigned ce_mone) {
@@ -131,10 +163,20 @@ __device__ __forceinline__ void sort_halves_512(float* buf, int stagger_ns = 0) 
   float* hc = buf + (size_t)hb * (1 << NB) * 32 + lane;
   const int blk = warp & 15;
   if (stagger_ns > 0 && qb > 0) __nanosleep((unsigned)(stagger_ns * qb));
-  // pass 1: phases 1..5 on bits {0..4}; phase-5 direction (bit 5) is warp-uniform
-  sort_pass<BitSet<0, 1, 2, 3, 4>, NB, 5,
-            XS_ST(1, 0), XS_ST(2, 1), XS_ST(2, 0), XS_ST(3, 2), XS_ST(3, 1), XS_ST(3, 0), XS_ST(4, 3), XS_ST(4, 2),
-            XS_ST(4, 1), XS_ST(4, 0), XS_ST(5, 4), XS_ST(5, 3), XS_ST(5, 2), XS_ST(5, 1), XS_ST(5, 0)>(hc, blk);
+  // pass 1: every thread sorts its 32-row block (bits {0..4}); ascending or descending by bit 5 of the block
+  // (= what bitonic phases 1..5 would leave), with the 191-CE odd-even merge network
+  {
+    const int ebase = BitSet<0, 1, 2, 3, 4>::template deposit<NB>(blk);
+    float* p = hc + ebase * 32;
+    float r[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = p[i * 32];
+    const unsigned ce_one = xs_ce_consts[0], ce_mone = xs_ce_consts[1];
+    if ((ebase >> 5) & 1) sort32_oem<true>(r, ce_one, ce_mone);
+    else sort32_oem<false>(r, ce_one, ce_mone);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) p[i * 32] = r[i];
+  }
   group_barrier(1 + qb, 256);
   // pass 2: phase 6 bits 5..1 (direction bit 6 warp-uniform)
   sort_pass<BitSet<1, 2, 3, 4, 5>, NB, 6, XS_ST(6, 5), XS_ST(6, 4), XS_ST(6, 3), XS_ST(6, 2), XS_ST(6, 1)>(hc, blk);
