@@ -222,6 +222,26 @@ int xsdba_reorder_f64(const double* sim_dev, const double* ref_dev, int64_t n_pt
                       int64_t stride_time, const xsdba_grouping_t* grp, double* out_dev, void* cuda_stream);
 
 /*
+ * Per-(point, group) selections on the segment sorter.
+ *  - xsdba_group_vecquantile_*: replaces nbutils.vecquantiles / _vecquantiles (nbutils.py:151-195): one
+ *    numba np.nanquantile(segment, rnk[point][group]) per segment (NaN rank -> NaN); rnk / out are
+ *    [n_pts][n_groups].  Used by _adapt_freq (_processing.py:107).
+ *  - xsdba_map_cdf_*: replaces utils.map_cdf / map_cdf_1d / _ecdf_1d (utils.py:35-84) per group: the value
+ *    of x with the same empirical CDF as y_value in y, for nv values (yvals_dev, float64 device array);
+ *    out is [n_pts][n_groups][nv].
+ */
+int xsdba_group_vecquantile_f32(const float* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                                const xsdba_grouping_t* grp, const float* rnk_dev, float* out_dev, void* cuda_stream);
+int xsdba_group_vecquantile_f64(const double* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                                const xsdba_grouping_t* grp, const double* rnk_dev, double* out_dev, void* cuda_stream);
+int xsdba_map_cdf_f32(const float* x_dev, const float* y_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                      const xsdba_grouping_t* grp, const double* yvals_dev, int32_t nv, float* out_dev,
+                      void* cuda_stream);
+int xsdba_map_cdf_f64(const double* x_dev, const double* y_dev, int64_t n_pts, int64_t stride_pt,
+                      int64_t stride_time, const xsdba_grouping_t* grp, const double* yvals_dev, int32_t nv,
+                      double* out_dev, void* cuda_stream);
+
+/*
  * Polynomial trend: replaces detrending.PolyDetrend.fit(...).ds.trend = _polydetrend_get_trend
  * (detrending.py:165-208; xarray polyfit/polyval per group through map_groups): y = x (+|*)
  * scaling[point][group] when scaling_dev != NULL (the scaled_sim of dqm_adjust, _adjustment.py:748-757),

@@ -156,6 +156,19 @@ def main():
     g["npdft_ref"], g["npdft_hist"], g["npdft_sim_std"], g["npdft_rots"], g["npdft_q"] = ref, hist, sim_std, rots, qn
     g["npdft_af_q"], g["npdft_adjusted"] = af_q, adj
 
+    # ---- vecquantiles (numba guvectorize, nbutils.py:151-161) and map_cdf_1d (utils.py:35-44) ----------------
+    for dt, tag in ((np.float32, "f32"), (np.float64, "f64")):
+        a = rng.gamma(2.0, 3.0, size=(40, 300)).astype(dt)
+        a[rng.random(a.shape) < 0.05] = np.nan
+        a[0, 1:] = np.nan
+        rk = rng.random(40).astype(dt); rk[3] = np.nan; rk[4] = 0.0; rk[5] = 1.0
+        g[f"vecq_{tag}_in"], g[f"vecq_{tag}_rnk"] = a, rk
+        g[f"vecq_{tag}_out"] = nbu._vecquantiles(a, rk)
+    xx = rng.normal(size=400).astype(np.float32); yy = (rng.normal(size=400) * 2 + 1).astype(np.float32)
+    xx[7] = np.nan; yy[11] = np.nan
+    yv = np.array([-1.0, 0.3, 2.5])
+    g["mapcdf_x"], g["mapcdf_y"], g["mapcdf_v"], g["mapcdf_out"] = xx, yy, yv, u.map_cdf_1d(xx, yy, yv)
+
     np.savez_compressed(os.path.join(OUT, "reference_kernels.npz"), **g)
     sz = os.path.getsize(os.path.join(OUT, "reference_kernels.npz"))
     print(f"wrote {len(g)} arrays, {sz/1024:.0f} KiB")

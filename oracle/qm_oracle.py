@@ -909,3 +909,51 @@ def mbcn_adjust(ref, hist, sim, af_q, rots, quantiles, blocks, kinds, method="ne
             for v in range(V):
                 scen[v, i, g] = reordering_1d(scen_block[v], npdft_block[v])[keep]
     return scen
+
+
+# ----------------------------------------------------------------------------------------------
+# vecquantiles (numba flavour) and map_cdf  (nbutils.py:151-195; utils.py:35-84)
+# ----------------------------------------------------------------------------------------------
+
+def numba_nanquantile(row, q):
+    """numba's np.nanquantile as compiled into ``_vecquantiles`` (numba/np/arraymath.py
+    ``_collect_percentiles_inner``, numba 0.65): float64, rank = 1 + (n-1)*((q*100)/100)."""
+    a = np.sort(np.asarray(row, np.float64)[~np.isnan(row)])
+    n = a.size
+    if n == 0:
+        return np.nan
+    pct = np.float64(q) * 100.0
+    if n == 1:
+        return a[0]
+    if pct == 100:
+        return a[-1]
+    if pct == 0:
+        return a[0]
+    rank = 1 + (n - 1) * (pct / 100.0)
+    f = np.floor(rank)
+    m = rank - f
+    k = int(f - 1)
+    return a[k] * (1 - m) + a[k + 1] * m
+
+
+def vecquantiles_numba(arr, rnk):
+    """nbutils.py:151-161 with numba's nanquantile; output in the data dtype."""
+    out = np.full(arr.shape[0], np.nan, arr.dtype)
+    for i in range(arr.shape[0]):
+        if not np.isnan(rnk[i]):
+            out[i] = numba_nanquantile(arr[i], rnk[i])
+    return out
+
+
+def ecdf_1d(x, value):
+    """utils.py:35-37."""
+    sx = np.r_[-np.inf, np.sort(x, axis=None)]
+    return np.searchsorted(sx, value, side="right") / np.sum(~np.isnan(sx))
+
+
+def map_cdf_1d(x, y, y_value):
+    """utils.py:40-44 (numpy's own nanquantile)."""
+    q = ecdf_1d(y, np.atleast_1d(y_value))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return np.nanquantile(x, q=q)

@@ -379,3 +379,32 @@ def test_mbcn_matches_oracle(group, window, years, n_iter):
     assert same.mean() > 0.98, same.mean()
     if group == "time":
         np.testing.assert_allclose(np.sort(scen, axis=-1), np.sort(scen_o, axis=-1), rtol=1e-6, atol=1e-6)
+
+
+def test_vecquantiles_reference_golden(golden):
+    """CUDA vecquantiles against the reference's numba _vecquantiles outputs (tests/golden): bit-exact."""
+    xs = _xs()
+    for tag in ("f32", "f64"):
+        a, rk, want = golden[f"vecq_{tag}_in"], golden[f"vecq_{tag}_rnk"], golden[f"vecq_{tag}_out"]
+        t = xs.TimeAxis.daily(2001, 1, "noleap")[: a.shape[1]]
+        got = _np(xs.vecquantiles(a, rk[:, None], time=t, group="time", time_axis=-1))[:, 0]
+        assert bits_equal(got, want), tag
+
+
+def test_map_cdf_reference_golden(golden):
+    xs = _xs()
+    x, y, v, want = golden["mapcdf_x"], golden["mapcdf_y"], golden["mapcdf_v"], golden["mapcdf_out"]
+    t = xs.TimeAxis.daily(2001, 2, "noleap")[: x.size]
+    got = _np(xs.map_cdf(xs.Dataset({"x": x[:, None], "y": y[:, None]}, time=t), y_value=v, group="time"))
+    assert got.dtype == np.float32                          # output_dtypes=[ds.x.dtype] (utils.py:83)
+    assert bits_equal(got[0, 0], want.astype(np.float32))
+    # grouped: every month against the oracle
+    rng = np.random.default_rng(2)
+    tt = xs.TimeAxis.daily(2001, 3, "noleap"); to = o.daily_time_axis(2001, 3, "noleap")
+    X = rng.normal(size=(len(tt), 5)).astype(np.float32); Y = (rng.normal(size=(len(tt), 5)) + 0.5).astype(np.float32)
+    got = _np(xs.map_cdf(xs.Dataset({"x": X, "y": Y}, time=tt), y_value=[0.2], group="time.month"))
+    gidx, G, _ = o.group_index(to, "time.month")
+    for p in range(5):
+        for g in range(G):
+            sel = gidx == g
+            assert got[p, g, 0] == np.float32(o.map_cdf_1d(X[sel, p], Y[sel, p], 0.2)[0])

@@ -138,3 +138,11 @@ def test_reordering_reference_kat():
     x = np.arange(1, 9).astype(float)
     y = np.arange(8, 0, -1).astype(float)
     np.testing.assert_array_equal(o.reordering_1d(x, y), x[::-1])
+
+
+def test_vecquantiles_and_map_cdf_vs_reference(golden):
+    for tag in ("f32", "f64"):
+        got = o.vecquantiles_numba(golden[f"vecq_{tag}_in"], golden[f"vecq_{tag}_rnk"])
+        assert bits_equal(got, golden[f"vecq_{tag}_out"])
+    got = o.map_cdf_1d(golden["mapcdf_x"], golden["mapcdf_y"], golden["mapcdf_v"])
+    assert bits_equal(got, golden["mapcdf_out"])

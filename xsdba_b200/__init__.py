@@ -2,7 +2,7 @@
 from .base import Grouper, parse_group  # noqa: F401
 from .calendar import TimeAxis  # noqa: F401
 from ._adjustment import (  # noqa: F401
-    Dataset, dqm_adjust, dqm_train, eqm_train, group_quantile, group_rank, loess_trend, poly_trend, qdm_adjust, qm_adjust,
+    Dataset, dqm_adjust, dqm_train, eqm_train, group_quantile, group_rank, loess_trend, map_cdf, poly_trend, vecquantiles, qdm_adjust, qm_adjust,
 )
 from .utils import equally_spaced_nodes  # noqa: F401
 from .adjustment import (  # noqa: F401

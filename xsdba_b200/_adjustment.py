@@ -348,3 +348,40 @@ def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_
     _lib.check(status, "dqm_adjust")
     ta = 0 if st != 1 or sim.ndim == 1 else -1
     return Dataset({"scen": scen, "trend": trend}, time=time, time_axis=ta)
+
+
+def vecquantiles(x, rnk, *, time, group="time", time_axis=0):
+    """``nbutils.vecquantiles`` per group (nbutils.py:164-195): the quantile of every (point, group) segment at its
+    own rank ``rnk`` (*points, n_groups) -> (*points, n_groups)."""
+    group = parse_group(group)
+    lib = _lib.load()
+    dt = _widest(x)
+    xs, n_pts, sp, st, pshape = _series(x, time_axis, len(time), dt)
+    h = group.handle(time)
+    r = _as_device(rnk, dt).contiguous()
+    if r.numel() != n_pts * h.n_groups:
+        raise ValueError("rnk must be (*points, n_groups)")
+    out = torch.empty((n_pts, h.n_groups), dtype=dt, device=xs.device)
+    fn = getattr(lib, f"xsdba_group_vecquantile_{_sfx(dt)}")
+    _lib.check(fn(xs.data_ptr(), n_pts, sp, st, h.ptr, r.data_ptr(), out.data_ptr(), _stream()), "vecquantiles")
+    return out.reshape(*pshape, h.n_groups)
+
+
+def map_cdf(ds, *, y_value, group="time"):
+    """``utils.map_cdf`` under ``Grouper.apply`` (utils.py:47-84): ds holds x and y; returns the value of x with the
+    same empirical CDF as ``y_value`` in y: (*points, n_groups, len(y_value))."""
+    group = parse_group(group)
+    lib = _lib.load()
+    time = ds.time
+    dt = _widest(ds["x"], ds["y"])
+    xs, n_pts, sp, st, pshape = _series(ds["x"], ds.time_axis, len(time), dt)
+    ys, n_pts_y, _, _, _ = _series(ds["y"], ds.time_axis, len(time), dt)
+    if n_pts_y != n_pts:
+        raise ValueError("x and y must have the same points")
+    h = group.handle(time)
+    yv = _as_device(np.atleast_1d(np.asarray(y_value, np.float64))).contiguous()
+    out = torch.empty((n_pts, h.n_groups, yv.numel()), dtype=dt, device=xs.device)
+    fn = getattr(lib, f"xsdba_map_cdf_{_sfx(dt)}")
+    _lib.check(fn(xs.data_ptr(), ys.data_ptr(), n_pts, sp, st, h.ptr, yv.data_ptr(), yv.numel(), out.data_ptr(), _stream()),
+               "map_cdf")
+    return out.reshape(*pshape, h.n_groups, yv.numel())

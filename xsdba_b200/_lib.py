@@ -51,6 +51,8 @@ for _t in ("f32", "f64"):
     SIGNATURES[f"xsdba_rotate_{_t}"] = (C.c_int, [vp, i64, i32, c_f32p, vp, vp])
     SIGNATURES[f"xsdba_standardize_{_t}"] = (C.c_int, [vp, i64, i64, i64, i64, i32, i64, vp, vp])
     SIGNATURES[f"xsdba_reorder_{_t}"] = (C.c_int, [vp, vp, i64, i64, i64, vp, vp, vp])
+    SIGNATURES[f"xsdba_group_vecquantile_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp])
+    SIGNATURES[f"xsdba_map_cdf_{_t}"] = (C.c_int, [vp, vp, i64, i64, i64, vp, vp, i32, vp, vp])
     SIGNATURES[f"xsdba_group_rank_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, i32, vp, vp])
 SIGNATURES["xsdba_qm_train_q64_f32"] = (C.c_int, [vp, vp, i64, i64, i64, vp, vp, i32, i32, vp, vp, vp])
 SIGNATURES["xsdba_debug_copy_rows_f32"] = (C.c_int, [vp, i64, i64, vp, vp, i32, vp])

@@ -1297,6 +1297,104 @@ reorder_kernel(const T* __restrict__ sim, const T* __restrict__ ref, long long n
   }
 }
 
+// =============================================================================================
+// K8: per-(point, group) selections built on the segment sorter.
+//   mode 0  nbutils.vecquantiles (nbutils.py:151-195): numba's np.nanquantile(row, rnk[row]) --
+//           rank = 1 + (n-1)*((q*100)/100), val = lower*(1-m) + upper*m in float64 (numba
+//           np/arraymath.py _collect_percentiles_inner), NaN rank -> NaN.
+//   mode 1  utils.map_cdf / map_cdf_1d / _ecdf_1d (utils.py:35-84): q = (1 + #{y <= v}) / (1 + n_y),
+//           then numpy's np.nanquantile(x, q) (float64 lerp, switch at gamma >= 0.5).
+// grid = (ceil(n_pts / C), n_groups); out is [n_pts][n_groups] (mode 0) or [n_pts][n_groups][nv] (mode 1).
+// =============================================================================================
+template <typename T, int C>
+__global__ void __launch_bounds__(kThreads)
+select_kernel(const T* __restrict__ x, const T* __restrict__ y, long long n_pts, long long sp, long long st,
+              const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups, int mode,
+              const T* __restrict__ rnk, const double* __restrict__ yvals, int nv, T* __restrict__ out, int n_pad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sum = reinterpret_cast<double*>(smem_raw);   // [C]
+  int* cnt = reinterpret_cast<int*>(sum + C);          // [C]
+  int* ycnt = cnt + C;                                 // [C]
+  T* sm = reinterpret_cast<T*>(smem_raw + C * 16);     // [n_pad][C]
+  const int g = blockIdx.y;
+  const long long n0 = (long long)blockIdx.x * C;
+  const int S = seg_off[g + 1] - seg_off[g];
+  const int32_t* rows = seg_rows + seg_off[g];
+  const int n_out = mode == 0 ? 1 : nv;
+  if (S == 0) {
+    for (int item = threadIdx.x; item < C * n_out; item += blockDim.x) {
+      const int c = item / n_out, k = item % n_out;
+      if (n0 + c < n_pts) out[((n0 + c) * n_groups + g) * n_out + k] = Num<T>::nan();
+    }
+    return;
+  }
+  load_segment<T, C>(sm, x, n0, n_pts, sp, st, rows, S, n_pad);
+  __syncthreads();
+  count_columns<T, C>(sm, n_pad, cnt, sum, false);
+  make_keys<T, C>(sm, n_pad, cnt, sum, 0, XSDBA_KIND_ADD);
+  sort_columns<T, C>(sm, n_pad);
+  for (int k = 0; k < n_out; ++k) {
+    double q = Num<double>::nan();
+    if (mode == 1) {  // _ecdf_1d(y, v): y's valid count and #{y <= v}, per column
+      if (threadIdx.x < C) { ycnt[threadIdx.x] = 0; cnt[threadIdx.x] = cnt[threadIdx.x]; sum[threadIdx.x] = 0.0; }
+      __syncthreads();
+      const double v = yvals[k];
+      int my_le = 0, my_n = 0;
+      for (int idx = threadIdx.x; idx < S * C; idx += blockDim.x) {  // idx % C constant per thread
+        const int r = idx / C, c = idx % C;
+        if (n0 + c >= n_pts) continue;
+        const int t = rows[r];
+        if (t < 0) continue;
+        const T yv = y[(n0 + c) * sp + (long long)t * st];
+        if (!is_nan(yv)) { ++my_n; if ((double)yv <= v) ++my_le; }
+      }
+      atomicAdd(&ycnt[threadIdx.x % C], my_le);
+      atomicAdd(&sum[threadIdx.x % C], (double)my_n);
+      __syncthreads();
+    }
+    if (threadIdx.x < C && n0 + threadIdx.x < n_pts) {
+      const int c = threadIdx.x;
+      const int n = cnt[c];
+      const T* col = sm + c;
+      double res = Num<double>::nan();
+      if (mode == 0) {
+        const T rk = rnk[(n0 + c) * n_groups + g];
+        if (!is_nan(rk) && n > 0) {
+          const double pct = (double)rk * 100.0;
+          if (n == 1) res = (double)col[0];
+          else if (pct == 100.0) res = (double)col[(size_t)(n - 1) * C];
+          else if (pct == 0.0) res = (double)col[0];
+          else {
+            const double rank = 1.0 + (double)(n - 1) * (pct / 100.0);
+            const double f = floor(rank);
+            const double m = rank - f;
+            long long kk = (long long)f - 1;
+            kk = kk < 0 ? 0 : (kk > n - 2 ? n - 2 : kk);
+            const double lower = (double)col[(size_t)kk * C], upper = (double)col[(size_t)(kk + 1) * C];
+            res = __dadd_rn(__dmul_rn(lower, __dsub_rn(1.0, m)), __dmul_rn(upper, m));
+          }
+        }
+      } else {
+        q = (1.0 + (double)ycnt[c]) / (1.0 + sum[c]);   // utils.py:35-37
+        if (n > 0 && q == q) {
+          if (q > 1.0) q = 1.0;
+          const double vi = q * (double)(n - 1);
+          long long i0 = (long long)floor(vi);
+          i0 = i0 < 0 ? 0 : (i0 > n - 1 ? n - 1 : i0);
+          const long long i1 = i0 + 1 > n - 1 ? n - 1 : i0 + 1;
+          const double gm = vi - (double)i0;
+          const T aT = col[(size_t)i0 * C], bT = col[(size_t)i1 * C];
+          const double a = (double)aT, b = (double)bT;
+          const double d = (double)Num<T>::sub(bT, aT);  // numpy _lerp: subtract(b, a) in the array dtype
+          res = gm >= 0.5 ? __dsub_rn(b, __dmul_rn(d, __dsub_rn(1.0, gm))) : __dadd_rn(a, __dmul_rn(d, gm));
+        }
+      }
+      out[((n0 + c) * n_groups + g) * n_out + k] = (T)res;
+    }
+    __syncthreads();
+  }
+}
+
 // elementwise jitter (processing.jitter / jitter_under_thresh / jitter_over_thresh, processing.py:124-257)
 template <typename T>
 __global__ void jitter_kernel(const T* __restrict__ x, long long n, JitterParams jp, T* __restrict__ out) {
@@ -1662,6 +1760,39 @@ int launch_reorder(const T* sim, const T* ref, int64_t n_pts, int64_t sp, int64_
 #undef XS_CASE
 }
 
+template <typename T, int C>
+int launch_select_c(const T* x, const T* y, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, int mode,
+                    const T* rnk, const double* yvals, int nv, T* out, int n_pad, cudaStream_t s) {
+  const size_t smem = (size_t)C * 16 + (size_t)n_pad * C * sizeof(T);
+  auto kern = select_kernel<T, C>;
+  int rc = set_smem(kern, smem);
+  if (rc) return rc;
+  dim3 grid((unsigned)((n_pts + C - 1) / C), (unsigned)grp->n_groups);
+  kern<<<grid, kThreads, smem, s>>>(x, y, n_pts, sp, st, grp->segments.off, grp->segments.rows, grp->n_groups, mode, rnk,
+                                    yvals, nv, out, n_pad);
+  ++g_launches;
+  return cuda_status(cudaGetLastError());
+}
+
+template <typename T>
+int launch_select(const T* x, const T* y, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, int mode,
+                  const T* rnk, const double* yvals, int nv, T* out, void* stream) {
+  if (!x || !grp || !out || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (mode == 0 && !rnk) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (mode == 1 && (!y || !yvals || nv <= 0)) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
+  if (n_pts == 0) return XSDBA_OK;
+  const int n_pad = std::max(2, next_pow2(grp->segments.max_len));
+  const int C = pick_cols<T>(n_pad);
+  cudaStream_t s = (cudaStream_t)stream;
+#define XS_CASE(CC) case CC: return launch_select_c<T, CC>(x, y, n_pts, sp, st, grp, mode, rnk, yvals, nv, out, n_pad, s)
+  switch (C) {
+    XS_CASE(32); XS_CASE(16); XS_CASE(8); XS_CASE(4); XS_CASE(2); XS_CASE(1);
+    default: return XSDBA_ERR_SEGMENT_TOO_LONG;
+  }
+#undef XS_CASE
+}
+
 template <typename T>
 int launch_rotate(const T* x, int64_t n_elem, int n_var, const float* rot_host, T* y, void* stream) {
   if (!x || !y || !rot_host || n_var < 1 || n_var > kMaxVar || n_elem < 0 || x == y) return XSDBA_ERR_INVALID_ARGUMENT;
@@ -1899,6 +2030,23 @@ int xsdba_reorder_f32(const float* sim, const float* ref, int64_t n_pts, int64_t
 int xsdba_reorder_f64(const double* sim, const double* ref, int64_t n_pts, int64_t sp, int64_t st,
                       const xsdba_grouping_t* grp, double* out, void* stream) {
   return launch_reorder<double>(sim, ref, n_pts, sp, st, grp, out, stream);
+}
+
+int xsdba_group_vecquantile_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                                const float* rnk, float* out, void* stream) {
+  return launch_select<float>(x, nullptr, n_pts, sp, st, grp, 0, rnk, nullptr, 0, out, stream);
+}
+int xsdba_group_vecquantile_f64(const double* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                                const double* rnk, double* out, void* stream) {
+  return launch_select<double>(x, nullptr, n_pts, sp, st, grp, 0, rnk, nullptr, 0, out, stream);
+}
+int xsdba_map_cdf_f32(const float* x, const float* y, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                      const double* yvals, int32_t nv, float* out, void* stream) {
+  return launch_select<float>(x, y, n_pts, sp, st, grp, 1, nullptr, yvals, nv, out, stream);
+}
+int xsdba_map_cdf_f64(const double* x, const double* y, int64_t n_pts, int64_t sp, int64_t st,
+                      const xsdba_grouping_t* grp, const double* yvals, int32_t nv, double* out, void* stream) {
+  return launch_select<double>(x, y, n_pts, sp, st, grp, 1, nullptr, yvals, nv, out, stream);
 }
 
 int xsdba_poly_trend_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
