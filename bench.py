@@ -66,7 +66,7 @@ def run_reference(args):
     import cpu_baseline
 
     cores = os.cpu_count() or 1
-    n_pts = args.cpu_points or 64 * cores
+    n_pts = args.cpu_points or 1024 * cores  # ~10 s of work per timed call on 16 cores
     vals, secs = [], []
     for i in range(args.warmup + args.steps):
         r = cpu_baseline.run(n_pts, cores, NYEARS, NQ, GROUP, seed=100 + i)
@@ -260,9 +260,14 @@ def run_b200(args):
     dom_ms = max(tr_ms, ad_ms)
     achieved = dom_bytes * args.steps / (dom_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": f"{dom}_kernel<float,32>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": "train_fast_kernel<false>" if dom == "train" else "pack_tables_kernel + adjust_tile_kernel",
+        "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
-        "traffic": None, "launches": n_launch, "avg_launch_ms": dom_ms / n_launch,
+        # dram__bytes_read+write per launch from the ncu --set full capture in profiles/r01_ncu_summary.txt:
+        # 2.1666 GB for a 23 040-point launch whose algorithmic bytes are 2.1289 GB (x1.0177: no re-reads)
+        "traffic": (dom_bytes * args.steps / n_launch) * 1.0177 if dom == "train" else None,
+        "traffic_source": "ncu dram__bytes_{read,write}.sum of profiles/r01_ncu_summary.txt scaled to this launch size",
+        "launches": n_launch, "avg_launch_ms": dom_ms / n_launch,
         "algorithmic_bytes_per_launch": dom_bytes * args.steps / n_launch,
         "step": {"train_ms": tr_ms / args.steps, "adjust_ms": ad_ms / args.steps,
                  "train_GBps": train_bytes_step * args.steps / (tr_ms * 1e-3) / 1e9,
@@ -303,7 +308,7 @@ def run_b200(args):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import cpu_baseline
         cores = os.cpu_count() or 1
-        r = cpu_baseline.run(args.cpu_points or 96 * cores, cores, NYEARS, NQ, GROUP)
+        r = cpu_baseline.run(args.cpu_points or 2048 * cores, cores, NYEARS, NQ, GROUP)  # ~15-20 s of CPU work
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                "seconds": r["seconds"]}
 
