@@ -408,3 +408,20 @@ def test_map_cdf_reference_golden(golden):
         for g in range(G):
             sel = gidx == g
             assert got[p, g, 0] == np.float32(o.map_cdf_1d(X[sel, p], Y[sel, p], 0.2)[0])
+
+
+def test_qdm_full_size_segments_fit_shared_memory():
+    """Regression: QDM with rank_window=True on 30-year daily data (930-slot segments) and nq=100 needs the sort
+    buffer AND the staged tables in one CTA -- the launcher narrows the tile instead of failing."""
+    xs = _xs()
+    rng = np.random.default_rng(1)
+    tx = xs.TimeAxis.daily(1981, 30, "noleap"); to = o.daily_time_axis(1981, 30, "noleap")
+    sim = synth.pr(rng, to, 34, "sim")
+    q = o.equally_spaced_nodes(100).astype(np.float32)
+    af = rng.normal(1.0, 0.1, size=(34, 365, 100)).astype(np.float32)
+    g = xs.Grouper("time.dayofyear", 31)
+    out = xs.qdm_adjust(xs.Dataset({"sim": sim, "af": af, "quantiles": q}, time=tx), group=g, interp="nearest",
+                        extrapolation="constant", kind="*", rank_window=True)
+    gidx, G, _ = o.group_index(to, "time.dayofyear")
+    simq_o = o.grouped_rank_pct(sim.T.copy()[:3], gidx, G, 31, True)
+    assert bits_equal(_np(out.sim_q).T[:3], simq_o)

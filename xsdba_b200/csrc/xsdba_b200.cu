@@ -1644,6 +1644,16 @@ int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba
   const DevTable& seg = rank_window ? grp->segments : grp->members;
   const int n_pad = std::max(2, next_pow2(seg.max_len));
   int C = pick_cols<T>(n_pad);
+  // the staged lookup tables share the CTA's shared memory with the sort buffer: narrow the tile until both fit
+  auto need = [&](int c) {
+    size_t top = 1;
+    while (top * 2 <= (size_t)nq) top *= 2;
+    const size_t tables = do_adjust ? ((size_t)6 * 2 * top * c + 4 * c) * sizeof(T) + 3 * c * sizeof(int) + 16 +
+                                          (size_t)2 * c * (nq | 1) * sizeof(T)
+                                    : 0;
+    return (size_t)c * 28 + 8 + (size_t)n_pad * c * sizeof(T) + tables;
+  };
+  while (C > 1 && need(C) > 216 * 1024) C >>= 1;
   cudaStream_t s = (cudaStream_t)stream;
 #define XS_CASE(CC) case CC: return launch_rank_c<T, CC>(sim, n_pts, sp, st, grp, seg, af, q, nq, interp, extrap, kind, do_adjust, scen, sim_q, n_pad, s, rank_mode)
   switch (C) {
