@@ -997,63 +997,151 @@ __device__ __forceinline__ double tricube_w(double u) {  // loess.py:31-35
   return u >= 1.0 ? 0.0 : c * c * c;
 }
 
+// LOESS window geometry of one compacted series of n samples (loess.py:104-119)
+struct LoessGeom {
+  int r, hw, R, HW;
+  __device__ LoessGeom(int n, double f) {
+    r = (int)(2.0 * floor(f * (double)n / 2.0) + 1.0);
+    hw = (r - 1) / 2;
+    R = r + 4 < n ? r + 4 : n;
+    HW = hw + 2;
+  }
+  // true when output i uses the weights computed at i = HW on the window [i-HW, i+HW] (loess.py:131-150)
+  __device__ bool interior(int i, int n) const { return i > HW && i < n - HW - 1; }
+};
+
+// K6c: the "interior" weights of every point: w[k] = tricube(|x[k] - x[HW]| / ((hw+1) dx)), k in [0, 2HW],
+// written k-major ([k][point]) so that the smoothing kernel reads them coalesced.
+__global__ void __launch_bounds__(kThreads)
+loess_weights_kernel(const int32_t* __restrict__ tc, const int32_t* __restrict__ nvalid, long long n_pts, int n_time,
+                     const double* __restrict__ xn, double f, int w_rows, double* __restrict__ wtab) {
+  const long long pt = (long long)blockIdx.x * 32 + (threadIdx.x & 31);
+  if (pt >= n_pts) return;
+  const int n = nvalid[pt];
+  const LoessGeom gm(n, f);
+  if (n < 2 * gm.HW + 3) return;  // no interior outputs for this point
+  const double dx = xn[1] - xn[0];
+  const double h = (double)(gm.hw + 1) * dx;
+  const double xc = xn[tc[(long long)gm.HW * n_pts + pt]];
+  for (int k = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); k <= 2 * gm.HW && k < w_rows;
+       k += gridDim.y * (blockDim.x >> 5))
+    wtab[(long long)k * n_pts + pt] = tricube_w(fabs(xn[tc[(long long)k * n_pts + pt]] - xc) / h);
+}
+
+// one output by the literal rule (edges, short series)
+template <typename T>
+__device__ double loess_one(const T* __restrict__ y, const int32_t* __restrict__ tcp, long long n_pts, int n, int i,
+                            const LoessGeom& gm, const double* __restrict__ xn, double dx, int degree) {
+  int lo, hi;                                                 // loess.py:124-135
+  if (i < gm.HW) { lo = 0; hi = gm.R; }
+  else if (i >= n - gm.HW - 1) { lo = n - gm.R; hi = n; }
+  else { lo = i - gm.HW; hi = i + gm.HW + 1; }
+  // weights: recomputed for i <= HW or i >= n-HW, otherwise those of the last recomputation (i = HW),
+  // i.e. taken from the samples [0, 2HW+1) around sample HW                    (loess.py:136-150)
+  const bool edge = (i <= gm.HW) || (i >= n - gm.HW);
+  const int ic = edge ? i : gm.HW;
+  const int wlo = edge ? lo : 0;
+  double h;
+  if (ic < gm.hw) h = (double)(gm.r - ic) * dx;
+  else if (ic >= n - gm.hw) h = (double)(ic - (n - gm.r) + 1) * dx;
+  else h = (double)(gm.hw + 1) * dx;
+  const double xc = xn[tcp[(long long)ic * n_pts]];
+  const double xi = xn[tcp[(long long)i * n_pts]];
+  double sw = 0, swy = 0, swx = 0, swxx = 0, swxy = 0;
+  for (int j = lo; j < hi; ++j) {
+    const int k = wlo + (j - lo);
+    const double w = k < n ? tricube_w(fabs(xn[tcp[(long long)k * n_pts]] - xc) / h) : 0.0;
+    const double yj = (double)y[(long long)j * n_pts];
+    sw += w; swy += w * yj;
+    if (degree == 1) {
+      const double xj = xn[tcp[(long long)j * n_pts]];
+      swx += w * xj; swxx += w * xj * xj; swxy += w * yj * xj;
+    }
+  }
+  if (degree == 0) return swy / sw;                           // loess.py:38-39
+  double a00 = sw, a01 = swx, a10 = swx, a11 = swxx, b0 = swy, b1 = swxy;  // loess.py:42-46
+  if (fabs(a10) > fabs(a00)) { double t_; t_ = a00; a00 = a10; a10 = t_; t_ = a01; a01 = a11; a11 = t_; t_ = b0; b0 = b1; b1 = t_; }
+  const double m = a10 / a00;
+  a11 -= m * a01; b1 -= m * b0;
+  const double beta1 = b1 / a11;
+  const double beta0 = (b0 - a01 * beta1) / a00;
+  return beta0 + beta1 * xi;
+}
+
+// K6b: thread = (point, chunk of RO consecutive outputs).  A chunk that is interior for the thread's series
+// runs as a register-tiled FIR on the precomputed weights (every y / w value is loaded once per chunk and
+// feeds RO accumulators); edge chunks and short series use the literal per-output rule.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, const int32_t* __restrict__ nvalid,
                     long long n_pts, long long sp, long long st, int n_time, const double* __restrict__ xn,
-                    double f, int degree, double* __restrict__ trend) {
+                    double f, int degree, const double* __restrict__ wtab, double* __restrict__ trend) {
+  constexpr int RO = 8;
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5, rows_per_cta = blockDim.x >> 5;
   const long long pt = (long long)blockIdx.x * 32 + lane;
   if (pt >= n_pts) return;
   const int n = nvalid[pt];
   if (n == 0) return;
   const double dx = xn[1] - xn[0];                              // loess.py:262-263
-  const int r = (int)(2.0 * floor(f * (double)n / 2.0) + 1.0);  // loess.py:113
-  const int hw = (r - 1) / 2;
-  const int R = r + 4 < n ? r + 4 : n;
-  const int HW = hw + 2;
+  const LoessGeom gm(n, f);
   const T* y = yc + pt;
   const int32_t* tcp = tc + pt;
-  for (int i = blockIdx.y * rows_per_cta + row; i < n; i += gridDim.y * rows_per_cta) {
-    int lo, hi;                                                 // loess.py:124-135
-    if (i < HW) { lo = 0; hi = R; }
-    else if (i >= n - HW - 1) { lo = n - R; hi = n; }
-    else { lo = i - HW; hi = i + HW + 1; }
-    // weights: recomputed for i <= HW or i >= n-HW, otherwise those of the last recomputation (i = HW),
-    // i.e. taken from the samples [0, 2HW+1) around sample HW                    (loess.py:136-150)
-    const bool edge = (i <= HW) || (i >= n - HW);
-    const int ic = edge ? i : HW;          // centre the weights are computed for
-    const int wlo = edge ? lo : 0;         // first sample of the window the weights are computed on
-    double h;
-    if (ic < hw) h = (double)(r - ic) * dx;
-    else if (ic >= n - hw) h = (double)(ic - (n - r) + 1) * dx;
-    else h = (double)(hw + 1) * dx;
-    const double xc = xn[tcp[(long long)ic * n_pts]];
-    const double xi = xn[tcp[(long long)i * n_pts]];
-    double sw = 0, swy = 0, swx = 0, swxx = 0, swxy = 0;
-    for (int j = lo; j < hi; ++j) {
-      const int k = wlo + (j - lo);        // sample whose distance defines the weight of window slot j-lo
-      const double w = k < n ? tricube_w(fabs(xn[tcp[(long long)k * n_pts]] - xc) / h) : 0.0;
-      const double yj = (double)y[(long long)j * n_pts];
-      sw += w; swy += w * yj;
-      if (degree == 1) {
-        const double xj = xn[tcp[(long long)j * n_pts]];
-        swx += w * xj; swxx += w * xj * xj; swxy += w * yj * xj;
+  const double* w = wtab + pt;
+  for (int i0 = (blockIdx.y * rows_per_cta + row) * RO; i0 < n; i0 += gridDim.y * rows_per_cta * RO) {
+    const bool fast = degree == 0 && gm.interior(i0, n) && gm.interior(i0 + RO - 1, n);
+    if (fast) {
+      // output i0+r sums w[k] * y[i0 + r - HW + k], k = 0..2HW.  With j = i0 - HW + m the pair (m, r) uses w[m - r].
+      double sw[RO], swy[RO], wr[RO];
+#pragma unroll
+      for (int r = 0; r < RO; ++r) { sw[r] = 0; swy[r] = 0; wr[r] = 0; }
+      const int K = 2 * gm.HW;  // last weight index
+      const T* yb = y + (long long)(i0 - gm.HW) * n_pts;
+      for (int m = 0; m <= K + RO - 1; ++m) {
+        // shift the weight window: wr[r] = w[m - r] (0 outside [0, K])
+#pragma unroll
+        for (int r = RO - 1; r > 0; --r) wr[r] = wr[r - 1];
+        wr[0] = m <= K ? w[(long long)m * n_pts] : 0.0;
+        const double yj = (double)yb[(long long)m * n_pts];
+#pragma unroll
+        for (int r = 0; r < RO; ++r) { sw[r] += wr[r]; swy[r] = fma(wr[r], yj, swy[r]); }
       }
+#pragma unroll
+      for (int r = 0; r < RO; ++r)
+        trend[pt * sp + (long long)tcp[(long long)(i0 + r) * n_pts] * st] = swy[r] / sw[r];
+    } else if (degree == 0 && n >= gm.R && i0 + RO <= n &&
+               ((i0 + RO - 1 <= gm.HW) || (i0 >= n - gm.HW))) {
+      // edge chunk: all RO outputs share the window [0, R) (left) or [n-R, n) (right) and recompute their weights
+      // (loess.py:138-147): every y_j / x_j is loaded once and feeds RO (weight, sum) pairs.
+      const int lo = (i0 + RO - 1 <= gm.HW) ? 0 : n - gm.R;
+      double xi[RO], ih[RO], sw[RO], swy[RO];
+#pragma unroll
+      for (int r = 0; r < RO; ++r) {
+        const int i = i0 + r;
+        double h;
+        if (i < gm.hw) h = (double)(gm.r - i) * dx;
+        else if (i >= n - gm.hw) h = (double)(i - (n - gm.r) + 1) * dx;
+        else h = (double)(gm.hw + 1) * dx;
+        ih[r] = 1.0 / h;
+        xi[r] = xn[tcp[(long long)i * n_pts]];
+        sw[r] = 0; swy[r] = 0;
+      }
+      for (int j = lo; j < lo + gm.R; ++j) {
+        const double xj = xn[tcp[(long long)j * n_pts]];
+        const double yj = (double)y[(long long)j * n_pts];
+#pragma unroll
+        for (int r = 0; r < RO; ++r) {
+          const double wgt = tricube_w(fabs(xj - xi[r]) * ih[r]);
+          sw[r] += wgt; swy[r] = fma(wgt, yj, swy[r]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RO; ++r)
+        trend[pt * sp + (long long)tcp[(long long)(i0 + r) * n_pts] * st] = swy[r] / sw[r];
+    } else {
+      for (int r = 0; r < RO && i0 + r < n; ++r)
+        trend[pt * sp + (long long)tcp[(long long)(i0 + r) * n_pts] * st] =
+            loess_one<T>(y, tcp, n_pts, n, i0 + r, gm, xn, dx, degree);
     }
-    double est;
-    if (degree == 0) {
-      est = swy / sw;                                           // loess.py:38-39
-    } else {                                                    // loess.py:42-46 (2x2 solve, partial pivoting)
-      double a00 = sw, a01 = swx, a10 = swx, a11 = swxx, b0 = swy, b1 = swxy;
-      if (fabs(a10) > fabs(a00)) { double t_; t_ = a00; a00 = a10; a10 = t_; t_ = a01; a01 = a11; a11 = t_; t_ = b0; b0 = b1; b1 = t_; }
-      const double m = a10 / a00;
-      a11 -= m * a01; b1 -= m * b0;
-      const double beta1 = b1 / a11;
-      const double beta0 = (b0 - a01 * beta1) / a00;
-      est = beta0 + beta1 * xi;
-    }
-    trend[pt * sp + (long long)tcp[(long long)i * n_pts] * st] = est;
   }
 }
 
@@ -1721,11 +1809,20 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
   }
   loess_compact_kernel<T><<<(unsigned)((n_pts + kThreads - 1) / kThreads), kThreads, 0, s>>>(
       x, n_pts, sp, st, n_time, grp->gidx, grp->n_groups, scaling, kind, yc, tc, nv, trend);
+  // interior weight table: at most 2*HW+1 <= f*n_time + 6 rows per point
+  const int w_rows = (int)std::min<double>((double)n_time, f * (double)n_time + 8.0);
+  double* wtab = nullptr;
+  if (cudaMallocAsync(&wtab, sizeof(double) * n_pts * w_rows, s) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFreeAsync(yc, s); cudaFreeAsync(tc, s); cudaFreeAsync(nv, s);
+    return XSDBA_ERR_OUT_OF_MEMORY;
+  }
+  loess_weights_kernel<<<dim3((unsigned)((n_pts + 31) / 32), 16), kThreads, 0, s>>>(tc, nv, n_pts, n_time, xn, f, w_rows, wtab);
   const unsigned chunks = (unsigned)std::min<int64_t>(std::max<int64_t>(1, (n_time + 63) / 64), 1024);
   loess_smooth_kernel<T><<<dim3((unsigned)((n_pts + 31) / 32), chunks), kThreads, 0, s>>>(yc, tc, nv, n_pts, sp, st, n_time,
-                                                                                          xn, f, degree, trend);
-  g_launches += 2;
-  cudaFreeAsync(yc, s); cudaFreeAsync(tc, s); cudaFreeAsync(nv, s);
+                                                                                          xn, f, degree, wtab, trend);
+  g_launches += 3;
+  cudaFreeAsync(yc, s); cudaFreeAsync(tc, s); cudaFreeAsync(nv, s); cudaFreeAsync(wtab, s);
   return cuda_status(cudaGetLastError());
 }
 
