@@ -113,6 +113,44 @@ int xsdba_jitter_f64(const double* x_dev, int64_t n, const double* jitter4_host,
                      void* cuda_stream);
 
 /*
+ * Frequency adaptation (the adapt_freq_thresh option of the three QM classes).
+ *  - xsdba_qm_train_adapt_*: eqm_train with _preprocess_dataset's adapt_freq step (_adjustment.py:69-70 ->
+ *    _processing._adapt_freq.func, _processing.py:75-131) on hist inside every group (after jitter, after the
+ *    window gather): P0_ref / P0_hist = ecdf at the threshold (float64 [n_pts][n_groups]), pth =
+ *    vecquantiles(ref, P0_hist) where dP0 > 0 else NaN (data dtype), the excess dry values of hist replaced
+ *    by U(thresh, pth) before its quantiles are taken.  P0_ref, P0_hist, pth are deterministic (bit-exact
+ *    against the oracle); which tied values are replaced and the fill values are hashes of (seed, element).
+ *  - xsdba_adapt_freq_apply_*: the adjust-side _adapt_freq_preprocess (_adjustment.py:32-45, 639-646) on
+ *    sim with the stored P0_ref / P0_hist / pth, per exact group; out has the strides of sim.
+ *  - xsdba_tail_mask_*: the max_tail_factor mask (_adjustment.py:647-658, 672-673): scen = adapted sim
+ *    wherever adapted sim > factor * last node of hist_q_raw of the sample's group (nearest broadcast).
+ */
+int xsdba_qm_train_adapt_f32(const float* ref_dev, const float* hist_dev, int64_t n_pts, int64_t stride_pt,
+                             int64_t stride_time, const xsdba_grouping_t* grp, const float* q_dev, int32_t nq,
+                             int32_t kind, const double* jitter4_host, double adapt_thresh, uint64_t seed,
+                             float* af_dev, float* hist_q_dev, double* P0_ref_dev, double* P0_hist_dev,
+                             float* pth_dev, void* cuda_stream);
+int xsdba_qm_train_adapt_f64(const double* ref_dev, const double* hist_dev, int64_t n_pts, int64_t stride_pt,
+                             int64_t stride_time, const xsdba_grouping_t* grp, const double* q_dev, int32_t nq,
+                             int32_t kind, const double* jitter4_host, double adapt_thresh, uint64_t seed,
+                             double* af_dev, double* hist_q_dev, double* P0_ref_dev, double* P0_hist_dev,
+                             double* pth_dev, void* cuda_stream);
+int xsdba_adapt_freq_apply_f32(const float* sim_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                               const xsdba_grouping_t* grp, double thresh, const double* P0_ref_dev,
+                               const double* P0_hist_dev, const float* pth_dev, uint64_t seed, float* out_dev,
+                               void* cuda_stream);
+int xsdba_adapt_freq_apply_f64(const double* sim_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                               const xsdba_grouping_t* grp, double thresh, const double* P0_ref_dev,
+                               const double* P0_hist_dev, const double* pth_dev, uint64_t seed, double* out_dev,
+                               void* cuda_stream);
+int xsdba_tail_mask_f32(const float* adapted_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                        const xsdba_grouping_t* grp, const float* hist_q_raw_dev, int32_t nq, double factor,
+                        float* scen_dev, void* cuda_stream);
+int xsdba_tail_mask_f64(const double* adapted_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                        const xsdba_grouping_t* grp, const double* hist_q_raw_dev, int32_t nq, double factor,
+                        double* scen_dev, void* cuda_stream);
+
+/*
  * Quantiles only: replaces nbutils.quantile over grouped segments (nbutils.py:224-271), used for
  * hist_q_raw (_adjustment.py:254-256) and by callers that want ref_q.  out is [n_pts][n_groups][nq].
  */

@@ -957,3 +957,71 @@ def map_cdf_1d(x, y, y_value):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         return np.nanquantile(x, q=q)
+
+
+# ----------------------------------------------------------------------------------------------
+# frequency adaptation  (_processing.py:20-142; _adjustment.py:32-45, 69-70, 639-646)
+# ----------------------------------------------------------------------------------------------
+
+def ecdf(x, value):
+    """utils.ecdf (utils.py:87-106) along the last axis: (x <= value).sum / notnull.sum (float64)."""
+    with np.errstate(all="ignore"):
+        return (x <= value).sum(axis=-1) / (~np.isnan(x)).sum(axis=-1)
+
+
+def rank_pct_tiebreak(seg, rng):
+    """utils.rank(pct=True, use_random_tiebreak=True) (utils.py:618-634) along the last axis."""
+    r = nanrankdata(seg)
+    r = r + rng.uniform(0.1, 0.25, size=seg.shape)
+    r = nanrankdata(r)
+    cnt = (~np.isnan(seg)).sum(axis=-1, keepdims=True)
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r = r / cnt
+        mn = np.nanmin(r, axis=-1, keepdims=True)
+        mx = np.nanmax(r, axis=-1, keepdims=True)
+        return mx * (r - mn) / (mx - mn)
+
+
+def adapt_freq_segment(sim, thresh, rng, ref=None, P0_ref=None, P0_hist=None, pth=None):
+    """``_adapt_freq.func`` on one group (_processing.py:75-131): sim [N, S] (and ref [N, S_ref], or the stored
+    triplet) -> sim_ad, pth, dP0, P0_ref, P0_hist.  The random parts use ``rng`` (the reference uses numpy's
+    global RNG)."""
+    P0_sim = ecdf(sim, thresh)
+    P0_hist = P0_sim if P0_hist is None else P0_hist
+    P0_ref = ecdf(ref, thresh) if P0_ref is None else P0_ref
+    with np.errstate(all="ignore"):
+        dP0 = np.where(P0_hist == 0, np.nan, (P0_hist - P0_ref) / P0_hist)
+    if ((dP0 <= 0) | np.isnan(dP0)).all():
+        return sim.copy(), np.nan * dP0, dP0, P0_ref, P0_hist
+    if pth is None:
+        pth = vecquantiles_numba(ref.astype(np.float64), P0_hist).astype(ref.dtype)
+        pth = np.where(dP0 > 0, pth, np.nan).astype(ref.dtype)
+    rnk = rank_pct_tiebreak(sim, rng)
+    no_adapt = ((dP0 <= 0) | np.isnan(dP0))[:, None]
+    with np.errstate(all="ignore"):
+        keep = (rnk < ((P0_ref / P0_hist) * P0_sim)[:, None]) | (rnk > P0_sim[:, None]) | np.isnan(sim)
+        fill = (pth[:, None] - thresh) * rng.random(sim.shape).astype(sim.dtype) + thresh
+    sim_ad = np.where(no_adapt, sim, np.where(keep, sim, fill)).astype(sim.dtype)
+    return sim_ad, pth, dP0, P0_ref, P0_hist
+
+
+def eqm_train_adapt_freq(ref, hist, gidx, n_groups, window, q, kind, thresh, rng):
+    """eqm_train with ``adapt_freq_thresh`` (_adjustment.py:259-286 -> _preprocess_dataset:69-70): returns
+    af, hist_q [N,G,nq] and P0_ref, P0_hist, pth [N,G]."""
+    dt = ref.dtype
+    N = ref.shape[0]
+    q = np.asarray(q, dt)
+    af = np.full((N, n_groups, q.size), np.nan, dt); hq = af.copy()
+    P0r = np.full((N, n_groups), np.nan); P0h = P0r.copy(); pth = np.full((N, n_groups), np.nan, dt)
+    for g in range(n_groups):
+        if not np.any(gidx == g):
+            continue
+        rseg = group_segment(ref, gidx, g, window)
+        hseg = group_segment(hist, gidx, g, window)
+        h_ad, pth[:, g], _, P0r[:, g], P0h[:, g] = adapt_freq_segment(hseg, thresh, rng, ref=rseg)
+        ref_q = nan_quantile(rseg, q)
+        hist_q = nan_quantile(h_ad, q)
+        af[:, g] = get_correction(hist_q, ref_q, kind)
+        hq[:, g] = hist_q
+    return af, hq, P0r, P0h, pth

@@ -425,3 +425,72 @@ def test_qdm_full_size_segments_fit_shared_memory():
     gidx, G, _ = o.group_index(to, "time.dayofyear")
     simq_o = o.grouped_rank_pct(sim.T.copy()[:3], gidx, G, 31, True)
     assert bits_equal(_np(out.sim_q).T[:3], simq_o)
+
+
+def _dry_inputs(years=8, N=6, seed=4):
+    """hist/sim drier than ref, so that frequency adaptation is needed (dP0 > 0)."""
+    rng = np.random.default_rng(seed)
+    to = o.daily_time_axis(1981, years, "noleap")
+    ref = synth.pr(rng, to, N, "hist", jitter=False, nan_frac=0.001)   # 60 % wet
+    hist = synth.pr(rng, to, N, "ref", jitter=False, nan_frac=0.001)   # 45 % wet
+    sim = synth.pr(rng, to, N, "ref", jitter=False, nan_frac=0.001)
+    return to, ref, hist, sim
+
+
+@pytest.mark.parametrize("group,window", [("time.month", 1), ("time.dayofyear", 15), ("time", 1)])
+def test_adapt_freq_train_matches_oracle(group, window):
+    """eqm_train(adapt_freq_thresh=...): P0_ref, P0_hist, pth are deterministic -> bit-exact; the adapted hist
+    quantiles depend on random fills -> compared like the reference's own test (2 decimals)."""
+    xs = _xs()
+    to, ref, hist, sim = _dry_inputs()
+    tx = xs.TimeAxis.daily(1981, 8, "noleap")
+    q = o.equally_spaced_nodes(20).astype(np.float32)
+    gidx, G, _ = o.group_index(to, group)
+    rng = np.random.default_rng(0)
+    af_o, hq_o, p0r_o, p0h_o, pth_o = o.eqm_train_adapt_freq(ref.T.copy(), hist.T.copy(), gidx, G, window, q, "*", 0.05, rng)
+    ds = xs.eqm_train(xs.Dataset({"ref": ref, "hist": hist}, time=tx), group=xs.Grouper(group, window), kind="*",
+                      quantiles=q, adapt_freq_thresh="0.05 mm/d")
+    assert bits_equal(_np(ds.P0_ref), p0r_o) and bits_equal(_np(ds.P0_hist), p0h_o)
+    assert bits_equal(_np(ds.pth), pth_o)
+    assert np.isfinite(pth_o).mean() > 0.9                       # adaptation really happens in this setup
+    hq = _np(ds.hist_q)
+    # nodes inside (thresh, pth) are order statistics of ~20 random fills per group: statistically equal only
+    assert np.isclose(hq, hq_o, rtol=0.25, atol=0.05).mean() > 0.95
+    assert np.isclose(hq, hq_o, rtol=1.0, atol=0.5).all()
+    big = hq_o > np.nanmax(pth_o) + 1e-3
+    np.testing.assert_array_equal(hq[big], hq_o[big])            # beyond pth nothing is random
+
+
+def test_adapt_freq_adjust_and_tail_factor():
+    xs = _xs()
+    to, ref, hist, sim = _dry_inputs()
+    tx = xs.TimeAxis.daily(1981, 8, "noleap")
+    obj = xs.EmpiricalQuantileMapping.train(ref, hist, time=tx, nquantiles=20, group="time.month", kind="*",
+                                            adapt_freq_thresh="0.05 mm/d", max_tail_factor=1.5)
+    scen = _np(obj.adjust(sim, time=tx))
+    # frequency adaptation of sim with the stored factors: the dry-day frequency moves towards ref's
+    gidx, G, _ = o.group_index(to, "time.month")
+    ad = _np(xs._adjustment._adapt_freq_preprocess(
+        xs.Dataset(obj.ds), xs._adjustment._as_device(sim), sim.shape[1], 1, sim.shape[1], obj.group, tx,
+        __import__("torch").float32, "0.05 mm/d"))
+    p0_before = np.nanmean(sim <= 0.05); p0_after = np.nanmean(ad <= 0.05); p0_ref = np.nanmean(ref <= 0.05)
+    assert abs(p0_after - p0_ref) < 0.02 < abs(p0_before - p0_ref)
+    assert bits_equal(np.where(sim > 0.05, ad, 0), np.where(sim > 0.05, sim, 0))      # wet days untouched
+    assert (np.isnan(ad) == np.isnan(sim)).all()
+    # expected number of replaced values per (point, group) against the oracle's rule
+    rng = np.random.default_rng(1)
+    p0r, p0h, pth = (_np(obj.ds[k]) for k in ("P0_ref", "P0_hist", "pth"))
+    n_gpu = n_ora = 0
+    for g in range(G):
+        sel = gidx == g
+        sa, *_ = o.adapt_freq_segment(sim[sel].T.copy(), 0.05, rng, P0_ref=p0r[:, g], P0_hist=p0h[:, g], pth=pth[:, g])
+        n_ora += (sa != sim[sel].T).sum() - np.isnan(sim[sel]).sum()
+        n_gpu += (ad[sel] != sim[sel]).sum() - np.isnan(sim[sel]).sum()
+    assert abs(n_gpu - n_ora) < 0.03 * n_ora
+    # max_tail_factor: values above 1.5 x the last raw hist quantile are passed through un-adjusted
+    hq_raw = _np(obj.ds["hist_q_raw"])
+    lastq = hq_raw[:, gidx, -1].T                                                       # (time, points)
+    mask = ad > 1.5 * lastq
+    assert mask.sum() > 0 and bits_equal(scen[mask], ad[mask])
+    plain = _np(xs.EmpiricalQuantileMapping(obj.ds, obj.group, "*", adapt_freq_thresh="0.05 mm/d").adjust(sim, time=tx))
+    assert bits_equal(np.where(mask, 0, scen), np.where(mask, 0, plain))

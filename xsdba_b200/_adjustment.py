@@ -105,7 +105,8 @@ def _reject_unsupported(**kw):
 
 def _train(ds, *, group, kind, quantiles, normalize, adapt_freq_thresh=None, jitter_under_thresh_value=None,
            jitter_over_thresh_value=None, jitter_over_thresh_upper_bnd=None, max_tail_factor=None, seed=0):
-    _reject_unsupported(adapt_freq_thresh=adapt_freq_thresh, max_tail_factor=max_tail_factor)
+    if adapt_freq_thresh is not None and normalize:
+        raise NotImplementedError("adapt_freq_thresh with DQM's normalisation is not built in xsdba_b200 yet")
     if (jitter_over_thresh_value is None) ^ (jitter_over_thresh_upper_bnd is None):
         raise ValueError("`jitter_over_thresh_value` and `jitter_over_thresh_upper_bnd` must both be specified or both "
                          "be `None` (default)")  # _adjustment.py:64-65
@@ -128,9 +129,27 @@ def _train(ds, *, group, kind, quantiles, normalize, adapt_freq_thresh=None, jit
     af = torch.empty((n_pts, G, nq), dtype=dt, device=ref.device)
     hq = torch.empty_like(af)
     sc = torch.empty((n_pts, G), dtype=dt, device=ref.device) if normalize else None
-    if jitter_under_thresh_value is not None or jitter_over_thresh_value is not None:
-        import ctypes as C
-        from .processing import jitter_params
+    import ctypes as C
+    from .processing import _quantity, jitter_params
+    p0r = p0h = pth = None
+    hq_raw = None
+    if max_tail_factor is not None:  # quantiles of hist before any pre-processing (_adjustment.py:254-256)
+        hq_raw = torch.empty_like(hq)
+        fnq = getattr(lib, f"xsdba_group_quantile_{_sfx(dt)}")
+        _lib.check(fnq(hist.data_ptr(), n_pts, sp, st, h.ptr, q.data_ptr(), nq, hq_raw.data_ptr(), _stream()), "hist_q_raw")
+    if adapt_freq_thresh is not None:
+        j4 = None
+        if jitter_under_thresh_value is not None or jitter_over_thresh_value is not None:
+            j4 = jitter_params(dt, lower=jitter_under_thresh_value, upper=jitter_over_thresh_value,
+                               maximum=jitter_over_thresh_upper_bnd)
+        p0r = torch.empty((n_pts, G), dtype=torch.float64, device=ref.device)
+        p0h = torch.empty_like(p0r)
+        pth = torch.empty((n_pts, G), dtype=dt, device=ref.device)
+        fn = getattr(lib, f"xsdba_qm_train_adapt_{_sfx(dt)}")
+        status = fn(ref.data_ptr(), hist.data_ptr(), n_pts, sp, st, h.ptr, q.data_ptr(), nq, _lib.KIND[kind],
+                    None if j4 is None else j4.ctypes.data_as(_lib.c_f64p), C.c_double(_quantity(adapt_freq_thresh)),
+                    C.c_uint64(seed), af.data_ptr(), hq.data_ptr(), p0r.data_ptr(), p0h.data_ptr(), pth.data_ptr(), _stream())
+    elif jitter_under_thresh_value is not None or jitter_over_thresh_value is not None:
         j4 = jitter_params(dt, lower=jitter_under_thresh_value, upper=jitter_over_thresh_value,
                            maximum=jitter_over_thresh_upper_bnd)
         fn = getattr(lib, f"xsdba_qm_train_jitter_{_sfx(dt)}")
@@ -146,7 +165,9 @@ def _train(ds, *, group, kind, quantiles, normalize, adapt_freq_thresh=None, jit
     out = Dataset(time=None)
     out["af"] = af.reshape(*pshape, G, nq)
     out["hist_q"] = hq.reshape(*pshape, G, nq)
-    out["hist_q_raw"] = None  # all-NaN dummy in the reference unless max_tail_factor (_adjustment.py:273-275)
+    out["hist_q_raw"] = None if hq_raw is None else hq_raw.reshape(*pshape, G, nq)  # NaN dummy in the reference otherwise
+    if p0r is not None:
+        out["P0_ref"], out["P0_hist"], out["pth"] = (t.reshape(*pshape, G) for t in (p0r, p0h, pth))
     if normalize:
         out["scaling"] = sc.reshape(*pshape, G)
     out["quantiles"] = q
@@ -192,9 +213,47 @@ def _tables(ds, n_pts, G, dt, names):
     return out
 
 
-def qm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None, max_tail_factor=None):
-    """``xsdba._adjustment.qm_adjust`` (_adjustment.py:594-676): ds holds af, hist_q, sim."""
-    _reject_unsupported(adapt_freq_thresh=adapt_freq_thresh, max_tail_factor=max_tail_factor)
+def _adapt_freq_preprocess(ds, sim, n_pts, sp, st, group, time, dt, adapt_freq_thresh, seed=0):
+    """``_adapt_freq_preprocess`` (_adjustment.py:32-45): frequency-adapt ``sim`` per exact group with the stored
+    P0_ref / P0_hist / pth."""
+    import ctypes as C
+    from .processing import _quantity
+    lib = _lib.load()
+    h = Grouper(group.name).handle(time)
+    G = h.n_groups
+    for k in ("P0_ref", "P0_hist", "pth"):
+        if ds.get(k) is None:
+            raise ValueError("`P0_ref`, `P0_hist`, `pth` must all be given for adapt_freq_thresh")  # _processing.py:66-67
+    p0r = _as_device(ds["P0_ref"], torch.float64).contiguous()
+    p0h = _as_device(ds["P0_hist"], torch.float64).contiguous()
+    pth = _as_device(ds["pth"], dt).contiguous()
+    if p0r.numel() != n_pts * G:
+        raise ValueError("P0_ref must be (*points, n_groups)")
+    out = torch.empty_like(sim)
+    fn = getattr(lib, f"xsdba_adapt_freq_apply_{_sfx(dt)}")
+    _lib.check(fn(sim.data_ptr(), n_pts, sp, st, h.ptr, C.c_double(_quantity(adapt_freq_thresh)), p0r.data_ptr(),
+                  p0h.data_ptr(), pth.data_ptr(), C.c_uint64(seed), out.data_ptr(), _stream()), "adapt_freq")
+    return out
+
+
+def _apply_tail_mask(ds, adapted, scen, n_pts, sp, st, group, time, dt, max_tail_factor):
+    """max_tail_factor (_adjustment.py:647-658, 672-673): keep the (pre-processed) sim where it exceeds
+    ``max_tail_factor`` times the last node of ``hist_q_raw``."""
+    import ctypes as C
+    lib = _lib.load()
+    if ds.get("hist_q_raw") is None:
+        raise ValueError("max_tail_factor needs `hist_q_raw` (train with max_tail_factor set)")
+    h = Grouper(group.name).handle(time)
+    (hq_raw,) = _tables(ds, n_pts, h.n_groups, dt, ("hist_q_raw",))
+    fn = getattr(lib, f"xsdba_tail_mask_{_sfx(dt)}")
+    _lib.check(fn(adapted.data_ptr(), n_pts, sp, st, h.ptr, hq_raw.data_ptr(), hq_raw.shape[-1], C.c_double(float(max_tail_factor)),
+                  scen.data_ptr(), _stream()), "max_tail_factor")
+    return scen
+
+
+def qm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None, max_tail_factor=None, seed=0):
+    """``xsdba._adjustment.qm_adjust`` (_adjustment.py:594-676): ds holds af, hist_q, sim (+ P0_ref, P0_hist, pth
+    for ``adapt_freq_thresh``; + hist_q_raw for ``max_tail_factor``)."""
     if interp not in ("nearest", "linear", "cubic") or extrapolation not in _lib.EXTRAP:
         raise ValueError("interp must be nearest/linear/cubic and extrapolation constant/nan")
     if interp == "cubic":
@@ -207,18 +266,21 @@ def qm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None,
     h = group.handle(time, with_window=False)
     af, hq = _tables(ds, n_pts, h.n_groups, dt, ("af", "hist_q"))
     nq = af.shape[-1]
+    if adapt_freq_thresh is not None:
+        sim = _adapt_freq_preprocess(ds, sim, n_pts, sp, st, group, time, dt, adapt_freq_thresh, seed)
     scen = torch.empty_like(sim)
     fn = getattr(lib, f"xsdba_qm_adjust_{_sfx(dt)}")
     status = fn(sim.data_ptr(), n_pts, sp, st, h.ptr, af.data_ptr(), hq.data_ptr(), nq, _lib.INTERP[interp],
                 _lib.EXTRAP[extrapolation], _lib.KIND[kind], scen.data_ptr(), _stream())
     _lib.check(status, "qm_adjust")
+    if max_tail_factor is not None:
+        scen = _apply_tail_mask(ds, sim, scen, n_pts, sp, st, group, time, dt, max_tail_factor)
     return Dataset({"scen": scen}, time=time, time_axis=0 if st != 1 or sim.ndim == 1 else -1)
 
 
 def qdm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None, rank_window=None,
-               max_tail_factor=None):
+               max_tail_factor=None, seed=0):
     """``xsdba._adjustment.qdm_adjust`` (_adjustment.py:783-886): ds holds af, quantiles, sim."""
-    _reject_unsupported(adapt_freq_thresh=adapt_freq_thresh, max_tail_factor=max_tail_factor)
     if interp == "cubic":
         raise NotImplementedError("cubic interpolation is not built in xsdba_b200 yet")
     group = parse_group(group)
@@ -235,6 +297,8 @@ def qdm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None
     (af,) = _tables(ds, n_pts, h.n_groups, dt, ("af",))
     q = _as_device(ds["quantiles"], dt).contiguous()
     nq = af.shape[-1]
+    if adapt_freq_thresh is not None:
+        sim = _adapt_freq_preprocess(ds, sim, n_pts, sp, st, group, time, dt, adapt_freq_thresh, seed)
     scen = torch.empty_like(sim)
     sim_q = torch.empty(sim.shape, dtype=torch.float64, device=sim.device)
     fn = getattr(lib, f"xsdba_qdm_adjust_{_sfx(dt)}")
@@ -242,6 +306,8 @@ def qdm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None
                 _lib.EXTRAP[extrapolation], _lib.KIND[kind], 1 if rank_window else 0, scen.data_ptr(),
                 sim_q.data_ptr(), _stream())
     _lib.check(status, "qdm_adjust")
+    if max_tail_factor is not None:
+        scen = _apply_tail_mask(ds, sim, scen, n_pts, sp, st, group, time, dt, max_tail_factor)
     return Dataset({"scen": scen, "sim_q": sim_q}, time=time, time_axis=0 if st != 1 or sim.ndim == 1 else -1)
 
 

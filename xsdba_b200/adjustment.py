@@ -21,8 +21,9 @@ from .utils import equally_spaced_nodes
 class _TrainAdjust:
     _train_fn = None
 
-    def __init__(self, ds, group, kind):
+    def __init__(self, ds, group, kind, adapt_freq_thresh=None, max_tail_factor=None):
         self.ds, self.group, self.kind = ds, group, kind
+        self.adapt_freq_thresh, self.max_tail_factor = adapt_freq_thresh, max_tail_factor
 
     @classmethod
     def from_dataset(cls, ds, *, group, kind):
@@ -40,7 +41,11 @@ class _TrainAdjust:
             quantiles = np.asarray(nquantiles)
         ds = cls._train_fn(L4.Dataset({"ref": ref, "hist": hist}, time=time, time_axis=time_axis), group=group,
                            kind=kind, quantiles=quantiles, **kw)
-        return cls(ds, group, kind)
+        return cls(ds, group, kind, kw.get("adapt_freq_thresh"), kw.get("max_tail_factor"))
+
+    def _extra(self):
+        keys = [k for k in ("P0_ref", "P0_hist", "pth", "hist_q_raw") if self.ds.get(k) is not None]
+        return {k: self.ds[k] for k in keys}
 
 
 class EmpiricalQuantileMapping(_TrainAdjust):
@@ -48,8 +53,10 @@ class EmpiricalQuantileMapping(_TrainAdjust):
     _train_fn = staticmethod(L4.eqm_train)
 
     def adjust(self, sim, *, time, interp="nearest", extrapolation="constant", time_axis=0):
-        ds = L4.Dataset({"sim": sim, "af": self.ds["af"], "hist_q": self.ds["hist_q"]}, time=time, time_axis=time_axis)
-        return L4.qm_adjust(ds, group=self.group, interp=interp, extrapolation=extrapolation, kind=self.kind)["scen"]
+        ds = L4.Dataset({"sim": sim, "af": self.ds["af"], "hist_q": self.ds["hist_q"], **self._extra()}, time=time,
+                        time_axis=time_axis)
+        return L4.qm_adjust(ds, group=self.group, interp=interp, extrapolation=extrapolation, kind=self.kind,
+                            adapt_freq_thresh=self.adapt_freq_thresh, max_tail_factor=self.max_tail_factor)["scen"]
 
 
 class QuantileDeltaMapping(EmpiricalQuantileMapping):
@@ -57,10 +64,11 @@ class QuantileDeltaMapping(EmpiricalQuantileMapping):
 
     def adjust(self, sim, *, time, interp="nearest", extrapolation="constant", rank_window=None, time_axis=0,
                extra_output=False):
-        ds = L4.Dataset({"sim": sim, "af": self.ds["af"], "quantiles": self.ds["quantiles"]}, time=time,
+        ds = L4.Dataset({"sim": sim, "af": self.ds["af"], "quantiles": self.ds["quantiles"], **self._extra()}, time=time,
                         time_axis=time_axis)
         out = L4.qdm_adjust(ds, group=self.group, interp=interp, extrapolation=extrapolation, kind=self.kind,
-                            rank_window=rank_window)
+                            rank_window=rank_window, adapt_freq_thresh=self.adapt_freq_thresh,
+                            max_tail_factor=self.max_tail_factor)
         return out if extra_output else out["scen"]  # OPTIONS[EXTRA_OUTPUT] (adjustment.py:738)
 
 

@@ -115,19 +115,63 @@ __device__ void make_keys(T* sm, int n_pad, const int* cnt, const double* sum, i
   __syncthreads();
 }
 
+struct AdaptParams {
+  int on;
+  double thresh;
+  unsigned long long seed;
+  double* P0_ref;   // [n_pts][n_groups]
+  double* P0_hist;  // [n_pts][n_groups]
+  void* pth;        // [n_pts][n_groups], data dtype
+};
+
+// per-column count of valid values and of values <= thresh (utils.ecdf, utils.py:87-106)
+template <typename T, int C>
+__device__ void count_le_columns(const T* sm, int n_pad, int* n_valid, int* n_le, double thresh) {
+  if (threadIdx.x < C) { n_valid[threadIdx.x] = 0; n_le[threadIdx.x] = 0; }
+  __syncthreads();
+  int a = 0, b = 0;
+  for (int idx = threadIdx.x; idx < n_pad * C; idx += blockDim.x) {
+    const T v = sm[idx];
+    if (!is_nan(v)) { ++a; if ((double)v <= thresh) ++b; }
+  }
+  atomicAdd(&n_valid[threadIdx.x % C], a);
+  atomicAdd(&n_le[threadIdx.x % C], b);
+  __syncthreads();
+}
+
+// numba's np.nanquantile on a sorted column (see select_kernel mode 0)
+template <typename T, int C>
+__device__ double numba_nanquantile_sorted(const T* col, int n, double q) {
+  if (n <= 0 || q != q) return Num<double>::nan();
+  const double pct = q * 100.0;
+  if (n == 1) return (double)col[0];
+  if (pct == 100.0) return (double)col[(size_t)(n - 1) * C];
+  if (pct == 0.0) return (double)col[0];
+  const double rank = 1.0 + (double)(n - 1) * (pct / 100.0);
+  const double f = floor(rank);
+  const double m = rank - f;
+  long long kk = (long long)f - 1;
+  kk = kk < 0 ? 0 : (kk > n - 2 ? n - 2 : kk);
+  const double lower = (double)col[(size_t)kk * C], upper = (double)col[(size_t)(kk + 1) * C];
+  return __dadd_rn(__dmul_rn(lower, __dsub_rn(1.0, m)), __dmul_rn(upper, m));
+}
+
 template <typename T, int C>
 __global__ void __launch_bounds__(kThreads)
 train_kernel(const T* __restrict__ ref, const T* __restrict__ hist, long long n_pts, long long sp, long long st,
              const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
              const T* __restrict__ q, int nq, int kind, int normalize, int mode, T* __restrict__ af,
              T* __restrict__ hist_q, T* __restrict__ scaling, int n_pad, JitterParams jp, int use_jitter,
-             const double* __restrict__ q64) {
+             const double* __restrict__ q64, AdaptParams ap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sum = reinterpret_cast<double*>(smem_raw);   // [C]
   double* mu_ref = sum + C;                            // [C]
   int* cnt = reinterpret_cast<int*>(mu_ref + C);       // [C]
   T* refq = reinterpret_cast<T*>(smem_raw + C * 24);   // [nq][C]  (24 = 8 + 8 + 4, padded to 8)
   T* sm = refq + (size_t)nq * C;                       // [n_pad][C]
+  // frequency adaptation state (only used when ap.on): per column P0_ref, P0_hist, pth, dP0
+  __shared__ double af_p0r[32], af_p0h[32], af_pth[32], af_dp0[32];
+  __shared__ int af_le[32], af_nh[32];
 
   const int g = blockIdx.y;
   const long long n0 = (long long)blockIdx.x * C;
@@ -149,15 +193,62 @@ train_kernel(const T* __restrict__ ref, const T* __restrict__ hist, long long n_
   }
 
   const int n_pass = mode == 0 ? 2 : 1;
+  const bool adapt = ap.on && mode == 0;
+  if (adapt) {
+    // _adapt_freq (_processing.py:75-86): P0_hist = ecdf(hist, thresh) needs a counting pre-pass over the
+    // (jittered) hist segment, because pth is taken from the sorted ref at that rank
+    load_segment<T, C>(sm, hist, n0, n_pts, sp, st, rows, S, n_pad, use_jitter ? &jp : nullptr, (long long)seg_off[g]);
+    __syncthreads();
+    count_le_columns<T, C>(sm, n_pad, af_nh, af_le, ap.thresh);
+    if (threadIdx.x < C) af_p0h[threadIdx.x] = (double)af_le[threadIdx.x] / (double)af_nh[threadIdx.x];
+    __syncthreads();
+  }
   for (int pass = 0; pass < n_pass; ++pass) {
     const T* src = pass == 0 ? ref : hist;
     // jitter applies to hist only, after the window gather (_adjustment.py:58-67, 80-81)
     load_segment<T, C>(sm, src, n0, n_pts, sp, st, rows, S, n_pad, (use_jitter && pass == 1) ? &jp : nullptr,
                        (long long)seg_off[g]);
     __syncthreads();
+    if (adapt && pass == 0) {
+      count_le_columns<T, C>(sm, n_pad, af_nh, af_le, ap.thresh);   // (af_nh is reused: ref counts here)
+      if (threadIdx.x < C) af_p0r[threadIdx.x] = (double)af_le[threadIdx.x] / (double)af_nh[threadIdx.x];
+      __syncthreads();
+    }
     count_columns<T, C>(sm, n_pad, cnt, sum, normalize != 0);
     make_keys<T, C>(sm, n_pad, cnt, sum, normalize, kind);
     sort_columns<T, C>(sm, n_pad);
+    if (adapt && pass == 0 && threadIdx.x < C) {
+      // dP0 and pth = vecquantiles(ref, P0_hist).where(dP0 > 0)   (_processing.py:84-99)
+      const int c = threadIdx.x;
+      const double p0r = af_p0r[c], p0h = af_p0h[c];
+      const double dp0 = p0h == 0.0 ? Num<double>::nan() : (p0h - p0r) / p0h;
+      double pth = Num<double>::nan();
+      if (dp0 > 0.0) pth = (double)(T)numba_nanquantile_sorted<T, C>(sm + c, cnt[c], p0h);
+      af_dp0[c] = dp0; af_pth[c] = pth;
+      if (n0 + c < n_pts) {
+        const long long o = (n0 + c) * n_groups + g;
+        ap.P0_ref[o] = p0r; ap.P0_hist[o] = p0h; reinterpret_cast<T*>(ap.pth)[o] = (T)pth;
+      }
+    }
+    if (adapt && pass == 1) {
+      // replace the excess "dry" values: sorted position i has tie-broken percentile rank i/(n-1)
+      // (_processing.py:104-122); then restore the order
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < n_pad * C; idx += blockDim.x) {
+        const int i = idx / C, c = idx % C;
+        const int n = cnt[c];
+        if (i >= n || !(af_dp0[c] > 0.0) || n < 2) continue;
+        const double rnk = (double)i / (double)(n - 1);
+        const double p0s = af_p0h[c];
+        const bool keep = (rnk < (af_p0r[c] / af_p0h[c]) * p0s) || (rnk > p0s);
+        if (!keep) {
+          const double u = (double)(T)hash_uniform(ap.seed, (unsigned long long)(((long long)seg_off[g] + i) * n_pts + n0 + c) * 2 + 1);
+          sm[idx] = (T)((af_pth[c] - ap.thresh) * u + ap.thresh);
+        }
+      }
+      __syncthreads();
+      sort_columns<T, C>(sm, n_pad);
+    }
     // quantiles: item -> (point c, node k), k fastest so that global writes are contiguous
     for (int item = threadIdx.x; item < C * nq; item += blockDim.x) {
       const int c = item / nq, k = item % nq;
@@ -1483,6 +1574,84 @@ select_kernel(const T* __restrict__ x, const T* __restrict__ y, long long n_pts,
   }
 }
 
+// =============================================================================================
+// K9: frequency adaptation of sim with stored factors (the adjust-side _adapt_freq_preprocess,
+// _adjustment.py:32-45, 639-646 -> _adapt_freq.func with P0_ref / P0_hist / pth given, _processing.py:75-122)
+// and the max_tail_factor mask (_adjustment.py:647-658, 672-673).  grid = (ceil(n_pts / C), n_groups).
+// The reference breaks rank ties with numpy's global RNG and fills with np.random.random_sample; here both
+// draws are counter-based hashes of (seed, element), so parity of the random part is distributional.
+// =============================================================================================
+template <typename T, int C>
+__global__ void __launch_bounds__(kThreads)
+adapt_apply_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long st,
+                   const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows, int n_groups,
+                   double thresh, const double* __restrict__ P0_ref, const double* __restrict__ P0_hist,
+                   const T* __restrict__ pth, unsigned long long seed, T* __restrict__ out, int n_pad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sum = reinterpret_cast<double*>(smem_raw);
+  int* cnt = reinterpret_cast<int*>(sum + C);
+  int* nle = cnt + C;
+  T* sm = reinterpret_cast<T*>(smem_raw + C * 16);
+  const int g = blockIdx.y;
+  const long long n0 = (long long)blockIdx.x * C;
+  const int m0 = mem_off[g], n_mem = mem_off[g + 1] - m0;
+  if (n_mem == 0) return;
+  load_segment<T, C>(sm, sim, n0, n_pts, sp, st, mem_rows + m0, n_mem, n_pad);
+  __syncthreads();
+  count_le_columns<T, C>(sm, n_pad, cnt, nle, thresh);
+  if (threadIdx.x < C) sum[threadIdx.x] = (double)nle[threadIdx.x] / (double)cnt[threadIdx.x];  // P0_sim
+  __syncthreads();
+  make_keys<T, C>(sm, n_pad, cnt, sum, 0, XSDBA_KIND_ADD);
+  sort_columns<T, C>(sm, n_pad);
+  for (int item = threadIdx.x; item < n_mem * C; item += blockDim.x) {
+    const int c = item % C, m = item / C;
+    const long long pt = n0 + c;
+    if (pt >= n_pts) continue;
+    const long long o = pt * sp + (long long)mem_rows[m0 + m] * st;
+    const T x = sim[o];
+    T res = x;
+    const int n = cnt[c];
+    const long long og = pt * n_groups + g;
+    const double p0r = P0_ref[og], p0h = P0_hist[og], p0s = sum[c];
+    const double dp0 = p0h == 0.0 ? Num<double>::nan() : (p0h - p0r) / p0h;
+    if (!is_nan(x) && dp0 > 0.0 && n > 1) {
+      const T* col = sm + c;
+      int lo = 0, hi = n;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[(size_t)mid * C] < x) lo = mid + 1; else hi = mid; }
+      const int lb = lo;
+      hi = n;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[(size_t)mid * C] <= x) lo = mid + 1; else hi = mid; }
+      const int ub = lo;
+      // random tie-break: a uniformly drawn position inside the tie block (utils.py:618-627)
+      const unsigned long long id = (unsigned long long)o;
+      int r0 = lb + (int)(hash_uniform(seed, 2 * id) * (double)(ub - lb));
+      r0 = r0 > ub - 1 ? ub - 1 : r0;
+      const double rnk = (double)r0 / (double)(n - 1);
+      const bool keep = (rnk < (p0r / p0h) * p0s) || (rnk > p0s);
+      if (!keep) res = (T)(((double)pth[og] - thresh) * (double)(T)hash_uniform(seed, 2 * id + 1) + thresh);
+    }
+    out[o] = res;
+  }
+}
+
+// scen = where(adapted_sim > max_tail_factor * hist_q_raw[..., -1] (broadcast nearest), adapted_sim, scen)
+template <typename T>
+__global__ void tail_mask_kernel(const T* __restrict__ adapted, long long n_pts, long long sp, long long st, int n_time,
+                                 const int32_t* __restrict__ gidx, int n_groups, const T* __restrict__ hq_raw, int nq,
+                                 double factor, T* __restrict__ scen) {
+  const long long total = n_pts * n_time;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long pt = sp == 1 ? e % n_pts : e / n_time;
+    const int t = (int)(sp == 1 ? e / n_pts : e % n_time);
+    const int g = gidx[t];
+    if (g < 0) continue;
+    const long long o = pt * sp + (long long)t * st;
+    const T a = adapted[o];
+    const T lastq = hq_raw[(pt * n_groups + g) * nq + nq - 1];
+    if ((double)a > factor * (double)lastq) scen[o] = a;
+  }
+}
+
 // elementwise jitter (processing.jitter / jitter_under_thresh / jitter_over_thresh, processing.py:124-257)
 template <typename T>
 __global__ void jitter_kernel(const T* __restrict__ x, long long n, JitterParams jp, T* __restrict__ out) {
@@ -1517,14 +1686,14 @@ template <typename K> int set_smem(K kernel, size_t bytes) {
 template <typename T, int C>
 int launch_train_c(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
                    const T* q, int nq, int kind, int normalize, int mode, T* af, T* hq, T* scaling, int n_pad,
-                   cudaStream_t s, const JitterParams& jp, int use_jitter, const double* q64) {
+                   cudaStream_t s, const JitterParams& jp, int use_jitter, const double* q64, const AdaptParams& ap) {
   const size_t smem = (size_t)C * 24 + ((size_t)nq * C + (size_t)n_pad * C) * sizeof(T);
   auto kern = train_kernel<T, C>;
   int rc = set_smem(kern, smem);
   if (rc) return rc;
   dim3 grid((unsigned)((n_pts + C - 1) / C), (unsigned)grp->n_groups);
   kern<<<grid, kThreads, smem, s>>>(ref, hist, n_pts, sp, st, grp->segments.off, grp->segments.rows, grp->n_groups, q,
-                                    nq, kind, normalize, mode, af, hq, scaling, n_pad, jp, use_jitter, q64);
+                                    nq, kind, normalize, mode, af, hq, scaling, n_pad, jp, use_jitter, q64, ap);
   ++g_launches;
   return cuda_status(cudaGetLastError());
 }
@@ -1564,7 +1733,8 @@ bool launch_train_fast(const double*, const double*, int64_t, int64_t, int64_t, 
 template <typename T>
 int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
                  const T* q, int nq, int kind, int normalize, int mode, T* af, T* hq, T* scaling, void* stream,
-                 const double* jitter = nullptr, unsigned long long seed = 0, const double* q64 = nullptr) {
+                 const double* jitter = nullptr, unsigned long long seed = 0, const double* q64 = nullptr,
+                 const AdaptParams* adapt = nullptr) {
   int fast_rc = 0;
   JitterParams jp;
   const double dnan = __builtin_nan("");
@@ -1580,9 +1750,12 @@ int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t
   const int n_pad = std::max(2, next_pow2(grp->segments.max_len));
   const int C = pick_cols<T>(n_pad);
   cudaStream_t s = (cudaStream_t)stream;
-  if (launch_train_fast(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, s, &fast_rc, jp, use_jitter, q64))
+  AdaptParams ap{};
+  if (adapt) ap = *adapt;
+  if (!ap.on &&
+      launch_train_fast(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, s, &fast_rc, jp, use_jitter, q64))
     return fast_rc;
-#define XS_CASE(CC) case CC: return launch_train_c<T, CC>(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, n_pad, s, jp, use_jitter, q64)
+#define XS_CASE(CC) case CC: return launch_train_c<T, CC>(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, n_pad, s, jp, use_jitter, q64, ap)
   switch (C) {
     XS_CASE(32); XS_CASE(16); XS_CASE(8); XS_CASE(4); XS_CASE(2); XS_CASE(1);
     default: return XSDBA_ERR_SEGMENT_TOO_LONG;
@@ -1900,6 +2073,52 @@ int launch_select(const T* x, const T* y, int64_t n_pts, int64_t sp, int64_t st,
 #undef XS_CASE
 }
 
+template <typename T, int C>
+int launch_adapt_apply_c(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, double thresh,
+                         const double* p0r, const double* p0h, const T* pth, unsigned long long seed, T* out, int n_pad,
+                         cudaStream_t s) {
+  const size_t smem = (size_t)C * 16 + (size_t)n_pad * C * sizeof(T);
+  auto kern = adapt_apply_kernel<T, C>;
+  int rc = set_smem(kern, smem);
+  if (rc) return rc;
+  dim3 grid((unsigned)((n_pts + C - 1) / C), (unsigned)grp->n_groups);
+  kern<<<grid, kThreads, smem, s>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows, grp->n_groups, thresh, p0r,
+                                    p0h, pth, seed, out, n_pad);
+  ++g_launches;
+  return cuda_status(cudaGetLastError());
+}
+
+template <typename T>
+int launch_adapt_apply(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, double thresh,
+                       const double* p0r, const double* p0h, const T* pth, unsigned long long seed, T* out, void* stream) {
+  if (!sim || !grp || !p0r || !p0h || !pth || !out || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
+  if (n_pts == 0) return XSDBA_OK;
+  const int n_pad = std::max(2, next_pow2(grp->members.max_len));
+  const int C = pick_cols<T>(n_pad);
+  cudaStream_t s = (cudaStream_t)stream;
+#define XS_CASE(CC) case CC: return launch_adapt_apply_c<T, CC>(sim, n_pts, sp, st, grp, thresh, p0r, p0h, pth, seed, out, n_pad, s)
+  switch (C) {
+    XS_CASE(32); XS_CASE(16); XS_CASE(8); XS_CASE(4); XS_CASE(2); XS_CASE(1);
+    default: return XSDBA_ERR_SEGMENT_TOO_LONG;
+  }
+#undef XS_CASE
+}
+
+template <typename T>
+int launch_tail_mask(const T* adapted, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* hq_raw,
+                     int nq, double factor, T* scen, void* stream) {
+  if (!adapted || !grp || !hq_raw || !scen || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (sp != 1 && st != 1) return XSDBA_ERR_UNSUPPORTED;
+  if (n_pts == 0) return XSDBA_OK;
+  const int64_t total = n_pts * grp->n_time;
+  const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 32);
+  tail_mask_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(adapted, n_pts, sp, st, (int)grp->n_time, grp->gidx,
+                                                                grp->n_groups, hq_raw, nq, factor, scen);
+  ++g_launches;
+  return cuda_status(cudaGetLastError());
+}
+
 template <typename T>
 int launch_rotate(const T* x, int64_t n_elem, int n_var, const float* rot_host, T* y, void* stream) {
   if (!x || !y || !rot_host || n_var < 1 || n_var > kMaxVar || n_elem < 0 || x == y) return XSDBA_ERR_INVALID_ARGUMENT;
@@ -2154,6 +2373,43 @@ int xsdba_map_cdf_f32(const float* x, const float* y, int64_t n_pts, int64_t sp,
 int xsdba_map_cdf_f64(const double* x, const double* y, int64_t n_pts, int64_t sp, int64_t st,
                       const xsdba_grouping_t* grp, const double* yvals, int32_t nv, double* out, void* stream) {
   return launch_select<double>(x, y, n_pts, sp, st, grp, 1, nullptr, yvals, nv, out, stream);
+}
+
+int xsdba_qm_train_adapt_f32(const float* ref, const float* hist, int64_t n_pts, int64_t sp, int64_t st,
+                             const xsdba_grouping_t* grp, const float* q, int32_t nq, int32_t kind,
+                             const double* jitter4_host, double adapt_thresh, uint64_t seed, float* af, float* hq,
+                             double* P0_ref, double* P0_hist, float* pth, void* stream) {
+  if (!P0_ref || !P0_hist || !pth || !(adapt_thresh == adapt_thresh)) return XSDBA_ERR_INVALID_ARGUMENT;
+  AdaptParams ap{1, adapt_thresh, seed, P0_ref, P0_hist, pth};
+  return launch_train<float>(ref, hist, n_pts, sp, st, grp, q, nq, kind, 0, 0, af, hq, nullptr, stream, jitter4_host, seed,
+                             nullptr, &ap);
+}
+int xsdba_qm_train_adapt_f64(const double* ref, const double* hist, int64_t n_pts, int64_t sp, int64_t st,
+                             const xsdba_grouping_t* grp, const double* q, int32_t nq, int32_t kind,
+                             const double* jitter4_host, double adapt_thresh, uint64_t seed, double* af, double* hq,
+                             double* P0_ref, double* P0_hist, double* pth, void* stream) {
+  if (!P0_ref || !P0_hist || !pth || !(adapt_thresh == adapt_thresh)) return XSDBA_ERR_INVALID_ARGUMENT;
+  AdaptParams ap{1, adapt_thresh, seed, P0_ref, P0_hist, pth};
+  return launch_train<double>(ref, hist, n_pts, sp, st, grp, q, nq, kind, 0, 0, af, hq, nullptr, stream, jitter4_host, seed,
+                              nullptr, &ap);
+}
+int xsdba_adapt_freq_apply_f32(const float* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                               double thresh, const double* P0_ref, const double* P0_hist, const float* pth, uint64_t seed,
+                               float* out, void* stream) {
+  return launch_adapt_apply<float>(sim, n_pts, sp, st, grp, thresh, P0_ref, P0_hist, pth, seed, out, stream);
+}
+int xsdba_adapt_freq_apply_f64(const double* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                               double thresh, const double* P0_ref, const double* P0_hist, const double* pth,
+                               uint64_t seed, double* out, void* stream) {
+  return launch_adapt_apply<double>(sim, n_pts, sp, st, grp, thresh, P0_ref, P0_hist, pth, seed, out, stream);
+}
+int xsdba_tail_mask_f32(const float* adapted, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                        const float* hq_raw, int32_t nq, double factor, float* scen, void* stream) {
+  return launch_tail_mask<float>(adapted, n_pts, sp, st, grp, hq_raw, nq, factor, scen, stream);
+}
+int xsdba_tail_mask_f64(const double* adapted, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                        const double* hq_raw, int32_t nq, double factor, double* scen, void* stream) {
+  return launch_tail_mask<double>(adapted, n_pts, sp, st, grp, hq_raw, nq, factor, scen, stream);
 }
 
 int xsdba_poly_trend_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
