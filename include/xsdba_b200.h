@@ -195,6 +195,27 @@ int xsdba_qdm_adjust_f64(const double* sim_dev, int64_t n_pts, int64_t stride_pt
                          double* scen_dev, double* sim_q_dev, void* cuda_stream);
 
 /*
+ * Adjust (QDM) with grouped interp="linear" (SURVEY.md 8f rank 2): the point set of SciPy's
+ * LinearNDInterpolator is the regular lattice (quantile node, padded group coordinate), identical for every
+ * gridpoint (_adjustment.py:873-880), so the Qhull triangulation is computed once on the host
+ * (scipy.spatial.Delaunay, the reference's own dependency) and only its per-cell diagonal choice is uploaded:
+ * diag_dev[(n_groups+1) * (nq-1)] uint8, 0 = diagonal (r,k)-(r+1,k+1), 1 = (r,k+1)-(r+1,k).  gcoord_dev[n_time]
+ * is the fractional padded group coordinate of every time step (Grouper.get_index(interp=True),
+ * base.py:306-320).  Factors must be NaN free.  (EQM/DQM grouped linear needs a per-gridpoint triangulation:
+ * still XSDBA_ERR_UNSUPPORTED.)
+ */
+int xsdba_qdm_adjust_linear_f32(const float* sim_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                                const xsdba_grouping_t* grp, const float* af_dev, const float* q_dev, int32_t nq,
+                                int32_t extrap, int32_t kind, int32_t rank_window, const double* gcoord_dev,
+                                const unsigned char* diag_dev, float* scen_dev, double* sim_q_dev,
+                                void* cuda_stream);
+int xsdba_qdm_adjust_linear_f64(const double* sim_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                                const xsdba_grouping_t* grp, const double* af_dev, const double* q_dev, int32_t nq,
+                                int32_t extrap, int32_t kind, int32_t rank_window, const double* gcoord_dev,
+                                const unsigned char* diag_dev, double* scen_dev, double* sim_q_dev,
+                                void* cuda_stream);
+
+/*
  * Percentile ranks only: replaces Grouper.apply(utils.rank, x, main_only = !rank_window, pct = True).
  */
 int xsdba_group_rank_f32(const float* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,

@@ -494,3 +494,30 @@ def test_adapt_freq_adjust_and_tail_factor():
     assert mask.sum() > 0 and bits_equal(scen[mask], ad[mask])
     plain = _np(xs.EmpiricalQuantileMapping(obj.ds, obj.group, "*", adapt_freq_thresh="0.05 mm/d").adjust(sim, time=tx))
     assert bits_equal(np.where(mask, 0, scen), np.where(mask, 0, plain))
+
+
+@pytest.mark.parametrize("group,years,nq,dt,kind,var", [("time.month", 4, 20, np.float32, "+", "tas"),
+                                                        ("time.month", 3, 50, np.float64, "*", "pr"),
+                                                        ("time.dayofyear", 4, 30, np.float32, "+", "tas")])
+@pytest.mark.parametrize("extrap", ["constant", "nan"])
+def test_qdm_adjust_grouped_linear_matches_oracle(group, years, nq, dt, kind, var, extrap):
+    """QDM with grouped interp="linear" (SciPy LinearNDInterpolator on the shared (quantile, group) lattice):
+    sim_q bit-exact, scen within 1e-6 (f32) / 1e-12 (f64) relative of the oracle, which calls SciPy itself."""
+    xs = _xs()
+    window = 1
+    case = (group, window, "noleap", years, nq, kind, var, dt)
+    tx, to, ref, hist, sim = _make(case, n_pts=7)
+    ref[:, 3] = synth.tas(np.random.default_rng(9), to, 1, "ref", dt)[:, 0] if var == "tas" else synth.pr(np.random.default_rng(9), to, 1, "ref", dt)[:, 0]
+    hist[:, 3] = ref[:, 3] * 1.01; hist[:, 4] = ref[:, 4] * 0.99   # (no all-NaN tables: NaN factors are not built for linear)
+    q = o.equally_spaced_nodes(nq).astype(dt)
+    gidx, G, _ = o.group_index(to, group)
+    af_o, _ = o.eqm_train(ref.T.copy(), hist.T.copy(), gidx, G, window, q, kind)
+    assert np.isfinite(af_o).all()
+    scen_o, simq_o = o.qdm_adjust(sim.T.copy(), af_o, q, group=group, time=to, window=window, interp="linear",
+                                  extrapolation=extrap, kind=kind)
+    out = xs.qdm_adjust(xs.Dataset({"sim": sim, "af": af_o, "quantiles": q}, time=tx), group=group, interp="linear",
+                        extrapolation=extrap, kind=kind)
+    assert bits_equal(_np(out.sim_q).T, simq_o)
+    scen = _np(out.scen).T
+    assert (np.isnan(scen) == np.isnan(scen_o)).all()
+    np.testing.assert_allclose(scen, scen_o, rtol=1e-6 if dt == np.float32 else 1e-12, atol=0, equal_nan=True)

@@ -278,6 +278,39 @@ def qm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None,
     return Dataset({"scen": scen}, time=time, time_axis=0 if st != 1 or sim.ndim == 1 else -1)
 
 
+_GEOM_CACHE: dict = {}
+
+
+def _qdm_linear_geometry(group, time, q, n_groups):
+    """Host part of grouped ``interp="linear"`` for QDM: the fractional group coordinate of every time step
+    (``Grouper.get_index(interp=True)``, base.py:306-320) and, from ONE Qhull triangulation of the lattice
+    (quantile node, padded group coordinate) -- the point set SciPy's ``griddata(method="linear")`` receives for
+    every gridpoint (utils.py:391-396) -- which diagonal splits each lattice cell."""
+    if group.prop not in ("month", "dayofyear"):
+        raise NotImplementedError(f"linear interpolation over time.{group.prop} groups is not built yet")
+    qn = q.detach().cpu().numpy().astype(np.float64)
+    key = (group.prop, n_groups, qn.tobytes())
+    if key not in _GEOM_CACHE:
+        from scipy.spatial import Delaunay  # SciPy is the reference's own dependency for this step
+        gg = np.arange(n_groups + 2, dtype=np.float64)
+        X, Y = np.meshgrid(qn, gg)
+        tri = Delaunay(np.stack([X.ravel(), Y.ravel()], axis=1))
+        nq = qn.size
+        diag = np.full((n_groups + 1, nq - 1), 255, np.uint8)
+        for smp in tri.simplices:
+            r, k = smp // nq, smp % nq
+            r0, k0 = int(r.min()), int(k.min())
+            if r.max() - r0 != 1 or k.max() - k0 != 1:
+                raise RuntimeError("unexpected Qhull simplex on the quantile lattice")
+            corners = set(zip((r - r0).tolist(), (k - k0).tolist()))
+            diag[r0, k0] = 0 if {(0, 0), (1, 1)} <= corners else 1
+        if (diag == 255).any():
+            raise RuntimeError("incomplete Qhull triangulation of the quantile lattice")
+        _GEOM_CACHE[key] = _as_device(diag).contiguous()
+    gcoord = _as_device(np.asarray(group.get_index(time, interp=True), np.float64)).contiguous()
+    return gcoord, _GEOM_CACHE[key]
+
+
 def qdm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None, rank_window=None,
                max_tail_factor=None, seed=0):
     """``xsdba._adjustment.qdm_adjust`` (_adjustment.py:783-886): ds holds af, quantiles, sim."""
@@ -301,10 +334,19 @@ def qdm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None
         sim = _adapt_freq_preprocess(ds, sim, n_pts, sp, st, group, time, dt, adapt_freq_thresh, seed)
     scen = torch.empty_like(sim)
     sim_q = torch.empty(sim.shape, dtype=torch.float64, device=sim.device)
-    fn = getattr(lib, f"xsdba_qdm_adjust_{_sfx(dt)}")
-    status = fn(sim.data_ptr(), n_pts, sp, st, h.ptr, af.data_ptr(), q.data_ptr(), nq, _lib.INTERP[interp],
-                _lib.EXTRAP[extrapolation], _lib.KIND[kind], 1 if rank_window else 0, scen.data_ptr(),
-                sim_q.data_ptr(), _stream())
+    if interp == "linear" and h.n_groups > 1:
+        gcoord, diag = _qdm_linear_geometry(group, time, q, h.n_groups)
+        if bool(torch.isnan(af).any()):
+            raise NotImplementedError("grouped linear interpolation with NaN adjustment factors is not built yet")
+        fn = getattr(lib, f"xsdba_qdm_adjust_linear_{_sfx(dt)}")
+        status = fn(sim.data_ptr(), n_pts, sp, st, h.ptr, af.data_ptr(), q.data_ptr(), nq, _lib.EXTRAP[extrapolation],
+                    _lib.KIND[kind], 1 if rank_window else 0, gcoord.data_ptr(), diag.data_ptr(), scen.data_ptr(),
+                    sim_q.data_ptr(), _stream())
+    else:
+        fn = getattr(lib, f"xsdba_qdm_adjust_{_sfx(dt)}")
+        status = fn(sim.data_ptr(), n_pts, sp, st, h.ptr, af.data_ptr(), q.data_ptr(), nq, _lib.INTERP[interp],
+                    _lib.EXTRAP[extrapolation], _lib.KIND[kind], 1 if rank_window else 0, scen.data_ptr(),
+                    sim_q.data_ptr(), _stream())
     _lib.check(status, "qdm_adjust")
     if max_tail_factor is not None:
         scen = _apply_tail_mask(ds, sim, scen, n_pts, sp, st, group, time, dt, max_tail_factor)

@@ -334,6 +334,52 @@ __device__ __forceinline__ T lookup_2d_nearest(const Tables<T, C>& tb, int c, lo
   return o[0];
 }
 
+// 2-D "linear" rule on the shared quantile axis (QDM, _adjustment.py:873-880): scipy griddata(method="linear") =
+// LinearNDInterpolator on the regular lattice (q_k, g'), g' the cyclically padded group coordinate.  Qhull splits
+// every lattice cell into two triangles; which diagonal it uses is data independent and comes from the host
+// (diag[(padded row) * (nq-1) + k], 0: (r,k)-(r+1,k+1), 1: (r,k+1)-(r+1,k)).  Barycentric weights in float64.
+// Staged slots 0,1,2 hold padded rows g, g+1, g+2 (no NaN factors: the host checks).  newg is the fractional
+// padded coordinate of the sample (Grouper.get_index(interp=True), base.py:306-320).
+template <typename T, int C>
+__device__ T lookup_2d_linear_shared(const Tables<T, C>& tb, int c, int g, double x, double newg,
+                                     const unsigned char* __restrict__ diag, int extrap) {
+  if (x != x || newg != newg) return Num<T>::nan();
+  const int nq = tb.nq;
+  const int pr0 = (int)floor(newg);
+  const double v = newg - (double)pr0;
+  int s0 = pr0 - g;                       // slot of the lower row
+  if (s0 < 0 || s0 > 2 || (v > 0.0 && s0 > 1)) return Num<T>::nan();
+  const int s1 = v > 0.0 ? s0 + 1 : s0;
+  const T* xs = tb.xsl[1] + c;            // the quantile axis is the same in every row
+  const T* y0 = tb.ysl[s0] + c;
+  const T* y1 = tb.ysl[s1] + c;
+  const double q_first = (double)xs[0], q_last = (double)xs[(size_t)(nq - 1) * C];
+  if (x < q_first || x > q_last) {
+    // outside the convex hull -> NaN from griddata, then _extrapolate_on_quantiles (nbutils.py:397-416) unless "nan"
+    if (extrap != 0) return Num<T>::nan();
+    const int k = x < q_first ? 0 : nq - 1;
+    const double f0 = (double)y0[(size_t)k * C], f1 = (double)y1[(size_t)k * C];
+    if (v == 0.0) return (T)f0;
+    const double slope = __ddiv_rn(__dsub_rn(f1, f0), 1.0);   // np.interp between two padded rows
+    return (T)__dadd_rn(__dmul_rn(slope, v), f0);
+  }
+  int k = lower_bound_bf<double, T, C>(xs, nq, x, tb.top) - 1;  // last node <= x ... (nodes < x) - 1
+  if (k < 0) k = 0;
+  if (k > nq - 2) k = nq - 2;
+  const double qk = (double)xs[(size_t)k * C], qk1 = (double)xs[(size_t)(k + 1) * C];
+  const double u = (x - qk) / (qk1 - qk);
+  const double yA = (double)y0[(size_t)k * C], yB = (double)y0[(size_t)(k + 1) * C];
+  if (v == 0.0) return (T)(yA * (1.0 - u) + yB * u);
+  const double yD = (double)y1[(size_t)k * C], yC = (double)y1[(size_t)(k + 1) * C];
+  double r;
+  if (diag[(size_t)pr0 * (nq - 1) + k] == 0) {   // diagonal A-C
+    r = v <= u ? yA * (1.0 - u) + yB * (u - v) + yC * v : yA * (1.0 - v) + yD * (v - u) + yC * u;
+  } else {                                        // diagonal B-D
+    r = u + v <= 1.0 ? yA * (1.0 - u - v) + yB * u + yD * v : yC * (u + v - 1.0) + yB * (1.0 - v) + yD * (1.0 - u);
+  }
+  return (T)r;
+}
+
 template <typename T> __device__ __forceinline__ T apply_corr(T x, T f, int kind) {
   return kind == 43 ? Num<T>::add(x, f) : Num<T>::mul(x, f);  // utils.py:146-162
 }

@@ -1249,7 +1249,8 @@ rank_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long 
             const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows,
             const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
             const T* __restrict__ af, const T* __restrict__ q, int nq, int interp, int extrap, int kind,
-            int do_adjust, T* __restrict__ scen, double* __restrict__ sim_q, int n_pad, int rank_mode) {
+            int do_adjust, T* __restrict__ scen, double* __restrict__ sim_q, int n_pad, int rank_mode,
+            const double* __restrict__ gcoord, const unsigned char* __restrict__ diag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* mnmx = reinterpret_cast<double*>(smem_raw);      // [2][C]
   double* sum = mnmx + 2 * C;                              // [C] (unused sum slot of count_columns)
@@ -1328,8 +1329,11 @@ rank_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long 
     }
     if (sim_q) sim_q[o] = sq;
     if (do_adjust) {
-      const T f = grouped ? lookup_2d_nearest<double, T, C>(tb, c, pt, g, sq, extrap)
-                          : lookup_1d<double, T, C>(tb, c, sq, interp, extrap);
+      T f;
+      if (!grouped) f = lookup_1d<double, T, C>(tb, c, sq, interp, extrap);
+      else if (interp == XSDBA_INTERP_LINEAR)
+        f = lookup_2d_linear_shared<T, C>(tb, c, g, sq, gcoord[mem_rows[m0 + item / C]], diag, extrap);
+      else f = lookup_2d_nearest<double, T, C>(tb, c, pt, g, sq, extrap);
       scen[o] = apply_corr<T>(x, f, kind);
     }
   }
@@ -1870,7 +1874,8 @@ int launch_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsd
 template <typename T, int C>
 int launch_rank_c(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
                   const DevTable& seg, const T* af, const T* q, int nq, int interp, int extrap, int kind,
-                  int do_adjust, T* scen, double* sim_q, int n_pad, cudaStream_t s, int rank_mode) {
+                  int do_adjust, T* scen, double* sim_q, int n_pad, cudaStream_t s, int rank_mode, const double* gcoord,
+                  const unsigned char* diag) {
   const size_t head = (size_t)C * 28 + (((size_t)C * 28) % 8 ? 4 : 0);
   const size_t smem = head + (size_t)n_pad * C * sizeof(T) +
                       (do_adjust ? ((tables_bytes<T, C>(nq) + 15) & ~(size_t)15) + stage_bytes<T, C>(nq) : tables_bytes<T, C>(0));
@@ -1881,7 +1886,7 @@ int launch_rank_c(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsd
   dim3 grid((unsigned)((n_pts + C - 1) / C), (unsigned)grp->n_groups);
   kern<<<grid, kThreads, smem, s>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows, seg.off, seg.rows,
                                     grp->n_groups, af, q, do_adjust ? nq : 0, interp, extrap, kind, do_adjust, scen,
-                                    sim_q, n_pad, rank_mode);
+                                    sim_q, n_pad, rank_mode, gcoord, diag);
   ++g_launches;
   return cuda_status(cudaGetLastError());
 }
@@ -1889,14 +1894,15 @@ int launch_rank_c(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsd
 template <typename T>
 int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* af,
                 const T* q, int nq, int interp, int extrap, int kind, int rank_window, int do_adjust, T* scen,
-                double* sim_q, void* stream, int rank_mode = 0) {
+                double* sim_q, void* stream, int rank_mode = 0, const double* gcoord = nullptr,
+                const unsigned char* diag = nullptr) {
   if (!sim || !grp || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (do_adjust) {
     if (!af || !q || !scen || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
     if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
     if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR) return XSDBA_ERR_INVALID_ARGUMENT;
     if (extrap != XSDBA_EXTRAP_CONSTANT && extrap != XSDBA_EXTRAP_NAN) return XSDBA_ERR_INVALID_ARGUMENT;
-    if (grp->n_groups > 1 && interp != XSDBA_INTERP_NEAREST) return XSDBA_ERR_UNSUPPORTED;
+    if (grp->n_groups > 1 && interp != XSDBA_INTERP_NEAREST && !(gcoord && diag)) return XSDBA_ERR_UNSUPPORTED;
   } else if (!sim_q) {
     return XSDBA_ERR_INVALID_ARGUMENT;
   }
@@ -1916,7 +1922,7 @@ int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba
   };
   while (C > 1 && need(C) > 216 * 1024) C >>= 1;
   cudaStream_t s = (cudaStream_t)stream;
-#define XS_CASE(CC) case CC: return launch_rank_c<T, CC>(sim, n_pts, sp, st, grp, seg, af, q, nq, interp, extrap, kind, do_adjust, scen, sim_q, n_pad, s, rank_mode)
+#define XS_CASE(CC) case CC: return launch_rank_c<T, CC>(sim, n_pts, sp, st, grp, seg, af, q, nq, interp, extrap, kind, do_adjust, scen, sim_q, n_pad, s, rank_mode, gcoord, diag)
   switch (C) {
     XS_CASE(32); XS_CASE(16); XS_CASE(8); XS_CASE(4); XS_CASE(2); XS_CASE(1);
     default: return XSDBA_ERR_SEGMENT_TOO_LONG;
@@ -2334,6 +2340,22 @@ int xsdba_rank_lookup_f64(const double* sim, int64_t n_pts, int64_t sp, int64_t 
                           int32_t rank_window, int32_t rank_mode, double* scen, double* sim_q, void* stream) {
   return launch_rank<double>(sim, n_pts, sp, st, grp, af, q, nq, interp, extrap, kind, rank_window, 1, scen, sim_q, stream,
                              rank_mode);
+}
+int xsdba_qdm_adjust_linear_f32(const float* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                                const float* af, const float* q, int32_t nq, int32_t extrap, int32_t kind,
+                                int32_t rank_window, const double* gcoord, const unsigned char* diag, float* scen,
+                                double* sim_q, void* stream) {
+  if (!gcoord || !diag) return XSDBA_ERR_INVALID_ARGUMENT;
+  return launch_rank<float>(sim, n_pts, sp, st, grp, af, q, nq, XSDBA_INTERP_LINEAR, extrap, kind, rank_window, 1, scen,
+                            sim_q, stream, 0, gcoord, diag);
+}
+int xsdba_qdm_adjust_linear_f64(const double* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                                const double* af, const double* q, int32_t nq, int32_t extrap, int32_t kind,
+                                int32_t rank_window, const double* gcoord, const unsigned char* diag, double* scen,
+                                double* sim_q, void* stream) {
+  if (!gcoord || !diag) return XSDBA_ERR_INVALID_ARGUMENT;
+  return launch_rank<double>(sim, n_pts, sp, st, grp, af, q, nq, XSDBA_INTERP_LINEAR, extrap, kind, rank_window, 1, scen,
+                             sim_q, stream, 0, gcoord, diag);
 }
 int xsdba_rotate_f32(const float* x, int64_t n_elem, int32_t n_var, const float* rot_host, float* y, void* stream) {
   return launch_rotate<float>(x, n_elem, n_var, rot_host, y, stream);
