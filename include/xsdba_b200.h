@@ -301,6 +301,20 @@ int xsdba_map_cdf_f64(const double* x_dev, const double* y_dev, int64_t n_pts, i
                       double* out_dev, void* cuda_stream);
 
 /*
+ * Energy score: replaces processing.escore / nbutils._escore (processing.py:393-489; nbutils.py:274-372;
+ * SURVEY.md 8f rank 3) without the optional scaling: tgt and sim are (variable, time, point) arrays, variables
+ * var_stride_* elements apart, n_var <= 8; observations with a NaN in any variable are dropped; n_sub > 0
+ * keeps about n_sub evenly spaced observations of each cloud.  out_dev[n_pts].
+ */
+int xsdba_escore_f32(const float* tgt_dev, const float* sim_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                     int64_t n_time_tgt, int64_t n_time_sim, int32_t n_var, int64_t var_stride_tgt,
+                     int64_t var_stride_sim, int32_t n_sub, float* out_dev, void* cuda_stream);
+int xsdba_escore_f64(const double* tgt_dev, const double* sim_dev, int64_t n_pts, int64_t stride_pt,
+                     int64_t stride_time, int64_t n_time_tgt, int64_t n_time_sim, int32_t n_var,
+                     int64_t var_stride_tgt, int64_t var_stride_sim, int32_t n_sub, double* out_dev,
+                     void* cuda_stream);
+
+/*
  * Polynomial trend: replaces detrending.PolyDetrend.fit(...).ds.trend = _polydetrend_get_trend
  * (detrending.py:165-208; xarray polyfit/polyval per group through map_groups): y = x (+|*)
  * scaling[point][group] when scaling_dev != NULL (the scaled_sim of dqm_adjust, _adjustment.py:748-757),

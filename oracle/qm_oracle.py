@@ -1025,3 +1025,18 @@ def eqm_train_adapt_freq(ref, hist, gidx, n_groups, window, q, kind, thresh, rng
         af[:, g] = get_correction(hist_q, ref_q, kind)
         hq[:, g] = hist_q
     return af, hq, P0r, P0h, pth
+
+
+def escore(tgt, sim):
+    """``_escore`` (nbutils.py:347-372): tgt [K, N], sim [K, M] (float64)."""
+    sim = sim[:, ~np.isnan(sim).any(axis=0)]
+    tgt = tgt[:, ~np.isnan(tgt).any(axis=0)]
+    n1, n2 = sim.shape[1], tgt.shape[1]
+    if 0 in (n1, n2):
+        return np.nan
+    dist = lambda A, B: np.sqrt(((A[:, :, None] - B[:, None, :]) ** 2).sum(axis=0))  # noqa: E731
+    sXY = dist(tgt, sim).mean()
+    sXX = dist(tgt, tgt).sum() / tgt.shape[1] ** 2
+    sYY = dist(sim, sim).sum() / sim.shape[1] ** 2
+    w = n1 * n2 / (n1 + n2)
+    return w * (sXY + sXY - sXX - sYY) / 2

@@ -521,3 +521,53 @@ def test_qdm_adjust_grouped_linear_matches_oracle(group, years, nq, dt, kind, va
     scen = _np(out.scen).T
     assert (np.isnan(scen) == np.isnan(scen_o)).all()
     np.testing.assert_allclose(scen, scen_o, rtol=1e-6 if dt == np.float32 else 1e-12, atol=0, equal_nan=True)
+
+
+def test_escore_reference_kat_and_oracle():
+    xs = _xs()
+    # reference tests/test_processing.py:215-226 -- value from Cannon's MBC R package
+    x = np.array([1, 4, 3, 6, 4, 7, 5, 8, 4, 5, 3, 7], dtype=np.float64).reshape(2, 6)
+    y = np.array([6, 6, 3, 8, 5, 7, 3, 7, 3, 6, 4, 3], dtype=np.float64).reshape(2, 6)
+    np.testing.assert_allclose(o.escore(x, y), 1.90018550338863)
+    got = _np(xs.escore(x[:, :, None], y[:, :, None]))
+    np.testing.assert_allclose(got, [1.90018550338863], rtol=1e-13)
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(4, 300, 5)).astype(np.float32); B = (rng.normal(size=(4, 250, 5)) + 0.3).astype(np.float32)
+    A[1, 7, 2] = np.nan; B[0, 3, 2] = np.nan
+    got = _np(xs.escore(A, B))
+    want = [o.escore(A[:, :, p].astype(np.float64), B[:, :, p].astype(np.float64)) for p in range(5)]
+    np.testing.assert_allclose(got, want, rtol=2e-6)
+    sub = _np(xs.escore(A, B, N=100))
+    want = [o.escore(A[:, ::3, p].astype(np.float64), B[:, ::3, p].astype(np.float64)) for p in range(5)]
+    np.testing.assert_allclose(sub, want, rtol=2e-6)
+
+
+def test_mbcn_escores_decrease():
+    """MBCn.train(n_escore>0): the energy score between ref and the transformed hist is recorded after every
+    rotation (_adjustment.py:325-326) and goes down as the N-pdf transform converges."""
+    xs = _xs()
+    to, ref, hist, sim = _mbcn_inputs(2, 2)
+    tx = xs.TimeAxis.daily(1981, 2, "noleap")
+    obj = xs.MBCn.train(ref, hist, time=tx, base_kws={"nquantiles": 20, "group": "time"}, n_iter=6, n_escore=200, seed=3)
+    esc = _np(obj.ds["escores"])[0]           # (points, n_iter)
+    assert esc.shape == (2, 6) and np.isfinite(esc).all()
+    assert (esc[:, -1] < esc[:, 0]).all()
+
+
+def test_trained_object_roundtrip(tmp_path):
+    """A trained adjustment is just its tables (base.py:75-100; reference tests/test_adjustment.py:186-195):
+    save -> load -> adjust gives the same bits as adjusting with the in-memory object."""
+    xs = _xs()
+    case = ("time.dayofyear", 31, "noleap", 4, 50, "*", "pr", np.float32)
+    tx, to, ref, hist, sim = _make(case, n_pts=9)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)
+        qdm = xs.QuantileDeltaMapping.train(ref, hist, time=tx, nquantiles=50, group=xs.Grouper("time.dayofyear", 31), kind="*")
+        a = _np(qdm.adjust(sim, time=tx))
+        qdm.save(tmp_path / "qdm.npz")
+        qdm2 = xs.QuantileDeltaMapping.load(tmp_path / "qdm.npz")
+        assert qdm2.group.name == "time.dayofyear" and qdm2.group.window == 31 and qdm2.kind == "*"
+        assert bits_equal(_np(qdm2.adjust(sim, time=tx)), a)
+    with pytest.raises(ValueError):
+        xs.EmpiricalQuantileMapping.load(tmp_path / "qdm.npz")

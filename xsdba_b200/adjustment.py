@@ -43,6 +43,32 @@ class _TrainAdjust:
                            kind=kind, quantiles=quantiles, **kw)
         return cls(ds, group, kind, kw.get("adapt_freq_thresh"), kw.get("max_tail_factor"))
 
+    # -- trained object <-> file (the reference keeps a trained adjustment as an xr.Dataset with jsonpickled
+    #    parameters in attrs and round-trips it through netCDF + from_dataset, base.py:75-100; without xarray the
+    #    same content goes to a .npz: the tables as arrays, the parameters as a JSON string) -------------------
+    def save(self, path):
+        import json
+        arrays = {}
+        for k, v in self.ds.items():
+            if v is None:
+                continue
+            arrays[k] = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+        params = {"cls": type(self).__name__, "group": self.group.name, "window": self.group.window, "kind": self.kind,
+                  "adapt_freq_thresh": self.adapt_freq_thresh, "max_tail_factor": self.max_tail_factor}
+        np.savez(path, _xsdba_adjustment=np.array(json.dumps(params)), **arrays)
+
+    @classmethod
+    def load(cls, path):
+        import json
+        with np.load(path, allow_pickle=False) as f:
+            params = json.loads(str(f["_xsdba_adjustment"]))
+            ds = L4.Dataset({k: f[k] for k in f.files if k != "_xsdba_adjustment"})
+        if params["cls"] != cls.__name__:
+            raise ValueError(f"{path} holds a {params['cls']}, not a {cls.__name__}")
+        from .base import Grouper
+        return cls(ds, Grouper(params["group"], params["window"]), params["kind"], params["adapt_freq_thresh"],
+                   params["max_tail_factor"])
+
     def _extra(self):
         keys = [k for k in ("P0_ref", "P0_hist", "pth", "hist_q_raw") if self.ds.get(k) is not None]
         return {k: self.ds[k] for k in keys}

@@ -1656,6 +1656,98 @@ __global__ void tail_mask_kernel(const T* __restrict__ adapted, long long n_pts,
   }
 }
 
+// =============================================================================================
+// K10: energy score (nbutils._escore, nbutils.py:274-372; processing.escore, processing.py:393-489) --
+// Szekely-Rizzo e-distance between the K-variate clouds tgt (K x n2) and sim (K x n1) of every gridpoint.
+// Arrays are (variable, time, point) with variables var_stride apart; observations with a NaN in any
+// variable are removed per array (remove_NaNs).  One CTA per point; O(n1*n2*K) pair distances accumulated
+// in float64 (the reference accumulates in the data dtype under fastmath: its summation order is unpinned).
+//   out = n1*n2/(n1+n2) * (2*mean|X-Y| - mean|X-X'| - mean|Y-Y'|) / 2
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+escore_kernel(const T* __restrict__ tgt, const T* __restrict__ sim, long long n_pts, long long sp, long long st,
+              int n_time_t, int n_time_s, int step_t, int step_s, int n_var, long long var_stride_t,
+              long long var_stride_s, T* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int* idx_t = reinterpret_cast<int*>(smem_raw);                 // valid observation rows of tgt
+  int* idx_s = idx_t + (n_time_t + step_t - 1) / step_t;         // valid observation rows of sim
+  __shared__ int n_t, n_s;
+  __shared__ double red[3][kThreads / 32];
+  const long long pt = blockIdx.x;
+  if (threadIdx.x == 0) {  // compaction of the valid observations (serial: tiny next to the O(n^2) loops)
+    int a = 0;
+    for (int t = 0; t < n_time_t; t += step_t) {
+      bool ok = true;
+      for (int v = 0; v < n_var; ++v) ok = ok && !is_nan(tgt[v * var_stride_t + pt * sp + (long long)t * st]);
+      if (ok) idx_t[a++] = t;
+    }
+    n_t = a;
+    a = 0;
+    for (int t = 0; t < n_time_s; t += step_s) {
+      bool ok = true;
+      for (int v = 0; v < n_var; ++v) ok = ok && !is_nan(sim[v * var_stride_s + pt * sp + (long long)t * st]);
+      if (ok) idx_s[a++] = t;
+    }
+    n_s = a;
+  }
+  __syncthreads();
+  const int n2 = n_t, n1 = n_s;
+  double sxy = 0, sxx = 0, syy = 0;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    T xi[kMaxVar];
+    for (int v = 0; v < n_var; ++v) xi[v] = tgt[v * var_stride_t + pt * sp + (long long)idx_t[i] * st];
+    for (int j = 0; j < n1; ++j) {
+      double d1 = 0;
+      for (int v = 0; v < n_var; ++v) {
+        const double d = (double)xi[v] - (double)sim[v * var_stride_s + pt * sp + (long long)idx_s[j] * st];
+        d1 += d * d;
+      }
+      sxy += sqrt(d1);
+    }
+    for (int j = 0; j < i; ++j) {
+      double d1 = 0;
+      for (int v = 0; v < n_var; ++v) {
+        const double d = (double)xi[v] - (double)tgt[v * var_stride_t + pt * sp + (long long)idx_t[j] * st];
+        d1 += d * d;
+      }
+      sxx += sqrt(d1);
+    }
+  }
+  for (int i = threadIdx.x; i < n1; i += blockDim.x) {
+    T yi[kMaxVar];
+    for (int v = 0; v < n_var; ++v) yi[v] = sim[v * var_stride_s + pt * sp + (long long)idx_s[i] * st];
+    for (int j = 0; j < i; ++j) {
+      double d1 = 0;
+      for (int v = 0; v < n_var; ++v) {
+        const double d = (double)yi[v] - (double)sim[v * var_stride_s + pt * sp + (long long)idx_s[j] * st];
+        d1 += d * d;
+      }
+      syy += sqrt(d1);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sxy += __shfl_xor_sync(0xffffffffu, sxy, o);
+    sxx += __shfl_xor_sync(0xffffffffu, sxx, o);
+    syy += __shfl_xor_sync(0xffffffffu, syy, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sxy; red[1][threadIdx.x >> 5] = sxx; red[2][threadIdx.x >> 5] = syy; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0, c = 0;
+    for (int w = 0; w < kThreads / 32; ++w) { a += red[0][w]; b += red[1][w]; c += red[2][w]; }
+    double res = Num<double>::nan();
+    if (n1 > 0 && n2 > 0) {
+      const double mxy = a / ((double)n2 * (double)n1);
+      const double mxx = 2.0 * b / ((double)n2 * (double)n2);
+      const double myy = 2.0 * c / ((double)n1 * (double)n1);
+      const double w = (double)n1 * (double)n2 / (double)(n1 + n2);
+      res = w * (mxy + mxy - mxx - myy) / 2.0;
+    }
+    out[pt] = (T)res;
+  }
+}
+
 // elementwise jitter (processing.jitter / jitter_under_thresh / jitter_over_thresh, processing.py:124-257)
 template <typename T>
 __global__ void jitter_kernel(const T* __restrict__ x, long long n, JitterParams jp, T* __restrict__ out) {
@@ -2126,6 +2218,25 @@ int launch_tail_mask(const T* adapted, int64_t n_pts, int64_t sp, int64_t st, co
 }
 
 template <typename T>
+int launch_escore(const T* tgt, const T* sim, int64_t n_pts, int64_t sp, int64_t st, int64_t nt_t, int64_t nt_s, int n_var,
+                  int64_t vs_t, int64_t vs_s, int n_sub, T* out, void* stream) {
+  if (!tgt || !sim || !out || n_pts < 0 || n_var < 1 || n_var > kMaxVar || nt_t <= 0 || nt_s <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (n_pts == 0) return XSDBA_OK;
+  // N > 0: about N evenly spaced observations of each cloud (processing.py:459-464)
+  const int step_t = n_sub > 0 ? (int)((nt_t + n_sub - 1) / n_sub) : 1;
+  const int step_s = n_sub > 0 ? (int)((nt_s + n_sub - 1) / n_sub) : 1;
+  const size_t smem = sizeof(int) * ((nt_t + step_t - 1) / step_t + (nt_s + step_s - 1) / step_s);
+  if (smem > 200 * 1024) return XSDBA_ERR_SEGMENT_TOO_LONG;
+  auto kern = escore_kernel<T>;
+  int rc = set_smem(kern, smem);
+  if (rc) return rc;
+  kern<<<(unsigned)n_pts, kThreads, smem, (cudaStream_t)stream>>>(tgt, sim, n_pts, sp, st, (int)nt_t, (int)nt_s, step_t,
+                                                                  step_s, n_var, vs_t, vs_s, out);
+  ++g_launches;
+  return cuda_status(cudaGetLastError());
+}
+
+template <typename T>
 int launch_rotate(const T* x, int64_t n_elem, int n_var, const float* rot_host, T* y, void* stream) {
   if (!x || !y || !rot_host || n_var < 1 || n_var > kMaxVar || n_elem < 0 || x == y) return XSDBA_ERR_INVALID_ARGUMENT;
   if (n_elem == 0) return XSDBA_OK;
@@ -2356,6 +2467,18 @@ int xsdba_qdm_adjust_linear_f64(const double* sim, int64_t n_pts, int64_t sp, in
   if (!gcoord || !diag) return XSDBA_ERR_INVALID_ARGUMENT;
   return launch_rank<double>(sim, n_pts, sp, st, grp, af, q, nq, XSDBA_INTERP_LINEAR, extrap, kind, rank_window, 1, scen,
                              sim_q, stream, 0, gcoord, diag);
+}
+int xsdba_escore_f32(const float* tgt, const float* sim, int64_t n_pts, int64_t sp, int64_t st, int64_t n_time_tgt,
+                     int64_t n_time_sim, int32_t n_var, int64_t var_stride_tgt, int64_t var_stride_sim, int32_t n_sub,
+                     float* out, void* stream) {
+  return launch_escore<float>(tgt, sim, n_pts, sp, st, n_time_tgt, n_time_sim, n_var, var_stride_tgt, var_stride_sim, n_sub,
+                              out, stream);
+}
+int xsdba_escore_f64(const double* tgt, const double* sim, int64_t n_pts, int64_t sp, int64_t st, int64_t n_time_tgt,
+                     int64_t n_time_sim, int32_t n_var, int64_t var_stride_tgt, int64_t var_stride_sim, int32_t n_sub,
+                     double* out, void* stream) {
+  return launch_escore<double>(tgt, sim, n_pts, sp, st, n_time_tgt, n_time_sim, n_var, var_stride_tgt, var_stride_sim, n_sub,
+                               out, stream);
 }
 int xsdba_rotate_f32(const float* x, int64_t n_elem, int32_t n_var, const float* rot_host, float* y, void* stream) {
   return launch_rotate<float>(x, n_elem, n_var, rot_host, y, stream);

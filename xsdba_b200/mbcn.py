@@ -132,8 +132,10 @@ def _iter_rot(rots, ii):
     return rots[ii] if ii == 0 else rots[ii] @ rots[ii - 1].T  # _adjustment.py:310, 448
 
 
-def mbcn_train(ref, hist, *, time, rot_matrices, quantiles, group, interp="nearest", extrapolation="constant"):
-    """``mbcn_train`` (_adjustment.py:331-423): ref, hist (V, time, *points) -> af_q (n_blocks, *points, n_iter, V, nq)."""
+def mbcn_train(ref, hist, *, time, rot_matrices, quantiles, group, interp="nearest", extrapolation="constant",
+               n_escore=-1):
+    """``mbcn_train`` (_adjustment.py:331-423): ref, hist (V, time, *points) -> af_q (n_blocks, *points, n_iter, V, nq)
+    and, when ``n_escore > 0``, the energy score after every iteration (n_blocks, *points, n_iter)."""
     group = parse_group(group)
     ref, pshape = _prep(ref)
     hist, _ = _prep(hist, ref.dtype)
@@ -143,6 +145,7 @@ def mbcn_train(ref, hist, *, time, rot_matrices, quantiles, group, interp="neare
     q64 = L4._as_device(np.asarray(quantiles, np.float64)).contiguous()
     blocks = grouped_time_indexes(time, group)
     af_q = torch.empty((len(blocks), N, len(rots), V, q64.numel()), dtype=dt, device=ref.device)
+    escores = torch.full((len(blocks), N, len(rots)), float("nan"), dtype=dt, device=ref.device)
     for ib, (gw, _) in enumerate(blocks):
         idx = torch.as_tensor(gw, device=ref.device)
         blk = _Block(len(gw), N, dt)
@@ -155,7 +158,13 @@ def mbcn_train(ref, hist, *, time, rot_matrices, quantiles, group, interp="neare
                 af = blk.factors(r[iv], h[iv], q64)
                 af_q[ib, :, ii, iv, :] = af[:, 0, :]
                 h[iv] = blk.add_factor_at_rank(h[iv], af, q64, interp, extrapolation)
-    return af_q.reshape(len(blocks), *pshape, len(rots), V, q64.numel())
+            if n_escore > 0:  # _adjustment.py:307-308, 325-326
+                from .processing import escore
+                escores[ib, :, ii] = escore(r, h, N=n_escore)
+    af_q = af_q.reshape(len(blocks), *pshape, len(rots), V, q64.numel())
+    if n_escore > 0:
+        return af_q, escores.reshape(len(blocks), *pshape, len(rots))
+    return af_q
 
 
 def mbcn_adjust(ref, hist, sim, *, time, af_q, rot_matrices, quantiles, group, kinds, interp="nearest",
@@ -236,13 +245,14 @@ class MBCn:
         if group.name == "time.month":
             raise NotImplementedError("Received `group==time.month` in `base_kws`. Monthly grouping is not currently "
                                       "supported in the MBCn class.")  # adjustment.py:1851-1852
-        if n_escore >= 0:
-            raise NotImplementedError("escores are not built in xsdba_b200 yet (SURVEY.md 8f rank 3)")
+        if n_escore == 0:
+            raise NotImplementedError("n_escore=0 is a no-op in the reference (_adjustment.py:307, 325); use n_escore > 0")
         n_var = ref.shape[0]
         rots = rand_rot_matrix(n_var, n_iter, seed) if rot_matrices is None else np.asarray(rot_matrices, np.float32)
-        af_q = mbcn_train(ref, hist, time=time, rot_matrices=rots, quantiles=base_kws["nquantiles"], group=group,
-                          interp=adj_kws["interp"], extrapolation=adj_kws["extrapolation"])
-        ds = {"af_q": af_q, "rot_matrices": rots, "quantiles": np.asarray(base_kws["nquantiles"], np.float64)}
+        res = mbcn_train(ref, hist, time=time, rot_matrices=rots, quantiles=base_kws["nquantiles"], group=group,
+                         interp=adj_kws["interp"], extrapolation=adj_kws["extrapolation"], n_escore=n_escore)
+        af_q, esc = res if n_escore > 0 else (res, None)
+        ds = {"af_q": af_q, "escores": esc, "rot_matrices": rots, "quantiles": np.asarray(base_kws["nquantiles"], np.float64)}
         return cls(ds, group, adj_kws["interp"], adj_kws["extrapolation"])
 
     def adjust(self, sim, ref, hist, *, time, kinds=None):

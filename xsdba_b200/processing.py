@@ -60,3 +60,26 @@ def jitter_under_thresh(x, thresh, seed: int = 0):
 def jitter_over_thresh(x, thresh, upper_bnd, seed: int = 0):
     """processing.py:151-177."""
     return jitter(x, upper=thresh, maximum=upper_bnd, seed=seed)
+
+
+def escore(tgt, sim, N: int = 0, scale: bool = False):
+    """``xsdba.processing.escore`` (processing.py:393-489): energy score between the multivariate clouds ``tgt`` and
+    ``sim``, arrays (variable, time, *points) -> (*points,).  ``scale=True`` is not built."""
+    from ._adjustment import _as_device, _stream
+    if scale:
+        raise NotImplementedError("escore(scale=True) is not built in xsdba_b200 yet")
+    lib = _lib.load()
+    t = _as_device(tgt)
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float32)
+    s_ = _as_device(sim, t.dtype)
+    pshape = tuple(t.shape[2:])
+    t = t.reshape(t.shape[0], t.shape[1], -1).contiguous()
+    s_ = s_.reshape(s_.shape[0], s_.shape[1], -1).contiguous()
+    V, Tt, Np = t.shape
+    Ts = s_.shape[1]
+    out = torch.empty((Np,), dtype=t.dtype, device=t.device)
+    fn = getattr(lib, "xsdba_escore_f32" if t.dtype == torch.float32 else "xsdba_escore_f64")
+    _lib.check(fn(t.data_ptr(), s_.data_ptr(), Np, 1, Np, Tt, Ts, V, Tt * Np, Ts * Np, int(N), out.data_ptr(), _stream()),
+               "escore")
+    return out.reshape(pshape)
