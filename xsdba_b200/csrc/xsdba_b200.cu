@@ -558,9 +558,10 @@ __global__ void __launch_bounds__(kThreads)
 adjust_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long st,
               const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows, int n_groups,
               const T* __restrict__ af, const T* __restrict__ hist_q, int nq, int interp, int extrap, int kind,
-              T* __restrict__ scen) {
+              T* __restrict__ scen, const unsigned* __restrict__ gate_count = nullptr, unsigned gate_cap = 0) {
   constexpr int C = 32;
   constexpr int U = 4;
+  if (gate_count && *gate_count <= gate_cap) return;  // overflow fallback of K2t: nothing to redo
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Tables<T, C> tb = carve_tables<T, C>(smem_raw, nq);
   T* stage = reinterpret_cast<T*>(smem_raw + ((tables_bytes<T, C>(nq) + 15) & ~(size_t)15));
@@ -768,15 +769,73 @@ __device__ __noinline__ float lookup_exact_slots(const PackedSlot<LD>* const (&s
   return lookup_2d_nearest<float, float, 32>(tb, lane, pt, g, x, extrap);
 }
 
+// Exact 2-D nearest rule straight from the raw global tables (no staging): used for the few samples the
+// float32 fast path of K2t cannot decide (near-ties, far nodes, empty rows).  Same candidate order as
+// lookup_2d_nearest_n: centre row first, then rows at distance 1, 2, ... (-, +), nodes ascending, strict <.
+__device__ float exact_lookup_global(const float* __restrict__ hist_q, const float* __restrict__ af, long long pt, int G,
+                                     int nq, int g, float x, int extrap) {
+  if (x != x) return Num<float>::nan();
+  const long long base = pt * (long long)G * nq;
+  const float* xr = hist_q + base + (long long)g * nq;
+  const float* yr = af + base + (long long)g * nq;
+  float blo = Num<float>::nan(), bhi = blo, clo = blo, chi = blo;
+  bool hb = false, hc = false;
+  for (int k = 0; k < nq; ++k) {
+    const float xv = xr[k], yv = yr[k];
+    if (xv == xv) { if (!hb) { blo = xv; hb = true; } bhi = xv; }
+    if (yv == yv) { if (!hc) { clo = yv; hc = true; } chi = yv; }
+  }
+  const double xd = (double)x;
+  if (xd < (double)blo) return extrap == 0 ? clo : Num<float>::nan();
+  if (xd > (double)bhi) return extrap == 0 ? chi : Num<float>::nan();
+  double best_d2 = __longlong_as_double(0x7ff0000000000000LL);
+  float best_y = Num<float>::nan();
+  for (int dist = 0; dist <= G + 1; ++dist) {
+    const double dg2 = (double)dist * (double)dist;
+    if (dg2 >= best_d2) break;
+    for (int sgn = -1; sgn <= 1; sgn += 2) {
+      if (dist == 0 && sgn > 0) break;
+      const int pr = g + 1 + sgn * dist;  // padded row index in [0, G+1]
+      if (pr < 0 || pr > G + 1) continue;
+      const int gg = (pr - 1 + G) % G;
+      const float* gx = hist_q + base + (long long)gg * nq;
+      const float* gy = af + base + (long long)gg * nq;
+      for (int k = 0; k < nq; ++k) {
+        const float xv = gx[k], yv = gy[k];
+        if (xv != xv || yv != yv) continue;
+        const double d = fabs(xd - (double)xv);
+        const double d2 = __dadd_rn(__dmul_rn(d, d), dg2);
+        if (d2 < best_d2) { best_d2 = d2; best_y = yv; }
+      }
+    }
+  }
+  return best_y;
+}
+
+struct FixEntry { long long off; long long pt; float x; int g; };
+
+// second pass of K2t: the deferred samples (typically ~1e-4 of all) get the exact rule
+__global__ void adjust_fix_kernel(const FixEntry* __restrict__ fix, const unsigned* __restrict__ count, unsigned cap,
+                                  const float* __restrict__ af, const float* __restrict__ hist_q, int G, int nq, int extrap,
+                                  int kind, float* __restrict__ scen) {
+  const unsigned n = min(*count, cap);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const FixEntry e = fix[i];
+    const float f = exact_lookup_global(hist_q, af, e.pt, G, nq, e.g, e.x, extrap);
+    scen[e.off] = kind == XSDBA_KIND_ADD ? __fadd_rn(e.x, f) : __fmul_rn(e.x, f);
+  }
+}
+
 constexpr int kTileMaxRows = 1024;  // member rows of one group kept in shared memory by K2t (x2 buffers)
 
 template <int TOP>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp, long long st,
                    const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows, int n_groups,
                    const float* __restrict__ af, const float* __restrict__ hist_q, int nq,
-                   const PackedSlot<2 * TOP>* __restrict__ packed, int extrap, int kind, float* __restrict__ scen) {
-  constexpr int C = 32, U = 8, LD = 2 * TOP, RING = 4;
+                   const PackedSlot<2 * TOP>* __restrict__ packed, int extrap, int kind, float* __restrict__ scen,
+                   FixEntry* __restrict__ fix, unsigned* __restrict__ fix_count, unsigned fix_cap) {
+  constexpr int C = 32, U = 8, LD = 2 * TOP, RING = 2;  // centre rows only: current group + the next one in flight
   typedef PackedSlot<LD> Slot;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Slot* ring = reinterpret_cast<Slot*>(smem_raw);
@@ -799,21 +858,17 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  // extended row e in [-1, G] is group (e+G)%G and lives in ring slot (e+1)%RING
+  // the row of group e lives in ring slot e % RING (use number e / RING of that slot's mbarrier)
   auto fetch = [&](int e) {
-    const int s = (e + 1) % RING;
+    const int s = e % RING;
     mbar_expect_tx(&bars[s], (uint32_t)sizeof(Slot));
-    bulk_g2s(&ring[s], &my[(e + G) % G], (uint32_t)sizeof(Slot), &bars[s]);
+    bulk_g2s(&ring[s], &my[e], (uint32_t)sizeof(Slot), &bars[s]);
   };
-  if (threadIdx.x == 0) { fetch(-1); fetch(0); fetch(1 <= G ? 1 : 0); }
+  if (threadIdx.x == 0) fetch(0);
   {
     const int r0 = mem_off[0], nr = mem_off[1] - r0;
     for (int i = threadIdx.x; i < nr; i += blockDim.x) rows_sm[i] = mem_rows[r0 + i];
   }
-  // fallback view for the exact routine (rows further than +-1 come from the raw tables)
-  Tables<float, C> tb;
-  tb.nq = nq; tb.top = TOP; tb.ld = LD; tb.gx = hist_q; tb.gy = af; tb.x_shared = false; tb.G = G;
-  tb.pt_stride = (long long)G * nq;
 
   for (int g = 0; g < G; ++g) {
     const int m0 = mem_off[g], n_rows = mem_off[g + 1] - m0;
@@ -827,19 +882,11 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
       const int idx = threadIdx.x + i * kThreads;
       nxt[i] = idx < n_next ? mem_rows[r_next + idx] : 0;
     }
-    // slots of rows g-1, g (already waited for in earlier steps except at g == 0) and g+1
-    if (g == 0) { mbar_wait(&bars[0], 0); mbar_wait(&bars[1], 0); }
-    {
-      const int e = g + 1, s = (e + 1) % RING;
-      mbar_wait(&bars[s], (uint32_t)(((e + 1) / RING) & 1));
-    }
-    __syncthreads();  // everyone is done with step g-1: slot of row g-2 is free, rows_sm[g&1] is complete
-    if (threadIdx.x == 0 && g + 2 <= G) fetch(g + 2);
+    __syncthreads();  // everyone is done with step g-1: its slot is free, rows_sm[g&1] is complete
+    if (threadIdx.x == 0 && g + 1 < G) fetch(g + 1);  // streams in while this group is processed
+    mbar_wait(&bars[g % RING], (uint32_t)((g / RING) & 1));
 
-    const Slot& sc = ring[(g + 1) % RING];
-    // view of the three rows for the exact routine: slot index 0,1,2 <-> rows g-1, g, g+1.  The ring is not
-    // contiguous in row order, so the exact routine gets per-slot pointers through a small table.
-    const Slot* s3[3] = {&ring[g % RING], &ring[(g + 1) % RING], &ring[(g + 2) % RING]};
+    const Slot& sc = ring[g % RING];
     const float* xs = sc.xs + lane;
     const float* ys = sc.ys + lane;
     const int n = sc.nv[lane];
@@ -889,9 +936,15 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
         const bool sure = ((fabsf(dl - dh) > 1e-5f * dmin) && (dmin < 0.99f)) || (x[j] != x[j]);
         f = below ? clo : f;
         f = above ? chi : f;
-        if (!(sure || below || above)) f = lookup_exact_slots<LD>(s3, tb, lane, pt, g, x[j], extrap);
-        if (m + j < n_rows && pt_ok)
-          dst[(long long)rows[m + j] * st] = kind == XSDBA_KIND_ADD ? __fadd_rn(x[j], f) : __fmul_rn(x[j], f);
+        if (m + j < n_rows && pt_ok) {
+          const long long off = (long long)rows[m + j] * st;
+          dst[off] = kind == XSDBA_KIND_ADD ? __fadd_rn(x[j], f) : __fmul_rn(x[j], f);
+          if (!(sure || below || above)) {
+            // float32 cannot decide (near-tie / far node / empty row): defer to the exact second pass
+            const unsigned slot = atomicAdd(fix_count, 1u);
+            if (slot < fix_cap) fix[slot] = FixEntry{(long long)(dst - scen) + off, pt, x[j], g};
+          }
+        }
       }
     }
     {
@@ -1863,7 +1916,7 @@ template <int TOP>
 bool launch_adjust_tile_t(const float* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
                           const float* af, const float* hq, int nq, int extrap, int kind, float* scen, cudaStream_t s) {
   typedef PackedSlot<2 * TOP> Slot;
-  const size_t smem_t = 4 * sizeof(Slot) + 2 * kTileMaxRows * sizeof(int) + 4 * sizeof(uint64_t) + 128;
+  const size_t smem_t = 2 * sizeof(Slot) + 2 * kTileMaxRows * sizeof(int) + 4 * sizeof(uint64_t) + 128;
   const size_t smem_p = sizeof(Slot) + stage_bytes<float, 32>(nq);
   if (smem_t > 220 * 1024 || smem_p > 220 * 1024) return false;
   const int64_t tiles = (n_pts + 31) / 32;
@@ -1889,13 +1942,36 @@ bool launch_adjust_tile_t(const float* sim, int64_t n_pts, int64_t sp, int64_t s
     cudaFreeAsync(packed, s);
     return false;
   }
+  // deferred-sample list: capacity 1/64 of the samples (ties are ~1e-4); on overflow the generic exact kernel
+  // redoes the whole block (it exits immediately otherwise), so the result never depends on the capacity
+  static const unsigned cap_div = getenv("XSDBA_B200_FIX_CAP_DIV") ? (unsigned)atoi(getenv("XSDBA_B200_FIX_CAP_DIV")) : 64u;
+  const unsigned fix_cap = (unsigned)std::min<int64_t>(std::max<int64_t>(n_pts * grp->n_time / cap_div, 1024), 1 << 28);
+  FixEntry* fix = nullptr;
+  unsigned* fix_count = nullptr;
+  if (cudaMallocAsync(&fix, (size_t)fix_cap * sizeof(FixEntry), s) != cudaSuccess ||
+      cudaMallocAsync(&fix_count, sizeof(unsigned), s) != cudaSuccess) {
+    cudaGetLastError();
+    if (fix) cudaFreeAsync(fix, s);
+    cudaFreeAsync(packed, s);
+    return false;
+  }
+  cudaMemsetAsync(fix_count, 0, sizeof(unsigned), s);
   pack_tables_kernel<TOP><<<dim3((unsigned)tiles, (unsigned)grp->n_groups), kThreads, smem_p, s>>>(af, hq, n_pts,
                                                                                                    grp->n_groups, nq, packed);
   adjust_tile_kernel<TOP><<<(unsigned)tiles, kThreads, smem_t, s>>>(sim, n_pts, sp, st, grp->members.off,
                                                                     grp->members.rows, grp->n_groups, af, hq, nq, packed,
-                                                                    extrap, kind, scen);
-  g_launches += 2;
-  cudaFreeAsync(packed, s);
+                                                                    extrap, kind, scen, fix, fix_count, fix_cap);
+  adjust_fix_kernel<<<148 * 4, 256, 0, s>>>(fix, fix_count, fix_cap, af, hq, grp->n_groups, nq, extrap, kind, scen);
+  {
+    const size_t smem_g = ((tables_bytes<float, 32>(nq) + 15) & ~(size_t)15) + stage_bytes<float, 32>(nq);
+    auto kern = adjust_kernel<float>;
+    if (set_smem(kern, smem_g) == XSDBA_OK)
+      kern<<<dim3((unsigned)tiles, (unsigned)grp->n_groups), kThreads, smem_g, s>>>(
+          sim, n_pts, sp, st, grp->members.off, grp->members.rows, grp->n_groups, af, hq, nq, XSDBA_INTERP_NEAREST, extrap,
+          kind, scen, fix_count, fix_cap);
+  }
+  g_launches += 4;
+  cudaFreeAsync(packed, s); cudaFreeAsync(fix, s); cudaFreeAsync(fix_count, s);
   return true;
 }
 
@@ -1958,7 +2034,7 @@ int launch_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsd
   int rc = set_smem(kern, smem);
   if (rc) return rc;
   kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows,
-                                                       grp->n_groups, af, hq, nq, interp, extrap, kind, scen);
+                                                       grp->n_groups, af, hq, nq, interp, extrap, kind, scen, nullptr, 0u);
   ++g_launches;
   return cuda_status(cudaGetLastError());
 }
