@@ -826,11 +826,18 @@ __global__ void adjust_fix_kernel(const FixEntry* __restrict__ fix, const unsign
   }
 }
 
+// shared-memory load by 32-bit shared address (keeps the search pointer a plain 32-bit register: LDS [R + imm])
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 constexpr int kTileMaxRows = 1024;  // member rows of one group kept in shared memory by K2t (x2 buffers)
 
 template <int TOP>
-__global__ void __launch_bounds__(kThreads, 4)
-adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp, long long st,
+__global__ void __launch_bounds__(kThreads, 3)
+adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp, int st,
                    const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows, int n_groups,
                    const float* __restrict__ af, const float* __restrict__ hist_q, int nq,
                    const PackedSlot<2 * TOP>* __restrict__ packed, int extrap, int kind, float* __restrict__ scen,
@@ -866,8 +873,10 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
   };
   if (threadIdx.x == 0) fetch(0);
   {
+    // every row list is padded with U copies of its last row, so that a batch never needs an index clamp
     const int r0 = mem_off[0], nr = mem_off[1] - r0;
-    for (int i = threadIdx.x; i < nr; i += blockDim.x) rows_sm[i] = mem_rows[r0 + i];
+    if (nr > 0)
+      for (int i = threadIdx.x; i < nr + U; i += blockDim.x) rows_sm[i] = mem_rows[r0 + min(i, nr - 1)];
   }
 
   for (int g = 0; g < G; ++g) {
@@ -880,7 +889,7 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
 #pragma unroll
     for (int i = 0; i < (kTileMaxRows + kThreads - 1) / kThreads; ++i) {
       const int idx = threadIdx.x + i * kThreads;
-      nxt[i] = idx < n_next ? mem_rows[r_next + idx] : 0;
+      nxt[i] = idx < n_next + U && n_next > 0 ? mem_rows[r_next + min(idx, n_next - 1)] : 0;
     }
     __syncthreads();  // everyone is done with step g-1: its slot is free, rows_sm[g&1] is complete
     if (threadIdx.x == 0 && g + 1 < G) fetch(g + 1);  // streams in while this group is processed
@@ -893,40 +902,41 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
     const float blo = sc.blo[lane], bhi = sc.bhi[lane];
     const float clo = extrap == 0 ? sc.clo[lane] : fnan, chi = extrap == 0 ? sc.chi[lane] : fnan;
 
-    float xn[U];
-    int m = warp * U;
-    if (m < n_rows) {
+    // two register sets (A, B) alternate between "being loaded" and "being processed": the next batch of U rows is
+    // always in flight while the current one is searched, and no register-to-register copies are needed
+    const uint32_t xb = (uint32_t)__cvta_generic_to_shared(xs);
+    const char* __restrict__ srcb = reinterpret_cast<const char*>(src);  // byte addressing: one IMAD.WIDE per sample
+    char* __restrict__ dstb = reinterpret_cast<char*>(dst);
+    const int st4 = st * 4;
+    auto load_batch = [&](int mb, float (&xv)[U], int (&ov)[U]) {
 #pragma unroll
-      for (int j = 0; j < U; ++j) xn[j] = src[(long long)rows[min(m + j, n_rows - 1)] * st];
-    }
-    for (; m < n_rows; m += n_warps * U) {
-      float x[U];
-      int po[U];  // byte offset of xs[pos] from xs: the search advances it by step rows (128 B each)
+      const int4 r0 = *reinterpret_cast<const int4*>(rows + mb), r1 = *reinterpret_cast<const int4*>(rows + mb + 4);
+      ov[0] = r0.x; ov[1] = r0.y; ov[2] = r0.z; ov[3] = r0.w;
+      ov[4] = r1.x; ov[5] = r1.y; ov[6] = r1.z; ov[7] = r1.w;
 #pragma unroll
-      for (int j = 0; j < U; ++j) { x[j] = xn[j]; po[j] = 0; }
-      const int mn = m + n_warps * U;
-      if (mn < n_rows) {
+      for (int j = 0; j < U; ++j) xv[j] = *reinterpret_cast<const float*>(srcb + (long long)ov[j] * st4);
+    };
+    auto process_batch = [&](int mb, const float (&x)[U], const int (&ov)[U]) {
+      uint32_t po[U];  // shared-memory address of xs[pos]: the search advances it by step rows (128 B each)
 #pragma unroll
-        for (int j = 0; j < U; ++j) xn[j] = src[(long long)rows[min(mn + j, n_rows - 1)] * st];
-      }
-      const char* xb = reinterpret_cast<const char*>(xs);
+      for (int j = 0; j < U; ++j) po[j] = xb;
 #pragma unroll
       for (int step = TOP; step > 0; step >>= 1) {
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-          const float v = *reinterpret_cast<const float*>(xb + po[j] + (step - 1) * (C * 4));
+          const float v = lds_f32(po[j] + (step - 1) * (C * 4));
           po[j] = v < x[j] ? po[j] + step * (C * 4) : po[j];
         }
       }
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        // po = offset of xs[i], i = #nodes < x (<= n); xs[n] = +inf.  ys sits LD rows after xs.
-        const bool first = po[j] == 0;
-        const int pl = first ? 0 : po[j] - C * 4;
-        const float xl = *reinterpret_cast<const float*>(xb + pl), xh = *reinterpret_cast<const float*>(xb + po[j]);
-        const float yl = *reinterpret_cast<const float*>(xb + pl + LD * C * 4);
+        // po = address of xs[i], i = #nodes < x (<= n); xs[n] = +inf.  ys sits LD rows after xs.
+        const bool first = po[j] == xb;
+        const uint32_t pl = first ? xb : po[j] - C * 4;
+        const float xl = lds_f32(pl), xh = lds_f32(po[j]);
+        const float yl = lds_f32(pl + LD * C * 4);
         const bool last = xh == finf;  // i == n (or a genuine +inf node: same treatment, dh = inf)
-        const float yh = *reinterpret_cast<const float*>(xb + (last ? pl : po[j]) + LD * C * 4);
+        const float yh = lds_f32((last ? pl : po[j]) + LD * C * 4);
         const float dl = first ? finf : x[j] - xl;
         const float dh = xh - x[j];
         const float dmin = fminf(dl, dh);
@@ -936,15 +946,31 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
         const bool sure = ((fabsf(dl - dh) > 1e-5f * dmin) && (dmin < 0.99f)) || (x[j] != x[j]);
         f = below ? clo : f;
         f = above ? chi : f;
-        if (m + j < n_rows && pt_ok) {
-          const long long off = (long long)rows[m + j] * st;
-          dst[off] = kind == XSDBA_KIND_ADD ? __fadd_rn(x[j], f) : __fmul_rn(x[j], f);
+        if (mb + j < n_rows && pt_ok) {
+          *reinterpret_cast<float*>(dstb + (long long)ov[j] * st4) =
+              kind == XSDBA_KIND_ADD ? __fadd_rn(x[j], f) : __fmul_rn(x[j], f);
           if (!(sure || below || above)) {
             // float32 cannot decide (near-tie / far node / empty row): defer to the exact second pass
             const unsigned slot = atomicAdd(fix_count, 1u);
-            if (slot < fix_cap) fix[slot] = FixEntry{(long long)(dst - scen) + off, pt, x[j], g};
+            if (slot < fix_cap) fix[slot] = FixEntry{(long long)(dst - scen) + (long long)ov[j] * st, pt, x[j], g};
           }
         }
+      }
+    };
+    {
+      float xa[U], xbv[U];
+      int oa[U], ob[U];
+      const int stride = n_warps * U;
+      int m = warp * U;
+      if (m < n_rows) load_batch(m, xa, oa);
+      while (m < n_rows) {
+        if (m + stride < n_rows) load_batch(m + stride, xbv, ob);
+        process_batch(m, xa, oa);
+        m += stride;
+        if (m >= n_rows) break;
+        if (m + stride < n_rows) load_batch(m + stride, xa, oa);
+        process_batch(m, xbv, ob);
+        m += stride;
       }
     }
     {
@@ -952,7 +978,7 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
 #pragma unroll
       for (int i = 0; i < (kTileMaxRows + kThreads - 1) / kThreads; ++i) {
         const int idx = threadIdx.x + i * kThreads;
-        if (idx < n_next) rn[idx] = nxt[i];
+        if (idx < n_next + U) rn[idx] = nxt[i];
       }
     }
   }
@@ -1918,7 +1944,7 @@ bool launch_adjust_tile_t(const float* sim, int64_t n_pts, int64_t sp, int64_t s
   typedef PackedSlot<2 * TOP> Slot;
   const size_t smem_t = 2 * sizeof(Slot) + 2 * kTileMaxRows * sizeof(int) + 4 * sizeof(uint64_t) + 128;
   const size_t smem_p = sizeof(Slot) + stage_bytes<float, 32>(nq);
-  if (smem_t > 220 * 1024 || smem_p > 220 * 1024) return false;
+  if (smem_t > 220 * 1024 || smem_p > 220 * 1024 || st < 0 || st > INT32_MAX / 4) return false;
   const int64_t tiles = (n_pts + 31) / 32;
   Slot* packed = nullptr;
   {
@@ -1958,7 +1984,7 @@ bool launch_adjust_tile_t(const float* sim, int64_t n_pts, int64_t sp, int64_t s
   cudaMemsetAsync(fix_count, 0, sizeof(unsigned), s);
   pack_tables_kernel<TOP><<<dim3((unsigned)tiles, (unsigned)grp->n_groups), kThreads, smem_p, s>>>(af, hq, n_pts,
                                                                                                    grp->n_groups, nq, packed);
-  adjust_tile_kernel<TOP><<<(unsigned)tiles, kThreads, smem_t, s>>>(sim, n_pts, sp, st, grp->members.off,
+  adjust_tile_kernel<TOP><<<(unsigned)tiles, kThreads, smem_t, s>>>(sim, n_pts, sp, (int)st, grp->members.off,
                                                                     grp->members.rows, grp->n_groups, af, hq, nq, packed,
                                                                     extrap, kind, scen, fix, fix_count, fix_cap);
   adjust_fix_kernel<<<148 * 4, 256, 0, s>>>(fix, fix_count, fix_cap, af, hq, grp->n_groups, nq, extrap, kind, scen);
@@ -1994,7 +2020,7 @@ bool launch_adjust_fast(const float* sim, int64_t n_pts, int64_t sp, int64_t st,
   if (grp->members.max_len > kAdjMaxRows) return false;
   int top = 1;
   while (top * 2 <= nq) top *= 2;
-  if (grp->members.max_len <= kTileMaxRows && !getenv("XSDBA_B200_NO_TILE") &&
+  if (grp->members.max_len <= kTileMaxRows - 8 && !getenv("XSDBA_B200_NO_TILE") &&
       launch_adjust_tile(sim, n_pts, sp, st, grp, af, hq, nq, top, extrap, kind, scen, s))
     return true;
   smem += (size_t)grp->members.max_len * sizeof(int);
