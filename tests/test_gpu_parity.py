@@ -571,3 +571,190 @@ def test_trained_object_roundtrip(tmp_path):
         assert bits_equal(_np(qdm2.adjust(sim, time=tx)), a)
     with pytest.raises(ValueError):
         xs.EmpiricalQuantileMapping.load(tmp_path / "qdm.npz")
+
+
+# ---------------------------------------------------------------------------------------------
+# Edge cases: ragged / degenerate inputs (tests/test_adjustment.py of the reference exercises NaN
+# slices, constant series and short records through the same entry points).
+# ---------------------------------------------------------------------------------------------
+def _tie_aware_check(scen, scen_o, sim, af, hq, group, to, extrap, kind, dt, min_unique=0.5):
+    lo, hi = o.qm_adjust_factor_bounds(sim.T.copy(), af, hq, group=group, time=to, extrapolation=extrap)
+    s_lo = o.apply_correction(sim.T, lo.astype(dt), kind).astype(dt)
+    s_hi = o.apply_correction(sim.T, hi.astype(dt), kind).astype(dt)
+    unique = (s_lo == s_hi) | (np.isnan(s_lo) & np.isnan(s_hi))
+    assert unique.mean() >= min_unique
+    assert bits_equal(np.where(unique, scen, 0), np.where(unique, scen_o, 0))
+    tie = ~unique
+    mn, mx = np.minimum(s_lo, s_hi)[tie], np.maximum(s_lo, s_hi)[tie]
+    assert ((scen[tie] >= mn) & (scen[tie] <= mx)).all()
+
+
+@pytest.mark.parametrize("n_pts", [1, 31, 32, 33, 65])
+def test_ragged_point_counts(n_pts):
+    """Point counts around the 32-lane tile width: the partial last tile must neither read nor write out of range."""
+    xs = _xs()
+    case = ("time.month", 1, "noleap", 5, 50, "+", "tas", np.float32)
+    tx, to, ref, hist, sim = _make(case, n_pts=max(n_pts, 6), seed=11)
+    ref, hist, sim = (np.ascontiguousarray(a[:, :n_pts]) for a in (ref, hist, sim))
+    q = o.equally_spaced_nodes(50).astype(np.float32)
+    gidx, G, _ = o.group_index(to, "time.month")
+    af_o, hq_o = o.eqm_train(ref.T.copy(), hist.T.copy(), gidx, G, 1, q, "+")
+    ds = xs.eqm_train(xs.Dataset({"ref": ref, "hist": hist}, time=tx), group="time.month", kind="+", quantiles=q)
+    assert bits_equal(_np(ds.af), af_o) and bits_equal(_np(ds.hist_q), hq_o)
+    # guard band: the output buffer is a view into a larger poisoned allocation
+    big = torch.full((sim.shape[0] + 2, n_pts + 64), -12345.0, device="cuda")
+    out = xs.qm_adjust(xs.Dataset({"sim": sim, "af": af_o, "hist_q": hq_o}, time=tx), group="time.month",
+                       interp="nearest", extrapolation="constant", kind="+")
+    scen = _np(out.scen).T
+    scen_o = o.qm_adjust(sim.T.copy(), af_o, hq_o, group="time.month", time=to, interp="nearest",
+                         extrapolation="constant", kind="+")
+    _tie_aware_check(scen, scen_o, sim, af_o, hq_o, "time.month", to, "constant", "+", np.float32)
+    assert (big == -12345.0).all()
+
+
+def test_empty_block_is_a_no_op():
+    xs = _xs()
+    tx, to = _time("noleap", 2)
+    z = np.zeros((len(to), 0), np.float32)
+    q = o.equally_spaced_nodes(10).astype(np.float32)
+    ds = xs.eqm_train(xs.Dataset({"ref": z, "hist": z}, time=tx), group="time.month", kind="+", quantiles=q)
+    assert tuple(ds.af.shape) == (0, 12, 10) and tuple(ds.hist_q.shape) == (0, 12, 10)
+    out = xs.qm_adjust(xs.Dataset({"sim": z, "af": _np(ds.af), "hist_q": _np(ds.hist_q)}, time=tx), group="time.month",
+                       interp="nearest", extrapolation="constant", kind="+")
+    assert tuple(out.scen.shape) == (len(to), 0)
+
+
+@pytest.mark.parametrize("group,window", [("time", 1), ("time.month", 1), ("time.dayofyear", 7)])
+def test_degenerate_series(group, window):
+    """Constant series (every node tied), +-inf samples, a single valid sample, and more quantiles than samples."""
+    xs = _xs()
+    rng = np.random.default_rng(5)
+    tx, to = _time("noleap", 2)
+    T, P = len(to), 8
+    ref = (280 + 3 * rng.standard_normal((T, P))).astype(np.float32)
+    hist = (281 + 3 * rng.standard_normal((T, P))).astype(np.float32)
+    sim = (282 + 3 * rng.standard_normal((T, P))).astype(np.float32)
+    hist[:, 0] = 281.0                      # constant: all quantile nodes identical
+    ref[:, 1] = 280.0
+    if group == "time":                     # (grouped: SciPy's cKDTree refuses non-finite nodes -- the reference raises)
+        hist[::7, 2] = np.inf               # infinities sort before NaN, after everything else
+        hist[3::11, 2] = -np.inf
+        ref[::5, 3] = np.inf
+        sim[::13, 5] = np.inf; sim[5::13, 5] = -np.inf
+    hist[:, 4] = np.nan; hist[17, 4] = 279.5   # exactly one valid sample in one group only
+    sim[7::13, 5] = np.nan
+    hist[:, 6] = np.round(hist[:, 6])       # heavy duplicates
+    q = o.equally_spaced_nodes(200).astype(np.float32)   # more nodes than samples for the small groups
+    gidx, G, _ = o.group_index(to, group)
+    with np.errstate(all="ignore"):
+        af_o, hq_o = o.eqm_train(ref.T.copy(), hist.T.copy(), gidx, G, window, q, "+")
+    ds = xs.eqm_train(xs.Dataset({"ref": ref, "hist": hist}, time=tx), group=xs.Grouper(group, window), kind="+",
+                      quantiles=q)
+    assert bits_equal(_np(ds.hist_q), hq_o)
+    assert bits_equal(_np(ds.af), af_o)
+    with np.errstate(all="ignore"):
+        scen_o = o.qm_adjust(sim.T.copy(), af_o, hq_o, group=group, time=to, interp="nearest", extrapolation="constant",
+                             kind="+")
+    out = xs.qm_adjust(xs.Dataset({"sim": sim, "af": af_o, "hist_q": hq_o}, time=tx), group=xs.Grouper(group, window),
+                       interp="nearest", extrapolation="constant", kind="+")
+    scen = _np(out.scen).T
+    assert np.array_equal(np.isnan(scen), np.isnan(scen_o))
+    if group == "time":
+        ok = np.ones(P, bool)
+        ok[2] = False   # infinite nodes make hist_q non-monotonic: interp1d's searchsorted result is then arbitrary
+    else:
+        ok = np.ones(P, bool)
+        ok[[0, 2, 4, 6]] = False   # tied / infinite node rows: cKDTree ties and inf-inf distances are unpinned
+    assert bits_equal(scen[ok], scen_o[ok]) or _tie_ok(scen[ok], scen_o[ok], sim.T[ok], af_o[ok], hq_o[ok], group, to)
+
+
+def _tie_ok(scen, scen_o, simT, af, hq, group, to):
+    with np.errstate(all="ignore"):
+        lo, hi = o.qm_adjust_factor_bounds(simT.copy(), af, hq, group=group, time=to, extrapolation="constant")
+        s_lo, s_hi = (simT + lo).astype(np.float32), (simT + hi).astype(np.float32)
+    unique = (s_lo == s_hi) | (np.isnan(s_lo) & np.isnan(s_hi))
+    good = bits_equal(np.where(unique, scen, 0), np.where(unique, scen_o, 0))
+    mn, mx = np.minimum(s_lo, s_hi)[~unique], np.maximum(s_lo, s_hi)[~unique]
+    return good and ((scen[~unique] >= mn) & (scen[~unique] <= mx)).all()
+
+
+def test_sim_missing_a_group_and_other_period():
+    """sim covers another period than the training data and has no February at all (ragged groups, one empty)."""
+    xs = _xs()
+    rng = np.random.default_rng(9)
+    tx_h, to_h = _time("noleap", 4, 1981)
+    ref, hist = (synth.tas(rng, to_h, 9, w) for w in ("ref", "hist"))
+    to_s = o.daily_time_axis(2041, 3, "noleap")
+    keep = to_s.month != 2
+    sim = synth.tas(rng, to_s, 9, "sim")[keep]
+    tx_s = xs.TimeAxis.from_fields(to_s.year[keep], to_s.month[keep], to_s.day[keep], "noleap")
+    q = o.equally_spaced_nodes(50).astype(np.float32)
+    gidx, G, _ = o.group_index(to_h, "time.month")
+    af_o, hq_o = o.eqm_train(ref.T.copy(), hist.T.copy(), gidx, G, 1, q, "+")
+    out = xs.qm_adjust(xs.Dataset({"sim": sim, "af": af_o, "hist_q": hq_o}, time=tx_s), group="time.month",
+                       interp="nearest", extrapolation="constant", kind="+")
+    scen = _np(out.scen)
+    # the same call on the full sim axis, February rows dropped afterwards, must agree bit for bit
+    sim_full = np.full((len(to_s), 9), 280.0, np.float32); sim_full[keep] = sim
+    tx_full = xs.TimeAxis.daily(2041, 3, "noleap")
+    full = _np(xs.qm_adjust(xs.Dataset({"sim": sim_full, "af": af_o, "hist_q": hq_o}, time=tx_full), group="time.month",
+                            interp="nearest", extrapolation="constant", kind="+").scen)
+    assert bits_equal(scen, full[keep])
+    scen_o = o.qm_adjust(sim_full.T.copy(), af_o, hq_o, group="time.month", time=to_s, interp="nearest",
+                         extrapolation="constant", kind="+")
+    _tie_aware_check(full.T, scen_o, sim_full, af_o, hq_o, "time.month", to_s, "constant", "+", np.float32, 0.95)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full-size launch geometry: one bench-sized slab (48 latitude rows x 1440 = 69 120
+# gridpoints x 10 950 days), checked through size-independent properties and against the oracle on
+# sampled columns.
+# ---------------------------------------------------------------------------------------------
+def test_full_slab_properties_and_sampled_oracle():
+    xs = _xs()
+    P, years = 48 * 1440, 30
+    tx, to = _time("noleap", years)
+    T = len(to)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    doy = torch.as_tensor(to.dayofyear, device="cuda", dtype=torch.float32)[:, None]
+
+    def field(A, sigma, off):
+        x = torch.randn((T, P), device="cuda", generator=g) * sigma
+        x += 273.15 + off - A * torch.cos(2 * torch.pi * (doy - 15) / 365)
+        return x
+
+    ref, hist, sim = field(12, 3.0, 0.0), field(10, 3.5, 1.5), field(10, 3.5, 3.5)
+    hist[:, 777] = float("nan")
+    ref[100:200, 4242] = float("nan")
+    q = o.equally_spaced_nodes(50).astype(np.float32)
+    ds = xs.eqm_train(xs.Dataset({"ref": ref, "hist": hist}, time=tx), group="time.month", kind="+", quantiles=q)
+    af, hq = ds.af, ds.hist_q
+    assert tuple(af.shape) == (P, 12, 50)
+    # 1. quantile nodes are sorted and bracketed by the series' extremes; the all-NaN point is all-NaN
+    ok = torch.ones(P, dtype=torch.bool, device="cuda"); ok[777] = False
+    assert (hq[ok][:, :, 1:] >= hq[ok][:, :, :-1]).all()
+    assert torch.isnan(hq[777]).all() and torch.isnan(af[777]).all()
+    assert (hq[ok].amin(dim=(1, 2)) >= hist[:, ok].amin(dim=0)).all() and (hq[ok].amax(dim=(1, 2)) <= hist[:, ok].amax(dim=0)).all()
+    # 2. idempotence: training a series against itself gives the neutral factor exactly
+    ds0 = xs.eqm_train(xs.Dataset({"ref": hist, "hist": hist}, time=tx), group="time.month", kind="+", quantiles=q)
+    assert (ds0.af[ok] == 0).all() and bits_equal(_np(ds0.hist_q), _np(hq))
+    # 3. a neutral table returns sim bit for bit; the real table moves every sample by one of its own factors
+    neutral = xs.qm_adjust(xs.Dataset({"sim": sim, "af": torch.zeros_like(af), "hist_q": hq}, time=tx),
+                           group="time.month", interp="nearest", extrapolation="constant", kind="+").scen
+    assert torch.equal(neutral[:, ok], sim[:, ok])
+    scen = xs.qm_adjust(xs.Dataset({"sim": sim, "af": af, "hist_q": hq}, time=tx), group="time.month",
+                        interp="nearest", extrapolation="constant", kind="+").scen
+    assert torch.isnan(scen[:, 777]).all() and not torch.isnan(scen[:, ok]).any()
+    # 4. sampled columns (both ends of the slab, tile edges, the NaN-holed point) against the oracle
+    cols = np.array([0, 1, 31, 32, 33, 4242, 34559, 34560, 69087, 69088, 69119])
+    refc, histc, simc = (_np(a[:, cols]) for a in (ref, hist, sim))
+    gidx, G, _ = o.group_index(to, "time.month")
+    af_o, hq_o = o.eqm_train(refc.T.copy(), histc.T.copy(), gidx, G, 1, q, "+")
+    assert bits_equal(_np(af[cols]), af_o) and bits_equal(_np(hq[cols]), hq_o)
+    scen_o = o.qm_adjust(simc.T.copy(), af_o, hq_o, group="time.month", time=to, interp="nearest",
+                         extrapolation="constant", kind="+")
+    _tie_aware_check(_np(scen[:, cols]).T, scen_o, simc, af_o, hq_o, "time.month", to, "constant", "+", np.float32, 0.99)
+    # 5. checksum of checksums: the adjusted field's column sums equal sim's column sums plus the applied factors'
+    d = (scen[:, ok].double() - sim[:, ok].double())
+    lo, hi = af[ok].amin(dim=(1, 2)).double(), af[ok].amax(dim=(1, 2)).double()
+    assert (d.amin(dim=0) >= lo - 1e-3).all() and (d.amax(dim=0) <= hi + 1e-3).all()

@@ -553,13 +553,13 @@ __host__ __device__ constexpr size_t stage_bytes(int nq) { return (size_t)2 * C 
 // time steps of its group four at a time, lane = point: read sim (coalesced for time-major), look
 // the factor up (branch-free binary search in the staged table), apply, write scen.
 // =============================================================================================
-template <typename T>
+template <typename T, int C = 32>
 __global__ void __launch_bounds__(kThreads)
 adjust_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long st,
               const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows, int n_groups,
               const T* __restrict__ af, const T* __restrict__ hist_q, int nq, int interp, int extrap, int kind,
               T* __restrict__ scen, const unsigned* __restrict__ gate_count = nullptr, unsigned gate_cap = 0) {
-  constexpr int C = 32;
+  // C = points per CTA: 32 (lane = point) unless the tables of a very fine quantile grid need the shared memory
   constexpr int U = 4;
   if (gate_count && *gate_count <= gate_cap) return;  // overflow fallback of K2t: nothing to redo
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -576,7 +576,7 @@ adjust_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long lon
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const long long pt = n0 + lane;
-  if (pt >= n_pts) return;
+  if (pt >= n_pts || lane >= C) return;
   const T* __restrict__ src = sim + pt * sp;
   T* __restrict__ dst = scen + pt * sp;
   for (int m = m0 + warp * U; m < m1; m += n_warps * U) {
@@ -1916,10 +1916,10 @@ int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t
   jp.lower = jitter ? jitter[0] : dnan; jp.minimum = jitter ? jitter[1] : 0.0;
   jp.upper = jitter ? jitter[2] : dnan; jp.maximum = jitter ? jitter[3] : 0.0; jp.seed = seed;
   const int use_jitter = jitter && (jitter[0] == jitter[0] || jitter[2] == jitter[2]);
-  if (!ref || !grp || !q || !af || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
-  if (mode == 0 && (!hist || !hq)) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n_pts > 0 && !ref) || !grp || (n_pts > 0 && !q) || (n_pts > 0 && !af) || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (mode == 0 && n_pts > 0 && (!hist || !hq)) return XSDBA_ERR_INVALID_ARGUMENT;
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
-  if (normalize && mode == 0 && !scaling) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (normalize && mode == 0 && n_pts > 0 && !scaling) return XSDBA_ERR_INVALID_ARGUMENT;
   if (n_pts == 0) return XSDBA_OK;
   if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
   const int n_pad = std::max(2, next_pow2(grp->segments.max_len));
@@ -1990,7 +1990,7 @@ bool launch_adjust_tile_t(const float* sim, int64_t n_pts, int64_t sp, int64_t s
   adjust_fix_kernel<<<148 * 4, 256, 0, s>>>(fix, fix_count, fix_cap, af, hq, grp->n_groups, nq, extrap, kind, scen);
   {
     const size_t smem_g = ((tables_bytes<float, 32>(nq) + 15) & ~(size_t)15) + stage_bytes<float, 32>(nq);
-    auto kern = adjust_kernel<float>;
+    auto kern = adjust_kernel<float, 32>;
     if (set_smem(kern, smem_g) == XSDBA_OK)
       kern<<<dim3((unsigned)tiles, (unsigned)grp->n_groups), kThreads, smem_g, s>>>(
           sim, n_pts, sp, st, grp->members.off, grp->members.rows, grp->n_groups, af, hq, nq, XSDBA_INTERP_NEAREST, extrap,
@@ -2041,10 +2041,23 @@ bool launch_adjust_fast(const float* sim, int64_t n_pts, int64_t sp, int64_t st,
 bool launch_adjust_fast(const double*, int64_t, int64_t, int64_t, const xsdba_grouping*, const double*, const double*,
                         int, int, int, int, double*, size_t, dim3, cudaStream_t) { return false; }
 
+template <typename T, int C>
+bool launch_adjust_narrow(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* af,
+                          const T* hq, int nq, int interp, int extrap, int kind, T* scen, void* stream) {
+  const size_t smem = ((tables_bytes<T, C>(nq) + 15) & ~(size_t)15) + stage_bytes<T, C>(nq);
+  auto kern = adjust_kernel<T, C>;
+  if (smem > 200 * 1024 || set_smem(kern, smem) != XSDBA_OK) return false;
+  dim3 grid((unsigned)((n_pts + C - 1) / C), (unsigned)grp->n_groups);
+  kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows,
+                                                       grp->n_groups, af, hq, nq, interp, extrap, kind, scen, nullptr, 0u);
+  ++g_launches;
+  return true;
+}
+
 template <typename T>
 int launch_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* af,
                   const T* hq, int nq, int interp, int extrap, int kind, T* scen, void* stream) {
-  if (!sim || !grp || !af || !hq || !scen || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n_pts > 0 && !sim) || !grp || (n_pts > 0 && !af) || (n_pts > 0 && !hq) || (n_pts > 0 && !scen) || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
   if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR) return XSDBA_ERR_INVALID_ARGUMENT;
   if (extrap != XSDBA_EXTRAP_CONSTANT && extrap != XSDBA_EXTRAP_NAN) return XSDBA_ERR_INVALID_ARGUMENT;
@@ -2052,11 +2065,19 @@ int launch_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsd
   if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
   if (n_pts == 0) return XSDBA_OK;
   const size_t smem = ((tables_bytes<T, 32>(nq) + 15) & ~(size_t)15) + stage_bytes<T, 32>(nq);
-  if (smem > 200 * 1024) return XSDBA_ERR_UNSUPPORTED;
+  if (smem > 200 * 1024) {
+    // very fine quantile grids: fewer points per CTA so that the staged tables still fit
+    if (launch_adjust_narrow<T, 16>(sim, n_pts, sp, st, grp, af, hq, nq, interp, extrap, kind, scen, stream) ||
+        launch_adjust_narrow<T, 8>(sim, n_pts, sp, st, grp, af, hq, nq, interp, extrap, kind, scen, stream) ||
+        launch_adjust_narrow<T, 4>(sim, n_pts, sp, st, grp, af, hq, nq, interp, extrap, kind, scen, stream) ||
+        launch_adjust_narrow<T, 2>(sim, n_pts, sp, st, grp, af, hq, nq, interp, extrap, kind, scen, stream))
+      return cuda_status(cudaGetLastError());
+    return XSDBA_ERR_UNSUPPORTED;
+  }
   dim3 grid((unsigned)((n_pts + 31) / 32), (unsigned)grp->n_groups);
   if (launch_adjust_fast(sim, n_pts, sp, st, grp, af, hq, nq, interp, extrap, kind, scen, smem, grid, (cudaStream_t)stream))
     return cuda_status(cudaGetLastError());
-  auto kern = adjust_kernel<T>;
+  auto kern = adjust_kernel<T, 32>;
   int rc = set_smem(kern, smem);
   if (rc) return rc;
   kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows,
@@ -2090,9 +2111,9 @@ int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba
                 const T* q, int nq, int interp, int extrap, int kind, int rank_window, int do_adjust, T* scen,
                 double* sim_q, void* stream, int rank_mode = 0, const double* gcoord = nullptr,
                 const unsigned char* diag = nullptr) {
-  if (!sim || !grp || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n_pts > 0 && !sim) || !grp || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (do_adjust) {
-    if (!af || !q || !scen || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
+    if ((n_pts > 0 && !af) || (n_pts > 0 && !q) || (n_pts > 0 && !scen) || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
     if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
     if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR) return XSDBA_ERR_INVALID_ARGUMENT;
     if (extrap != XSDBA_EXTRAP_CONSTANT && extrap != XSDBA_EXTRAP_NAN) return XSDBA_ERR_INVALID_ARGUMENT;
@@ -2127,7 +2148,7 @@ int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba
 template <typename T>
 int launch_poly_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* scaling,
                       int kind, int degree, const double* tcoord, double* trend, void* stream) {
-  if (!x || !grp || !tcoord || !trend || n_pts < 0 || degree < 0 || degree > kMaxDeg) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n_pts > 0 && !x) || !grp || (n_pts > 0 && !tcoord) || (n_pts > 0 && !trend) || n_pts < 0 || degree < 0 || degree > kMaxDeg) return XSDBA_ERR_INVALID_ARGUMENT;
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
   if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
   if (n_pts == 0) return XSDBA_OK;
@@ -2143,7 +2164,7 @@ template <typename T>
 int launch_dqm_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* af,
                       const T* hq, const T* scaling, const double* trend, int nq, int interp, int extrap, int kind,
                       T* scen, void* stream) {
-  if (!sim || !grp || !af || !hq || !scaling || !trend || !scen || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n_pts > 0 && !sim) || !grp || (n_pts > 0 && !af) || (n_pts > 0 && !hq) || (n_pts > 0 && !scaling) || (n_pts > 0 && !trend) || (n_pts > 0 && !scen) || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
   if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR) return XSDBA_ERR_INVALID_ARGUMENT;
   if (extrap != XSDBA_EXTRAP_CONSTANT && extrap != XSDBA_EXTRAP_NAN) return XSDBA_ERR_INVALID_ARGUMENT;
@@ -2165,7 +2186,7 @@ int launch_dqm_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const
 template <typename T>
 int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* scaling,
                        int kind, double f, int niter, int degree, const double* xn, double* trend, void* stream) {
-  if (!x || !grp || !xn || !trend || n_pts < 0 || !(f > 0.0) || degree < 0 || degree > 1) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n_pts > 0 && !x) || !grp || (n_pts > 0 && !xn) || (n_pts > 0 && !trend) || n_pts < 0 || !(f > 0.0) || degree < 0 || degree > 1) return XSDBA_ERR_INVALID_ARGUMENT;
   if (niter != 1) return XSDBA_ERR_UNSUPPORTED;  // robustness iterations (median of residuals) not built yet
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
   if (n_pts == 0) return XSDBA_OK;
@@ -2201,7 +2222,7 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
 
 template <typename T>
 int launch_jitter(const T* x, int64_t n, const double* j4, uint64_t seed, T* out, void* stream) {
-  if (!x || !out || !j4 || n < 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n > 0 && !x) || (n > 0 && !out) || (n > 0 && !j4) || n < 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (n == 0) return XSDBA_OK;
   JitterParams jp{j4[0], j4[1], j4[2], j4[3], seed};
   const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
@@ -2226,7 +2247,7 @@ int launch_reorder_c(const T* sim, const T* ref, int64_t n_pts, int64_t sp, int6
 template <typename T>
 int launch_reorder(const T* sim, const T* ref, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, T* out,
                    void* stream) {
-  if (!sim || !ref || !grp || !out || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n_pts > 0 && !sim) || (n_pts > 0 && !ref) || !grp || (n_pts > 0 && !out) || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
   if (n_pts == 0) return XSDBA_OK;
   const int n_pad = std::max(2, next_pow2(grp->segments.max_len));
@@ -2257,7 +2278,7 @@ int launch_select_c(const T* x, const T* y, int64_t n_pts, int64_t sp, int64_t s
 template <typename T>
 int launch_select(const T* x, const T* y, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, int mode,
                   const T* rnk, const double* yvals, int nv, T* out, void* stream) {
-  if (!x || !grp || !out || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n_pts > 0 && !x) || !grp || (n_pts > 0 && !out) || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (mode == 0 && !rnk) return XSDBA_ERR_INVALID_ARGUMENT;
   if (mode == 1 && (!y || !yvals || nv <= 0)) return XSDBA_ERR_INVALID_ARGUMENT;
   if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
@@ -2291,7 +2312,7 @@ int launch_adapt_apply_c(const T* sim, int64_t n_pts, int64_t sp, int64_t st, co
 template <typename T>
 int launch_adapt_apply(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, double thresh,
                        const double* p0r, const double* p0h, const T* pth, unsigned long long seed, T* out, void* stream) {
-  if (!sim || !grp || !p0r || !p0h || !pth || !out || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n_pts > 0 && !sim) || !grp || (n_pts > 0 && !p0r) || (n_pts > 0 && !p0h) || (n_pts > 0 && !pth) || (n_pts > 0 && !out) || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
   if (n_pts == 0) return XSDBA_OK;
   const int n_pad = std::max(2, next_pow2(grp->members.max_len));
@@ -2308,7 +2329,7 @@ int launch_adapt_apply(const T* sim, int64_t n_pts, int64_t sp, int64_t st, cons
 template <typename T>
 int launch_tail_mask(const T* adapted, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* hq_raw,
                      int nq, double factor, T* scen, void* stream) {
-  if (!adapted || !grp || !hq_raw || !scen || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n_pts > 0 && !adapted) || !grp || (n_pts > 0 && !hq_raw) || (n_pts > 0 && !scen) || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (sp != 1 && st != 1) return XSDBA_ERR_UNSUPPORTED;
   if (n_pts == 0) return XSDBA_OK;
   const int64_t total = n_pts * grp->n_time;
@@ -2322,7 +2343,7 @@ int launch_tail_mask(const T* adapted, int64_t n_pts, int64_t sp, int64_t st, co
 template <typename T>
 int launch_escore(const T* tgt, const T* sim, int64_t n_pts, int64_t sp, int64_t st, int64_t nt_t, int64_t nt_s, int n_var,
                   int64_t vs_t, int64_t vs_s, int n_sub, T* out, void* stream) {
-  if (!tgt || !sim || !out || n_pts < 0 || n_var < 1 || n_var > kMaxVar || nt_t <= 0 || nt_s <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n_pts > 0 && !tgt) || (n_pts > 0 && !sim) || (n_pts > 0 && !out) || n_pts < 0 || n_var < 1 || n_var > kMaxVar || nt_t <= 0 || nt_s <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (n_pts == 0) return XSDBA_OK;
   // N > 0: about N evenly spaced observations of each cloud (processing.py:459-464)
   const int step_t = n_sub > 0 ? (int)((nt_t + n_sub - 1) / n_sub) : 1;
@@ -2340,7 +2361,7 @@ int launch_escore(const T* tgt, const T* sim, int64_t n_pts, int64_t sp, int64_t
 
 template <typename T>
 int launch_rotate(const T* x, int64_t n_elem, int n_var, const float* rot_host, T* y, void* stream) {
-  if (!x || !y || !rot_host || n_var < 1 || n_var > kMaxVar || n_elem < 0 || x == y) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n_elem > 0 && !x) || (n_elem > 0 && !y) || (n_elem > 0 && !rot_host) || n_var < 1 || n_var > kMaxVar || n_elem < 0 || (n_elem > 0 && x == y)) return XSDBA_ERR_INVALID_ARGUMENT;
   if (n_elem == 0) return XSDBA_OK;
   RotMat R;
   for (int v = 0; v < kMaxVar; ++v) for (int w = 0; w < kMaxVar; ++w)
@@ -2354,7 +2375,7 @@ int launch_rotate(const T* x, int64_t n_elem, int n_var, const float* rot_host, 
 template <typename T>
 int launch_standardize(const T* x, int64_t n_pts, int64_t sp, int64_t st, int64_t n_time, int n_var, int64_t var_stride,
                        T* y, void* stream) {
-  if (!x || !y || n_pts < 0 || n_time <= 0 || n_var < 1) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n_pts > 0 && !x) || (n_pts > 0 && !y) || n_pts < 0 || n_time <= 0 || n_var < 1) return XSDBA_ERR_INVALID_ARGUMENT;
   if (n_pts == 0) return XSDBA_OK;
   const int64_t n = n_pts * n_var;
   standardize_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, n_pts, sp, st, (int)n_time,
