@@ -299,13 +299,22 @@ struct FastSmem {
   static __host__ __device__ constexpr size_t total(int nq) { return refq + (size_t)3 * nq * 33 * 4; }
 };
 
+// base + row * stride_bytes as ONE IMAD.WIDE (the C expression compiles to a 64 x 64 multiply sequence)
+__device__ __forceinline__ const char* row_address(const char* base, int row, int stride_bytes) {
+  long long r;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(row), "r"(stride_bytes), "l"(reinterpret_cast<long long>(base)));
+  return reinterpret_cast<const char*>(r);
+}
+
 template <bool JITTER>
 __global__ void __launch_bounds__(kFastThreads, 1)
 train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist, long long n_pts, long long st,
                   const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
-                  const float* __restrict__ q, int nq, int kind, int normalize, int mode, float* __restrict__ af,
+                  const float* __restrict__ q, int nq, int kind, int normalize_arg, int mode, float* __restrict__ af,
                   float* __restrict__ hist_q, float* __restrict__ scaling, JitterParams jp, int use_jitter,
                   const double* __restrict__ q64, int stagger_ns) {
+  // JITTER = the general instantiation (jitter and / or dqm_train's normalisation); <false> is the lean EQM one
+  const int normalize = JITTER ? normalize_arg : 0;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* buf = reinterpret_cast<float*>(smem_raw + FastSmem::buf);
   int* rows_tab = reinterpret_cast<int*>(smem_raw + FastSmem::rows);
@@ -348,14 +357,18 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
   const int half = warp & 1;
   const int n_pass = mode == 0 ? 2 : 1;
   for (int pass = 0; pass < n_pass; ++pass) {
-    const float* __restrict__ src = (pass == 0 ? ref : hist) + n0 + lane;
+    // columns past n_pts read column n0 instead (always valid memory); their results are never written out
+    const char* __restrict__ srcb = reinterpret_cast<const char*>((pass == 0 ? ref : hist) + n0 + (col_ok ? lane : 0));
+    const int st4 = (int)st * 4;  // byte stride between time steps (launcher guarantees it fits)
     // ---- load: warp w takes slots w, w+32, ...; slot s -> half s&1, in-half row s>>1 ------------
     float v[32];
     int my_cnt = 0;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const int t = rows_tab[warp + 32 * i];
-      v[i] = (t >= 0 && col_ok) ? src[(long long)t * st] : fnan;
+      const char* pa = row_address(srcb, t, st4);
+      v[i] = fnan;
+      if (t >= 0) v[i] = *reinterpret_cast<const float*>(pa);
     }
     if (JITTER && use_jitter && pass == 1) {  // hist only, per window slot (_adjustment.py:58-67)
       const long long seg_base = seg_off[g];
@@ -364,9 +377,19 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
         v[i] = jitter_value<float>(v[i], jp, (unsigned long long)((seg_base + warp + 32 * i) * n_pts + n0 + lane));
     }
     double my_sum = 0.0;
+    if (normalize) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (v[i] == v[i]) { ++my_cnt; if (normalize) my_sum += (double)v[i]; }
+      for (int i = 0; i < 32; ++i) if (v[i] == v[i]) my_sum += (double)v[i];
+    }
+    // lean instantiation: valid count and the sort key (NaN -> +inf, NaNs sort last) from one predicate per element
+    if (!JITTER) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        asm("{\n\t.reg .pred p;\n\tsetp.num.f32 p, %1, %1;\n\t@p add.s32 %0, %0, 1;\n\t@!p mov.f32 %1, %2;\n\t}"
+            : "+r"(my_cnt), "+f"(v[i]) : "f"(finf));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) my_cnt += (v[i] == v[i]) ? 1 : 0;
     }
     pcnt[warp * 32 + lane] = my_cnt;
     if (normalize) psum[warp * 32 + lane] = my_sum;
@@ -394,7 +417,7 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
     {
       float* dst = buf + ((size_t)half * 512 + (warp >> 1)) * 32 + lane;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) dst[(size_t)i * 16 * 32] = (v[i] == v[i]) ? v[i] : finf;
+      for (int i = 0; i < 32; ++i) dst[(size_t)i * 16 * 32] = JITTER ? ((v[i] == v[i]) ? v[i] : finf) : v[i];
     }
     __syncthreads();
     sort_halves_512(buf, stagger_ns);
@@ -1878,11 +1901,13 @@ bool launch_train_fast(const float* ref, const float* hist, int64_t n_pts, int64
                        const xsdba_grouping* grp, const float* q, int nq, int kind, int normalize, int mode, float* af,
                        float* hq, float* scaling, cudaStream_t s, int* rc, const JitterParams& jp, int use_jitter,
                        const double* q64) {
-  if (sp != 1 || grp->segments.max_len > 1024 || nq > kFastMaxNq || getenv("XSDBA_B200_NO_FAST")) return false;
+  if (sp != 1 || st < 0 || st > INT32_MAX / 4 || grp->segments.max_len > 1024 || nq > kFastMaxNq ||
+      getenv("XSDBA_B200_NO_FAST"))
+    return false;
   const size_t smem = FastSmem::total(nq);
   dim3 grid((unsigned)((n_pts + 31) / 32), (unsigned)grp->n_groups);
   static const int stagger_ns = getenv("XSDBA_B200_STAGGER_NS") ? atoi(getenv("XSDBA_B200_STAGGER_NS")) : 0;
-  if (use_jitter) {
+  if (use_jitter || normalize) {
     *rc = set_smem(train_fast_kernel<true>, smem);
     if (*rc) return true;
     train_fast_kernel<true><<<grid, kFastThreads, smem, s>>>(ref, hist, n_pts, st, grp->segments.off, grp->segments.rows,
