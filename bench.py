@@ -263,10 +263,10 @@ def run_b200(args):
         "bound": "hbm", "kernel": "train_fast_kernel<false>" if dom == "train" else "pack_tables_kernel + adjust_tile_kernel",
         "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
-        # dram__bytes_read+write per launch from the ncu --set full capture in profiles/r01_ncu_summary.txt:
-        # 2.1666 GB for a 23 040-point launch whose algorithmic bytes are 2.1289 GB (x1.0177: no re-reads)
-        "traffic": (dom_bytes * args.steps / n_launch) * 1.0177 if dom == "train" else None,
-        "traffic_source": "ncu dram__bytes_{read,write}.sum of profiles/r01_ncu_summary.txt scaled to this launch size",
+        # dram__bytes_read+write per launch from the ncu --set full capture in profiles/r01_ncu_final.txt:
+        # 6.505 GB for a 69 120-point launch whose algorithmic bytes are 6.387 GB (x1.0185: no re-reads)
+        "traffic": (dom_bytes * args.steps / n_launch) * 1.0185 if dom == "train" else None,
+        "traffic_source": "ncu dram__bytes_{read,write}.sum of profiles/r01_ncu_final.txt scaled to this launch size",
         "launches": n_launch, "avg_launch_ms": dom_ms / n_launch,
         "algorithmic_bytes_per_launch": dom_bytes * args.steps / n_launch,
         "step": {"train_ms": tr_ms / args.steps, "adjust_ms": ad_ms / args.steps,
