@@ -135,6 +135,18 @@ int xsdba_qm_train_adapt_f64(const double* ref_dev, const double* hist_dev, int6
                              int32_t kind, const double* jitter4_host, double adapt_thresh, uint64_t seed,
                              double* af_dev, double* hist_q_dev, double* P0_ref_dev, double* P0_hist_dev,
                              double* pth_dev, void* cuda_stream);
+/* dqm_train with adapt_freq_thresh (_adjustment.py:95-192): hist is frequency-adapted first, then both series are
+ * normalised by their group means (the ADAPTED hist's mean); scaling_dev [n_pts][n_groups] as xsdba_qm_train_*. */
+int xsdba_dqm_train_adapt_f32(const float* ref_dev, const float* hist_dev, int64_t n_pts, int64_t stride_pt,
+                              int64_t stride_time, const xsdba_grouping_t* grp, const float* q_dev, int32_t nq,
+                              int32_t kind, const double* jitter4_host, double adapt_thresh, uint64_t seed,
+                              float* af_dev, float* hist_q_dev, float* scaling_dev, double* P0_ref_dev,
+                              double* P0_hist_dev, float* pth_dev, void* cuda_stream);
+int xsdba_dqm_train_adapt_f64(const double* ref_dev, const double* hist_dev, int64_t n_pts, int64_t stride_pt,
+                              int64_t stride_time, const xsdba_grouping_t* grp, const double* q_dev, int32_t nq,
+                              int32_t kind, const double* jitter4_host, double adapt_thresh, uint64_t seed,
+                              double* af_dev, double* hist_q_dev, double* scaling_dev, double* P0_ref_dev,
+                              double* P0_hist_dev, double* pth_dev, void* cuda_stream);
 int xsdba_adapt_freq_apply_f32(const float* sim_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
                                const xsdba_grouping_t* grp, double thresh, const double* P0_ref_dev,
                                const double* P0_hist_dev, const float* pth_dev, uint64_t seed, float* out_dev,

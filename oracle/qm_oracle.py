@@ -1027,6 +1027,35 @@ def eqm_train_adapt_freq(ref, hist, gidx, n_groups, window, q, kind, thresh, rng
     return af, hq, P0r, P0h, pth
 
 
+def dqm_train_adapt_freq(ref, hist, gidx, n_groups, window, q, kind, thresh, rng):
+    """dqm_train with ``adapt_freq_thresh`` (_adjustment.py:155-190): hist is frequency-adapted by
+    ``_preprocess_dataset`` first, then both series are normalised by their means.  Returns af, hist_q [N,G,nq],
+    scaling [N,G] and P0_ref, P0_hist, pth [N,G]."""
+    dt = ref.dtype
+    N = ref.shape[0]
+    q = np.asarray(q, dt)
+    af = np.full((N, n_groups, q.size), np.nan, dt); hq = af.copy()
+    sc = np.full((N, n_groups), np.nan, dt)
+    P0r = np.full((N, n_groups), np.nan); P0h = P0r.copy(); pth = np.full((N, n_groups), np.nan, dt)
+    for g in range(n_groups):
+        if not np.any(gidx == g):
+            continue
+        rseg = group_segment(ref, gidx, g, window)
+        hseg = group_segment(hist, gidx, g, window)
+        h_ad, pth[:, g], _, P0r[:, g], P0h[:, g] = adapt_freq_segment(hseg, thresh, rng, ref=rseg)
+        h_ad = h_ad.astype(dt)
+        mu_ref = _nanmean_rows(rseg)
+        mu_hist = _nanmean_rows(h_ad)
+        refn = apply_correction(rseg, invert(mu_ref, kind)[:, None].astype(dt), kind)
+        histn = apply_correction(h_ad, invert(mu_hist, kind)[:, None].astype(dt), kind)
+        ref_q = nan_quantile(refn.astype(dt), q)
+        hist_q = nan_quantile(histn.astype(dt), q)
+        af[:, g] = get_correction(hist_q, ref_q, kind)
+        hq[:, g] = hist_q
+        sc[:, g] = get_correction(mu_hist, mu_ref, kind)
+    return af, hq, sc, P0r, P0h, pth
+
+
 def escore(tgt, sim):
     """``_escore`` (nbutils.py:347-372): tgt [K, N], sim [K, M] (float64)."""
     sim = sim[:, ~np.isnan(sim).any(axis=0)]

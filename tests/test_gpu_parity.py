@@ -461,6 +461,51 @@ def test_adapt_freq_train_matches_oracle(group, window):
     np.testing.assert_array_equal(hq[big], hq_o[big])            # beyond pth nothing is random
 
 
+def test_dqm_train_with_adapt_freq_matches_oracle():
+    """dqm_train(adapt_freq_thresh=...): frequency adaptation first, normalisation by the ADAPTED hist's mean after.
+    P0 / pth are deterministic (bit-exact); scaling and the nodes depend on random fills (statistical)."""
+    xs = _xs()
+    to, ref, hist, sim = _dry_inputs()
+    tx = xs.TimeAxis.daily(1981, 8, "noleap")
+    q = o.equally_spaced_nodes(20).astype(np.float32)
+    gidx, G, _ = o.group_index(to, "time.month")
+    rng = np.random.default_rng(0)
+    af_o, hq_o, sc_o, p0r_o, p0h_o, pth_o = o.dqm_train_adapt_freq(ref.T.copy(), hist.T.copy(), gidx, G, 1, q, "*", 0.05, rng)
+    ds = xs.dqm_train(xs.Dataset({"ref": ref, "hist": hist}, time=tx), group="time.month", kind="*", quantiles=q,
+                      adapt_freq_thresh="0.05 mm/d")
+    assert bits_equal(_np(ds.P0_ref), p0r_o) and bits_equal(_np(ds.P0_hist), p0h_o) and bits_equal(_np(ds.pth), pth_o)
+    # the fills are U(thresh, pth) with pth << mean: they move the mean (hence scaling and every normalised node) by
+    # well under a percent, differently for every random stream
+    np.testing.assert_allclose(_np(ds.scaling), sc_o, rtol=2e-2)
+    hq = _np(ds.hist_q)
+    assert np.isclose(hq, hq_o, rtol=0.25, atol=0.02).mean() > 0.95
+    # without the option the result differs (the adaptation is really applied before the normalisation)
+    ds0 = xs.dqm_train(xs.Dataset({"ref": ref, "hist": hist}, time=tx), group="time.month", kind="*", quantiles=q)
+    assert not np.allclose(_np(ds0.scaling), _np(ds.scaling), rtol=1e-4)
+
+
+def test_dqm_adjust_with_adapt_freq_and_tail_factor():
+    """DetrendedQuantileMapping with adapt_freq_thresh + max_tail_factor (_adjustment.py:727-746, 776-777): the masked
+    samples are the frequency-adapted sim, everything else equals the pipeline fed with the adapted sim directly."""
+    xs = _xs()
+    to, ref, hist, sim = _dry_inputs()
+    tx = xs.TimeAxis.daily(1981, 8, "noleap")
+    obj = xs.DetrendedQuantileMapping.train(ref, hist, time=tx, nquantiles=20, group="time.month", kind="*",
+                                            adapt_freq_thresh="0.05 mm/d", max_tail_factor=1.5)
+    scen = _np(obj.adjust(sim, time=tx, detrend=1))
+    import torch as _t
+    ad = _np(xs._adjustment._adapt_freq_preprocess(
+        xs.Dataset(obj.ds), xs._adjustment._as_device(sim), sim.shape[1], 1, sim.shape[1], obj.group, tx, _t.float32,
+        "0.05 mm/d"))
+    gidx, G, _ = o.group_index(to, "time.month")
+    lastq = _np(obj.ds["hist_q_raw"])[:, gidx, -1].T
+    mask = ad > 1.5 * lastq
+    assert mask.sum() > 0 and bits_equal(scen[mask], ad[mask])
+    plain = xs.DetrendedQuantileMapping(obj.ds, obj.group, "*")          # no options: plain DQM on the adapted sim
+    ref_scen = _np(plain.adjust(ad, time=tx, detrend=1))
+    assert bits_equal(np.where(mask, 0, scen), np.where(mask, 0, ref_scen))
+
+
 def test_adapt_freq_adjust_and_tail_factor():
     xs = _xs()
     to, ref, hist, sim = _dry_inputs()

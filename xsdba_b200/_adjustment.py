@@ -105,8 +105,6 @@ def _reject_unsupported(**kw):
 
 def _train(ds, *, group, kind, quantiles, normalize, adapt_freq_thresh=None, jitter_under_thresh_value=None,
            jitter_over_thresh_value=None, jitter_over_thresh_upper_bnd=None, max_tail_factor=None, seed=0):
-    if adapt_freq_thresh is not None and normalize:
-        raise NotImplementedError("adapt_freq_thresh with DQM's normalisation is not built in xsdba_b200 yet")
     if (jitter_over_thresh_value is None) ^ (jitter_over_thresh_upper_bnd is None):
         raise ValueError("`jitter_over_thresh_value` and `jitter_over_thresh_upper_bnd` must both be specified or both "
                          "be `None` (default)")  # _adjustment.py:64-65
@@ -145,10 +143,11 @@ def _train(ds, *, group, kind, quantiles, normalize, adapt_freq_thresh=None, jit
         p0r = torch.empty((n_pts, G), dtype=torch.float64, device=ref.device)
         p0h = torch.empty_like(p0r)
         pth = torch.empty((n_pts, G), dtype=dt, device=ref.device)
-        fn = getattr(lib, f"xsdba_qm_train_adapt_{_sfx(dt)}")
+        fn = getattr(lib, f"xsdba_{'dqm' if normalize else 'qm'}_train_adapt_{_sfx(dt)}")
+        outs = (af.data_ptr(), hq.data_ptr()) + ((sc.data_ptr(),) if normalize else ())
         status = fn(ref.data_ptr(), hist.data_ptr(), n_pts, sp, st, h.ptr, q.data_ptr(), nq, _lib.KIND[kind],
                     None if j4 is None else j4.ctypes.data_as(_lib.c_f64p), C.c_double(_quantity(adapt_freq_thresh)),
-                    C.c_uint64(seed), af.data_ptr(), hq.data_ptr(), p0r.data_ptr(), p0h.data_ptr(), pth.data_ptr(), _stream())
+                    C.c_uint64(seed), *outs, p0r.data_ptr(), p0h.data_ptr(), pth.data_ptr(), _stream())
     elif jitter_under_thresh_value is not None or jitter_over_thresh_value is not None:
         j4 = jitter_params(dt, lower=jitter_under_thresh_value, upper=jitter_over_thresh_value,
                            maximum=jitter_over_thresh_upper_bnd)
@@ -415,10 +414,11 @@ def loess_trend(x, *, time, f=0.2, niter=1, d=0, kind="+", scaling=None, scaling
     return trend
 
 
-def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_thresh=None, max_tail_factor=None):
-    """``xsdba._adjustment.dqm_adjust`` (_adjustment.py:679-780): ds holds scaling, af, hist_q, sim.
+def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_thresh=None, max_tail_factor=None,
+               seed=0):
+    """``xsdba._adjustment.dqm_adjust`` (_adjustment.py:679-780): ds holds scaling, af, hist_q, sim (+ P0_ref,
+    P0_hist, pth for ``adapt_freq_thresh``; + hist_q_raw for ``max_tail_factor``).
     ``detrend`` is an int (PolyDetrend degree on the adjust group) or a PolyDetrend / LoessDetrend."""
-    _reject_unsupported(adapt_freq_thresh=adapt_freq_thresh, max_tail_factor=max_tail_factor)
     if interp == "cubic":
         raise NotImplementedError("cubic interpolation is not built in xsdba_b200 yet")
     group = parse_group(group)
@@ -433,6 +433,11 @@ def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_
     scaling = _as_device(ds["scaling"], dt).contiguous()
     if scaling.numel() != n_pts * h.n_groups:
         raise ValueError("scaling must be (*points, n_groups)")
+    if adapt_freq_thresh is not None:   # _adjustment.py:727-733: on the exact groups, before anything else
+        sim = _adapt_freq_preprocess(ds, sim, n_pts, sp, st, group, time, dt, adapt_freq_thresh, seed)
+    adapted = sim
+    if max_tail_factor is not None and group.prop not in ("group", "dayofyear") and interp != "nearest":
+        raise NotImplementedError("max_tail_factor with a month-interpolated last quantile is not built yet")
     if isinstance(detrend, (int, np.integer)):
         detrend = PolyDetrend(degree=int(detrend), kind=kind, group=group)   # _adjustment.py:759-762
     if isinstance(detrend, PolyDetrend):
@@ -454,6 +459,8 @@ def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_
                 trend.data_ptr(), nq, _lib.INTERP[interp], _lib.EXTRAP[extrapolation], _lib.KIND[kind],
                 scen.data_ptr(), _stream())
     _lib.check(status, "dqm_adjust")
+    if max_tail_factor is not None:     # _adjustment.py:734-746, 776-777
+        scen = _apply_tail_mask(ds, adapted, scen, n_pts, sp, st, group, time, dt, max_tail_factor)
     ta = 0 if st != 1 or sim.ndim == 1 else -1
     return Dataset({"scen": scen, "trend": trend}, time=time, time_axis=ta)
 

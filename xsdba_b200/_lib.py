@@ -55,6 +55,8 @@ for _t in ("f32", "f64"):
     SIGNATURES[f"xsdba_map_cdf_{_t}"] = (C.c_int, [vp, vp, i64, i64, i64, vp, vp, i32, vp, vp])
     SIGNATURES[f"xsdba_qm_train_adapt_{_t}"] = (
         C.c_int, [vp, vp, i64, i64, i64, vp, vp, i32, i32, c_f64p, C.c_double, C.c_uint64, vp, vp, vp, vp, vp, vp])
+    SIGNATURES[f"xsdba_dqm_train_adapt_{_t}"] = (
+        C.c_int, [vp, vp, i64, i64, i64, vp, vp, i32, i32, c_f64p, C.c_double, C.c_uint64, vp, vp, vp, vp, vp, vp, vp])
     SIGNATURES[f"xsdba_adapt_freq_apply_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, C.c_double, vp, vp, vp, C.c_uint64, vp, vp])
     SIGNATURES[f"xsdba_tail_mask_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, i32, C.c_double, vp, vp])
     SIGNATURES[f"xsdba_qdm_adjust_linear_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp])

@@ -103,10 +103,11 @@ class DetrendedQuantileMapping(_TrainAdjust):
     _train_fn = staticmethod(L4.dqm_train)
 
     def adjust(self, sim, *, time, interp="nearest", extrapolation="constant", detrend=1, time_axis=0):
-        ds = L4.Dataset({"sim": sim, "af": self.ds["af"], "hist_q": self.ds["hist_q"], "scaling": self.ds["scaling"]},
-                        time=time, time_axis=time_axis)
+        ds = L4.Dataset({"sim": sim, "af": self.ds["af"], "hist_q": self.ds["hist_q"], "scaling": self.ds["scaling"],
+                         **self._extra()}, time=time, time_axis=time_axis)
         return L4.dqm_adjust(ds, group=self.group, interp=interp, extrapolation=extrapolation, detrend=detrend,
-                             kind=self.kind)["scen"]
+                             kind=self.kind, adapt_freq_thresh=self.adapt_freq_thresh,
+                             max_tail_factor=self.max_tail_factor)["scen"]
 
 
 def train_adjust_host(ref: np.ndarray, hist: np.ndarray, sim: np.ndarray, *, time, sim_time, nquantiles=50,

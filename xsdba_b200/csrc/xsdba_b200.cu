@@ -214,9 +214,31 @@ train_kernel(const T* __restrict__ ref, const T* __restrict__ hist, long long n_
       if (threadIdx.x < C) af_p0r[threadIdx.x] = (double)af_le[threadIdx.x] / (double)af_nh[threadIdx.x];
       __syncthreads();
     }
-    count_columns<T, C>(sm, n_pad, cnt, sum, normalize != 0);
-    make_keys<T, C>(sm, n_pad, cnt, sum, normalize, kind);
+    // with frequency adaptation dqm_train normalises the ADAPTED hist (_adjustment.py:155-168: preprocessing comes
+    // first) and pth is a quantile of the RAW ref: both passes sort raw values here and normalise afterwards
+    const int norm_now = adapt ? 0 : normalize;
+    count_columns<T, C>(sm, n_pad, cnt, sum, norm_now != 0);
+    make_keys<T, C>(sm, n_pad, cnt, sum, norm_now, kind);
     sort_columns<T, C>(sm, n_pad);
+    // mean of the (sorted, NaN-free below cnt) column, then x (+|*) inv(mean): the late normalisation of the adapt path
+    auto normalise_sorted = [&]() {
+      if (threadIdx.x < C) sum[threadIdx.x] = 0.0;
+      __syncthreads();
+      const int c = threadIdx.x % C;
+      double my_sum = 0.0;
+      for (int idx = threadIdx.x; idx < n_pad * C; idx += blockDim.x)
+        if (idx / C < cnt[c]) my_sum += (double)sm[idx];
+      atomicAdd(&sum[c], my_sum);
+      __syncthreads();
+      const T mu = (T)(sum[c] / (double)cnt[c]);
+      const T inv = kind == XSDBA_KIND_ADD ? -mu : Num<T>::div((T)1, mu);
+      for (int idx = threadIdx.x; idx < n_pad * C; idx += blockDim.x) {
+        if (idx / C >= cnt[c]) continue;
+        T v = kind == XSDBA_KIND_ADD ? Num<T>::add(sm[idx], inv) : Num<T>::mul(sm[idx], inv);
+        sm[idx] = is_nan(v) ? Num<T>::inf() : v;
+      }
+      __syncthreads();
+    };
     if (adapt && pass == 0 && threadIdx.x < C) {
       // dP0 and pth = vecquantiles(ref, P0_hist).where(dP0 > 0)   (_processing.py:84-99)
       const int c = threadIdx.x;
@@ -229,6 +251,11 @@ train_kernel(const T* __restrict__ ref, const T* __restrict__ hist, long long n_
         const long long o = (n0 + c) * n_groups + g;
         ap.P0_ref[o] = p0r; ap.P0_hist[o] = p0h; reinterpret_cast<T*>(ap.pth)[o] = (T)pth;
       }
+    }
+    if (adapt && pass == 0 && normalize) {
+      __syncthreads();
+      normalise_sorted();
+      sort_columns<T, C>(sm, n_pad);
     }
     if (adapt && pass == 1) {
       // replace the excess "dry" values: sorted position i has tie-broken percentile rank i/(n-1)
@@ -247,6 +274,7 @@ train_kernel(const T* __restrict__ ref, const T* __restrict__ hist, long long n_
         }
       }
       __syncthreads();
+      if (normalize) normalise_sorted();
       sort_columns<T, C>(sm, n_pad);
     }
     // quantiles: item -> (point c, node k), k fastest so that global writes are contiguous
@@ -2668,6 +2696,24 @@ int xsdba_map_cdf_f64(const double* x, const double* y, int64_t n_pts, int64_t s
   return launch_select<double>(x, y, n_pts, sp, st, grp, 1, nullptr, yvals, nv, out, stream);
 }
 
+int xsdba_dqm_train_adapt_f32(const float* ref, const float* hist, int64_t n_pts, int64_t sp, int64_t st,
+                              const xsdba_grouping_t* grp, const float* q, int32_t nq, int32_t kind,
+                              const double* jitter4_host, double adapt_thresh, uint64_t seed, float* af, float* hq,
+                              float* scaling, double* P0_ref, double* P0_hist, float* pth, void* stream) {
+  if (!P0_ref || !P0_hist || !pth || !(adapt_thresh == adapt_thresh)) return XSDBA_ERR_INVALID_ARGUMENT;
+  AdaptParams ap{1, adapt_thresh, seed, P0_ref, P0_hist, pth};
+  return launch_train<float>(ref, hist, n_pts, sp, st, grp, q, nq, kind, 1, 0, af, hq, scaling, stream, jitter4_host, seed,
+                             nullptr, &ap);
+}
+int xsdba_dqm_train_adapt_f64(const double* ref, const double* hist, int64_t n_pts, int64_t sp, int64_t st,
+                              const xsdba_grouping_t* grp, const double* q, int32_t nq, int32_t kind,
+                              const double* jitter4_host, double adapt_thresh, uint64_t seed, double* af, double* hq,
+                              double* scaling, double* P0_ref, double* P0_hist, double* pth, void* stream) {
+  if (!P0_ref || !P0_hist || !pth || !(adapt_thresh == adapt_thresh)) return XSDBA_ERR_INVALID_ARGUMENT;
+  AdaptParams ap{1, adapt_thresh, seed, P0_ref, P0_hist, pth};
+  return launch_train<double>(ref, hist, n_pts, sp, st, grp, q, nq, kind, 1, 0, af, hq, scaling, stream, jitter4_host,
+                              seed, nullptr, &ap);
+}
 int xsdba_qm_train_adapt_f32(const float* ref, const float* hist, int64_t n_pts, int64_t sp, int64_t st,
                              const xsdba_grouping_t* grp, const float* q, int32_t nq, int32_t kind,
                              const double* jitter4_host, double adapt_thresh, uint64_t seed, float* af, float* hq,
