@@ -106,3 +106,52 @@ def test_equally_spaced_nodes_matches_reference(golden):
     import xsdba_b200 as xs
     assert (xs.equally_spaced_nodes(50) == golden["nodes_50"]).all()
     assert (xs.equally_spaced_nodes(5, eps=1e-4) == golden["nodes_5_eps"]).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# stack_periods / unstack_periods index logic (base.py:1072-1381, freq="YS") -- host only
+# ---------------------------------------------------------------------------------------------
+def test_stack_periods_non_overlapping_and_overlapping():
+    from xsdba_b200.calendar import TimeAxis
+    from xsdba_b200.periods import stack_periods, unstack_periods
+    t = TimeAxis.daily(1950, 150, "noleap")
+    p = stack_periods(t, window=30)
+    assert len(p) == 5 and p.start_years == (1950, 1980, 2010, 2040, 2070)
+    assert all(n == 30 * 365 for n in p.lengths) and p.slices[-1].stop == len(t)
+    x = np.arange(len(t), dtype=np.float64)[:, None] * np.ones((1, 3))
+    y, cov = unstack_periods([x[s] for s in p.slices], p, t)
+    assert cov == slice(0, len(t)) and np.array_equal(y, x)
+    p = stack_periods(t, window=30, stride=10)
+    assert p.start_years == tuple(range(1950, 2071, 10))          # the last complete window starts in 2070
+    y, cov = unstack_periods([x[s] for s in p.slices], p, t)
+    assert cov == slice(0, len(t)) and np.array_equal(y, x)        # every day exactly once, in order
+    # time-last layout
+    y2, _ = unstack_periods([x.T[:, s] for s in p.slices], p, t, time_axis=-1)
+    assert np.array_equal(y2, x.T)
+
+
+def test_stack_periods_docstring_table_and_edges():
+    """The example of unstack_periods' docstring (base.py:1293-1307): stride = window / 5, min_length = 4 strides,
+    7 strides of data -> 4 periods, the last one shorter; kept strides 0-2 | 3 | 4 | 5-6."""
+    from xsdba_b200.calendar import TimeAxis
+    from xsdba_b200.periods import stack_periods, unstack_periods
+    t = TimeAxis.daily(2000, 7, "noleap")
+    p = stack_periods(t, window=5, stride=1, min_length=4)
+    assert p.start_years == (2000, 2001, 2002, 2003)
+    assert p.lengths == (5 * 365, 5 * 365, 5 * 365, 4 * 365)
+    marks = [np.full((n, 1), i) for i, n in enumerate(p.lengths)]
+    y, cov = unstack_periods(marks, p, t)
+    assert cov == slice(0, 7 * 365)
+    assert np.array_equal(y[:, 0], np.repeat([0, 0, 0, 1, 2, 3, 3], 365))
+    # incomplete last window is dropped by default; a series ending before 31 December does not close its year
+    assert len(stack_periods(t, window=5, stride=1)) == 3
+    assert len(stack_periods(t[:-1], window=7)) == 0 and len(stack_periods(t, window=7)) == 1
+    # first window must start in January (base.py:1200-1208)
+    assert stack_periods(t[40:], window=3, stride=1).start_years[0] == 2001
+    with pytest.raises(ValueError):
+        stack_periods(TimeAxis.daily(2000, 7, "standard"), window=5)
+    with pytest.raises(ValueError):
+        stack_periods(t, window=2, stride=3)
+    with pytest.raises(NotImplementedError):
+        pp = stack_periods(t, window=4, stride=2)
+        unstack_periods([np.zeros((n, 1)) for n in pp.lengths], pp, t)

@@ -585,6 +585,14 @@ def test_escore_reference_kat_and_oracle():
     sub = _np(xs.escore(A, B, N=100))
     want = [o.escore(A[:, ::3, p].astype(np.float64), B[:, ::3, p].astype(np.float64)) for p in range(5)]
     np.testing.assert_allclose(sub, want, rtol=2e-6)
+    # scale=True: both clouds standardised with the thinned target's nanmean / population nanstd (processing.py:455-464)
+    def std_pair(a, b):
+        avg = np.nanmean(a, axis=1, keepdims=True); sd = np.nanstd(a, axis=1, keepdims=True)
+        return (a - avg) / sd, (b - avg) / sd
+    A64, B64 = A.astype(np.float64), B.astype(np.float64)
+    got = _np(xs.escore(A64, B64, N=100, scale=True))
+    want = [o.escore(*std_pair(A64[:, ::3, p], B64[:, ::3, p])) for p in range(5)]
+    np.testing.assert_allclose(got, want, rtol=1e-10)
 
 
 def test_mbcn_escores_decrease():
@@ -803,3 +811,28 @@ def test_full_slab_properties_and_sampled_oracle():
     d = (scen[:, ok].double() - sim[:, ok].double())
     lo, hi = af[ok].amin(dim=(1, 2)).double(), af[ok].amax(dim=(1, 2)).double()
     assert (d.amin(dim=0) >= lo - 1e-3).all() and (d.amax(dim=0) <= hi + 1e-3).all()
+
+
+def test_adjust_periods_moving_windows():
+    """stack_periods -> adjust -> unstack_periods (base.py:1072-1381): a 60-year sim adjusted in 30-year windows every
+    10 years equals the manual per-window calls stitched at the centre strides."""
+    xs = _xs()
+    rng = np.random.default_rng(21)
+    tx_h, to_h = _time("noleap", 30, 1981)
+    ref, hist = (synth.tas(rng, to_h, 7, w) for w in ("ref", "hist"))
+    tx_s = xs.TimeAxis.daily(2011, 60, "noleap")
+    to_s = o.daily_time_axis(2011, 60, "noleap")
+    sim = synth.tas(rng, to_s, 7, "sim")
+    obj = xs.EmpiricalQuantileMapping.train(ref, hist, time=tx_h, nquantiles=50, group="time.month", kind="+")
+    scen, cov = xs.adjust_periods(obj, sim, time=tx_s, window=30, stride=10)
+    assert cov == slice(0, len(tx_s)) and tuple(scen.shape) == sim.shape
+    scen = _np(scen)
+    # manual: windows start 2011, 2021, 2031, 2041; kept years [2011, 2031) | [2031, 2041) | [2041, 2051) | [2051, 2071)
+    per = xs.stack_periods(tx_s, window=30, stride=10)
+    assert per.start_years == (2011, 2021, 2031, 2041)
+    keep = [(2011, 2031), (2031, 2041), (2041, 2051), (2051, 2071)]
+    for slc, (ya, yb) in zip(per.slices, keep):
+        full = _np(obj.adjust(sim[slc], time=tx_s[slc]))
+        yr = tx_s.year[slc]
+        sel = (yr >= ya) & (yr < yb)
+        assert bits_equal(scen[slc][sel], full[sel])

@@ -13,3 +13,4 @@ from .detrending import LoessDetrend, PolyDetrend  # noqa: F401
 __version__ = "0.1.0"
 from .processing import escore, jitter, jitter_over_thresh, jitter_under_thresh  # noqa: F401
 from .mbcn import MBCn, mbcn_adjust, mbcn_train, rand_rot_matrix  # noqa: F401
+from .periods import Periods, adjust_periods, stack_periods, unstack_periods  # noqa: F401

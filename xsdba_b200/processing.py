@@ -64,15 +64,23 @@ def jitter_over_thresh(x, thresh, upper_bnd, seed: int = 0):
 
 def escore(tgt, sim, N: int = 0, scale: bool = False):
     """``xsdba.processing.escore`` (processing.py:393-489): energy score between the multivariate clouds ``tgt`` and
-    ``sim``, arrays (variable, time, *points) -> (*points,).  ``scale=True`` is not built."""
+    ``sim``, arrays (variable, time, *points) -> (*points,).  ``scale=True`` standardises both clouds with the
+    (sub-sampled) target's NaN-skipping mean and population standard deviation first (processing.py:462-464)."""
     from ._adjustment import _as_device, _stream
-    if scale:
-        raise NotImplementedError("escore(scale=True) is not built in xsdba_b200 yet")
     lib = _lib.load()
     t = _as_device(tgt)
     if t.dtype not in (torch.float32, torch.float64):
         t = t.to(torch.float32)
     s_ = _as_device(sim, t.dtype)
+    if scale:
+        if N > 0:  # the statistics are those of the thinned series (processing.py:455-460 come first)
+            t = t[:, :: -(-t.shape[1] // N)]
+            s_ = s_[:, :: -(-s_.shape[1] // N)]
+            N = 0
+        avg = torch.nanmean(t, dim=1, keepdim=True)
+        std = torch.sqrt(torch.nanmean((t - avg) ** 2, dim=1, keepdim=True))
+        t = (t - avg) / std
+        s_ = (s_ - avg) / std
     pshape = tuple(t.shape[2:])
     t = t.reshape(t.shape[0], t.shape[1], -1).contiguous()
     s_ = s_.reshape(s_.shape[0], s_.shape[1], -1).contiguous()
