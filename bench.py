@@ -260,7 +260,7 @@ def run_b200(args):
     dom_ms = max(tr_ms, ad_ms)
     achieved = dom_bytes * args.steps / (dom_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "train_fast_kernel<false>" if dom == "train" else "pack_tables_kernel + adjust_tile_kernel",
+        "bound": "hbm", "kernel": "train_fast_kernel<false, false>" if dom == "train" else "pack_tables_kernel + adjust_tile_kernel",
         "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
         # dram__bytes_read+write per launch from the ncu --set full capture in profiles/r01_ncu_final.txt:

@@ -69,10 +69,20 @@ __device__ __forceinline__ T jitter_value(T v, const JitterParams& jp, unsigned 
 // ---------------------------------------------------------------------------------------------
 // Column sort in shared memory.  sm is [n_pad][C] (column c of row r at sm[r*C + c]); n_pad is a
 // power of two; NaNs have been replaced by +inf by the caller.  Every column is sorted ascending.
-// v0: one compare-exchange per thread per step (bitonic network), __syncthreads between stages.
+//
+// sort_columns_v0: one compare-exchange per thread per step (bitonic network), a __syncthreads and a
+// shared-memory round trip per stage -- log2(n)(log2(n)+1)/2 of them.
+// sort_columns_rb: the same network, register blocked.  A thread takes the 32 rows of one column that
+// differ in 5 consecutive index bits, runs up to 5 stages on them in registers and writes them back, so
+// a phase of p stages costs ceil(p/5) round trips and the first five phases (a full sort of every
+// 32-row block) cost one: 11 round trips instead of 55 for 1024 rows.  (K1f's sorter in sort.cuh is the
+// hand-scheduled float32 / 1024-thread special case of this; this one serves every other kernel.)
+// With C < 32 columns several lanes of a warp work on different row sets of the same column; when the
+// exchange bits include bit 0 those sets are 32+ rows apart and hit the same banks (32/C-way conflict),
+// which is why the narrow tiles of very long segments (C < 8) stay on v0.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int C>
-__device__ void sort_columns(T* sm, int n_pad) {
+__device__ void sort_columns_v0(T* sm, int n_pad) {
   const int half_items = (n_pad >> 1) * C;
   for (int k = 2; k <= n_pad; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -92,6 +102,104 @@ __device__ void sort_columns(T* sm, int n_pad) {
       __syncthreads();
     }
   }
+}
+
+// stages of exchange bits R-1 .. 0 (local) on the 2^R registers, all in direction DESC
+template <typename T, int R, bool DESC>
+__device__ __forceinline__ void rb_stages(T (&r)[1 << R]) {
+#pragma unroll
+  for (int lb = R - 1; lb >= 0; --lb) {
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) {
+      if (j & (1 << lb)) continue;
+      const T lo = Num<T>::mn(r[j], r[j | (1 << lb)]);
+      const T hi = Num<T>::mx(r[j], r[j | (1 << lb)]);
+      r[j] = DESC ? hi : lo;
+      r[j | (1 << lb)] = DESC ? lo : hi;
+    }
+  }
+}
+
+// full bitonic sort of the 2^R registers; the last phase runs in direction `desc`
+template <typename T, int R>
+__device__ __forceinline__ void rb_sort_block(T (&r)[1 << R], bool desc) {
+#pragma unroll
+  for (int ph = 1; ph < R; ++ph) {
+#pragma unroll
+    for (int lb = ph - 1; lb >= 0; --lb) {
+#pragma unroll
+      for (int j = 0; j < (1 << R); ++j) {
+        if (j & (1 << lb)) continue;
+        const bool d = ((j >> ph) & 1) != 0;  // compile-time after unrolling
+        const T lo = Num<T>::mn(r[j], r[j | (1 << lb)]);
+        const T hi = Num<T>::mx(r[j], r[j | (1 << lb)]);
+        r[j] = d ? hi : lo;
+        r[j | (1 << lb)] = d ? lo : hi;
+      }
+    }
+  }
+  if (desc) rb_stages<T, R, true>(r);
+  else rb_stages<T, R, false>(r);
+}
+
+// One pass over the whole tile: exchange bits [b_lo, b_lo + R) of phase p (FIRST: phases 1..R at once).
+// L = log2(n_pad).  Ends with __syncthreads.
+template <typename T, int C, int R, bool FIRST>
+__device__ __forceinline__ void rb_pass(T* sm, int n_pad, int L, int b_lo, int p) {
+  const int n_items = (n_pad >> R) * C;
+  for (int item = threadIdx.x; item < n_items; item += blockDim.x) {
+    const int c = item % C, s = item / C;
+    const int base = ((s >> b_lo) << (b_lo + R)) | (s & ((1 << b_lo) - 1));
+    T* col = sm + (size_t)base * C + c;
+    const size_t step = (size_t)C << b_lo;
+    T r[1 << R];
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) r[j] = col[j * step];
+    const bool desc = p < L && ((base >> p) & 1);
+    if (FIRST) {
+      rb_sort_block<T, R>(r, desc);
+    } else if (desc) {
+      rb_stages<T, R, true>(r);
+    } else {
+      rb_stages<T, R, false>(r);
+    }
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) col[j * step] = r[j];
+  }
+  __syncthreads();
+}
+
+template <typename T, int C, bool FIRST>
+__device__ __forceinline__ void rb_pass_r(T* sm, int n_pad, int L, int b_lo, int p, int R) {
+  switch (R) {
+    case 1: rb_pass<T, C, 1, FIRST>(sm, n_pad, L, b_lo, p); break;
+    case 2: rb_pass<T, C, 2, FIRST>(sm, n_pad, L, b_lo, p); break;
+    case 3: rb_pass<T, C, 3, FIRST>(sm, n_pad, L, b_lo, p); break;
+    case 4: rb_pass<T, C, 4, FIRST>(sm, n_pad, L, b_lo, p); break;
+    default: rb_pass<T, C, 5, FIRST>(sm, n_pad, L, b_lo, p); break;
+  }
+}
+
+template <typename T, int C>
+__device__ void sort_columns_rb(T* sm, int n_pad) {
+  int L = 0;
+  while ((1 << L) < n_pad) ++L;
+  const int R0 = L < 5 ? L : 5;
+  rb_pass_r<T, C, true>(sm, n_pad, L, 0, R0, R0);  // phases 1..R0: every 2^R0-row block sorted
+  for (int p = R0 + 1; p <= L; ++p) {
+    int top = p;  // stages of bits p-1 .. 0, in chunks of up to 5 from the top
+    while (top > 0) {
+      const int R = top < 5 ? top : 5;
+      rb_pass_r<T, C, false>(sm, n_pad, L, top - R, p, R);
+      top -= R;
+    }
+  }
+}
+
+template <typename T, int C>
+__device__ void sort_columns(T* sm, int n_pad) {
+  if (C >= 8 && n_pad >= 32) sort_columns_rb<T, C>(sm, n_pad);
+  else sort_columns_v0<T, C>(sm, n_pad);
 }
 
 // Value at position i (may be negative, python-style) of the reference's sorted full-length row:
@@ -146,6 +254,7 @@ struct Tables {
   const T* gx;      // hist_q (per point) or q (shared, x_shared = true)
   const T* gy;      // af
   bool x_shared;
+  bool centre_only; // only slot 1 is staged: rows g-1 / g+1 are read from global memory when (rarely) needed
   int G;            // number of groups (rows are cyclic)
   long long pt_stride;  // G*nq
 };
@@ -253,7 +362,7 @@ __device__ __noinline__ T nearest_cross_rows(const Tables<T, C>& tb, int c, long
     for (int sgn = -1; sgn <= 1; sgn += 2) {
       const int pr = r + 1 + sgn * dist;  // padded row index
       if (pr < 0 || pr > tb.G + 1) continue;
-      if (dist == 1) {
+      if (dist == 1 && !tb.centre_only) {
         const int slot = 1 + sgn;
         nearest_in_row<TX, T, C>(tb.xsl[slot] + c, tb.ysl[slot] + c,
                                  tb.nvl[slot][c], x, dg2, best_d2, best_y);

@@ -163,7 +163,7 @@ train_kernel(const T* __restrict__ ref, const T* __restrict__ hist, long long n_
              const T* __restrict__ q, int nq, int kind, int normalize, int mode, T* __restrict__ af,
              T* __restrict__ hist_q, T* __restrict__ scaling, int n_pad, JitterParams jp, int use_jitter,
              const double* __restrict__ q64, AdaptParams ap) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sum = reinterpret_cast<double*>(smem_raw);   // [C]
   double* mu_ref = sum + C;                            // [C]
   int* cnt = reinterpret_cast<int*>(mu_ref + C);       // [C]
@@ -334,16 +334,16 @@ __device__ __forceinline__ const char* row_address(const char* base, int row, in
   return reinterpret_cast<const char*>(r);
 }
 
-template <bool JITTER>
+template <bool JITTER, bool NORM>
 __global__ void __launch_bounds__(kFastThreads, 1)
 train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist, long long n_pts, long long st,
                   const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
                   const float* __restrict__ q, int nq, int kind, int normalize_arg, int mode, float* __restrict__ af,
                   float* __restrict__ hist_q, float* __restrict__ scaling, JitterParams jp, int use_jitter,
                   const double* __restrict__ q64, int stagger_ns) {
-  // JITTER = the general instantiation (jitter and / or dqm_train's normalisation); <false> is the lean EQM one
-  const int normalize = JITTER ? normalize_arg : 0;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // <false, false> is the lean EQM instantiation; NORM adds dqm_train's normalisation, JITTER the jitter options
+  const int normalize = NORM ? normalize_arg : 0;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float* buf = reinterpret_cast<float*>(smem_raw + FastSmem::buf);
   int* rows_tab = reinterpret_cast<int*>(smem_raw + FastSmem::rows);
   int* pcnt = reinterpret_cast<int*>(smem_raw + FastSmem::pcnt);
@@ -410,7 +410,7 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
       for (int i = 0; i < 32; ++i) if (v[i] == v[i]) my_sum += (double)v[i];
     }
     // lean instantiation: valid count and the sort key (NaN -> +inf, NaNs sort last) from one predicate per element
-    if (!JITTER) {
+    if (!NORM) {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         asm("{\n\t.reg .pred p;\n\tsetp.num.f32 p, %1, %1;\n\t@p add.s32 %0, %0, 1;\n\t@!p mov.f32 %1, %2;\n\t}"
@@ -445,7 +445,7 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
     {
       float* dst = buf + ((size_t)half * 512 + (warp >> 1)) * 32 + lane;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) dst[(size_t)i * 16 * 32] = JITTER ? ((v[i] == v[i]) ? v[i] : finf) : v[i];
+      for (int i = 0; i < 32; ++i) dst[(size_t)i * 16 * 32] = NORM ? ((v[i] == v[i]) ? v[i] : finf) : v[i];
     }
     __syncthreads();
     sort_halves_512(buf, stagger_ns);
@@ -518,6 +518,7 @@ __device__ void stage_tables(Tables<T, C>& tb, T* stage /*[2][C][nq|1]*/, long l
   T* sy = stage + (size_t)C * pitch;
   for (int s = 0; s < (grouped ? 3 : 1); ++s) {
     const int slot = grouped ? s : 1;
+    if (tb.centre_only && slot != 1) continue;
     const int g = grouped ? (r + slot - 1 + tb.G) % tb.G : 0;
     int has_nan = 0;
     for (int idx = threadIdx.x; idx < C * nq; idx += blockDim.x) {
@@ -568,33 +569,36 @@ __device__ void stage_tables(Tables<T, C>& tb, T* stage /*[2][C][nq|1]*/, long l
   }
 }
 
+// slots = 3: rows g-1, g, g+1 staged; slots = 1: the centre row only (Tables::centre_only)
 template <typename T, int C>
-__device__ Tables<T, C> carve_tables(unsigned char* base, int nq) {
+__device__ Tables<T, C> carve_tables(unsigned char* base, int nq, int slots = 3) {
   Tables<T, C> tb;
   tb.nq = nq;
   int top = 1;
   while (top * 2 <= nq) top *= 2;
   tb.top = top;
   tb.ld = 2 * top;
+  tb.centre_only = slots == 1;
   T* xs = reinterpret_cast<T*>(base);
-  T* ys = xs + (size_t)3 * tb.ld * C;
-  tb.blo = ys + (size_t)3 * tb.ld * C;
+  T* ys = xs + (size_t)slots * tb.ld * C;
+  tb.blo = ys + (size_t)slots * tb.ld * C;
   tb.bhi = tb.blo + C;
   tb.clo = tb.bhi + C;
   tb.chi = tb.clo + C;
   int* nv = reinterpret_cast<int*>(tb.chi + C);
   for (int sl = 0; sl < 3; ++sl) {
-    tb.xsl[sl] = xs + (size_t)sl * tb.ld * C;
-    tb.ysl[sl] = ys + (size_t)sl * tb.ld * C;
+    const int pos = slots == 1 ? 0 : sl;
+    tb.xsl[sl] = xs + (size_t)pos * tb.ld * C;
+    tb.ysl[sl] = ys + (size_t)pos * tb.ld * C;
     tb.nvl[sl] = nv + sl * C;
   }
   return tb;
 }
 template <typename T, int C>
-__host__ __device__ constexpr size_t tables_bytes(int nq) {
+__host__ __device__ constexpr size_t tables_bytes(int nq, int slots = 3) {
   int top = 1;
   while (top * 2 <= nq) top *= 2;
-  return ((size_t)6 * (nq > 0 ? 2 * top : 0) * C + 4 * C) * sizeof(T) + 3 * C * sizeof(int);
+  return ((size_t)2 * slots * (nq > 0 ? 2 * top : 0) * C + 4 * C) * sizeof(T) + 3 * C * sizeof(int);
 }
 template <typename T, int C>
 __host__ __device__ constexpr size_t stage_bytes(int nq) { return (size_t)2 * C * (nq | 1) * sizeof(T); }
@@ -613,7 +617,7 @@ adjust_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long lon
   // C = points per CTA: 32 (lane = point) unless the tables of a very fine quantile grid need the shared memory
   constexpr int U = 4;
   if (gate_count && *gate_count <= gate_cap) return;  // overflow fallback of K2t: nothing to redo
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   Tables<T, C> tb = carve_tables<T, C>(smem_raw, nq);
   T* stage = reinterpret_cast<T*>(smem_raw + ((tables_bytes<T, C>(nq) + 15) & ~(size_t)15));
   tb.gx = hist_q; tb.gy = af; tb.x_shared = false; tb.G = n_groups; tb.pt_stride = (long long)n_groups * nq;
@@ -666,7 +670,7 @@ adjust_fast_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
   constexpr int C = 32;
   constexpr int U = 8;         // rows per batch; two batches in flight per warp (software pipeline)
   constexpr int LD = 2 * TOP;  // rows per staged slot (tb.ld)
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   Tables<float, C> tb = carve_tables<float, C>(smem_raw, nq);
   float* stage = reinterpret_cast<float*>(smem_raw + ((tables_bytes<float, C>(nq) + 15) & ~(size_t)15));
   int* rows_sm = reinterpret_cast<int*>(stage + 2 * C * (nq | 1));
@@ -769,7 +773,7 @@ __global__ void __launch_bounds__(kThreads)
 pack_tables_kernel(const float* __restrict__ af, const float* __restrict__ hist_q, long long n_pts, int n_groups,
                    int nq, PackedSlot<2 * TOP>* __restrict__ packed) {
   constexpr int C = 32, LD = 2 * TOP;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   PackedSlot<LD>* slot = reinterpret_cast<PackedSlot<LD>*>(smem_raw);
   float* stage = reinterpret_cast<float*>(smem_raw + sizeof(PackedSlot<LD>));
   Tables<float, C> tb;
@@ -806,19 +810,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                    smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// exact (float64 / cross-row) lookup on three ring slots holding rows g-1, g, g+1
-template <int LD>
-__device__ __noinline__ float lookup_exact_slots(const PackedSlot<LD>* const (&s3)[3], Tables<float, 32> tb, int lane,
-                                                 long long pt, int g, float x, int extrap) {
-  for (int sl = 0; sl < 3; ++sl) {
-    tb.xsl[sl] = const_cast<float*>(s3[sl]->xs);
-    tb.ysl[sl] = const_cast<float*>(s3[sl]->ys);
-    tb.nvl[sl] = const_cast<int*>(s3[sl]->nv);
-  }
-  tb.blo = const_cast<float*>(s3[1]->blo); tb.bhi = const_cast<float*>(s3[1]->bhi);
-  tb.clo = const_cast<float*>(s3[1]->clo); tb.chi = const_cast<float*>(s3[1]->chi);
-  return lookup_2d_nearest<float, float, 32>(tb, lane, pt, g, x, extrap);
-}
 
 // Exact 2-D nearest rule straight from the raw global tables (no staging): used for the few samples the
 // float32 fast path of K2t cannot decide (near-ties, far nodes, empty rows).  Same candidate order as
@@ -960,7 +951,6 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
     char* __restrict__ dstb = reinterpret_cast<char*>(dst);
     const int st4 = st * 4;
     auto load_batch = [&](int mb, float (&xv)[U], int (&ov)[U]) {
-#pragma unroll
       const int4 r0 = *reinterpret_cast<const int4*>(rows + mb), r1 = *reinterpret_cast<const int4*>(rows + mb + 4);
       ov[0] = r0.x; ov[1] = r0.y; ov[2] = r0.z; ov[3] = r0.w;
       ov[4] = r1.x; ov[5] = r1.y; ov[6] = r1.z; ov[7] = r1.w;
@@ -1153,7 +1143,7 @@ dqm_adjust_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long
                   const T* __restrict__ af, const T* __restrict__ hist_q, const T* __restrict__ scaling,
                   const double* __restrict__ trend, int nq, int interp, int extrap, int kind, T* __restrict__ scen) {
   constexpr int C = 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   Tables<T, C> tb = carve_tables<T, C>(smem_raw, nq);
   T* stage = reinterpret_cast<T*>(smem_raw + ((tables_bytes<T, C>(nq) + 15) & ~(size_t)15));
   tb.gx = hist_q; tb.gy = af; tb.x_shared = false; tb.G = n_groups; tb.pt_stride = (long long)n_groups * nq;
@@ -1380,15 +1370,15 @@ rank_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long 
             const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
             const T* __restrict__ af, const T* __restrict__ q, int nq, int interp, int extrap, int kind,
             int do_adjust, T* __restrict__ scen, double* __restrict__ sim_q, int n_pad, int rank_mode,
-            const double* __restrict__ gcoord, const unsigned char* __restrict__ diag) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+            const double* __restrict__ gcoord, const unsigned char* __restrict__ diag, int slots) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double* mnmx = reinterpret_cast<double*>(smem_raw);      // [2][C]
   double* sum = mnmx + 2 * C;                              // [C] (unused sum slot of count_columns)
   int* cnt = reinterpret_cast<int*>(sum + C);              // [C]
   unsigned char* p = smem_raw + C * 28 + ((C * 28) % 8 ? 4 : 0);
   T* sm = reinterpret_cast<T*>(p);                         // [n_pad][C]
-  Tables<T, C> tb = carve_tables<T, C>(p + (size_t)n_pad * C * sizeof(T), nq);
-  T* stage = reinterpret_cast<T*>(p + (size_t)n_pad * C * sizeof(T) + ((tables_bytes<T, C>(nq) + 15) & ~(size_t)15));
+  Tables<T, C> tb = carve_tables<T, C>(p + (size_t)n_pad * C * sizeof(T), nq, slots);
+  T* stage = reinterpret_cast<T*>(p + (size_t)n_pad * C * sizeof(T) + ((tables_bytes<T, C>(nq, slots) + 15) & ~(size_t)15));
 
   const int g = blockIdx.y;
   const long long n0 = (long long)blockIdx.x * C;
@@ -1554,7 +1544,7 @@ reorder_kernel(const T* __restrict__ sim, const T* __restrict__ ref, long long n
                const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows,
                const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int window, int n_pad,
                T* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sum = reinterpret_cast<double*>(smem_raw);
   int* cnt = reinterpret_cast<int*>(sum + C);
   T* sref = reinterpret_cast<T*>(smem_raw + C * 16);      // sorted ref keys [n_pad][C]
@@ -1624,7 +1614,7 @@ __global__ void __launch_bounds__(kThreads)
 select_kernel(const T* __restrict__ x, const T* __restrict__ y, long long n_pts, long long sp, long long st,
               const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups, int mode,
               const T* __restrict__ rnk, const double* __restrict__ yvals, int nv, T* __restrict__ out, int n_pad) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sum = reinterpret_cast<double*>(smem_raw);   // [C]
   int* cnt = reinterpret_cast<int*>(sum + C);          // [C]
   int* ycnt = cnt + C;                                 // [C]
@@ -1721,7 +1711,7 @@ adapt_apply_kernel(const T* __restrict__ sim, long long n_pts, long long sp, lon
                    const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows, int n_groups,
                    double thresh, const double* __restrict__ P0_ref, const double* __restrict__ P0_hist,
                    const T* __restrict__ pth, unsigned long long seed, T* __restrict__ out, int n_pad) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sum = reinterpret_cast<double*>(smem_raw);
   int* cnt = reinterpret_cast<int*>(sum + C);
   int* nle = cnt + C;
@@ -1799,7 +1789,7 @@ __global__ void __launch_bounds__(kThreads)
 escore_kernel(const T* __restrict__ tgt, const T* __restrict__ sim, long long n_pts, long long sp, long long st,
               int n_time_t, int n_time_s, int step_t, int step_s, int n_var, long long var_stride_t,
               long long var_stride_s, T* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   int* idx_t = reinterpret_cast<int*>(smem_raw);                 // valid observation rows of tgt
   int* idx_s = idx_t + (n_time_t + step_t - 1) / step_t;         // valid observation rows of sim
   __shared__ int n_t, n_s;
@@ -1935,19 +1925,20 @@ bool launch_train_fast(const float* ref, const float* hist, int64_t n_pts, int64
   const size_t smem = FastSmem::total(nq);
   dim3 grid((unsigned)((n_pts + 31) / 32), (unsigned)grp->n_groups);
   static const int stagger_ns = getenv("XSDBA_B200_STAGGER_NS") ? atoi(getenv("XSDBA_B200_STAGGER_NS")) : 0;
-  if (use_jitter || normalize) {
-    *rc = set_smem(train_fast_kernel<true>, smem);
-    if (*rc) return true;
-    train_fast_kernel<true><<<grid, kFastThreads, smem, s>>>(ref, hist, n_pts, st, grp->segments.off, grp->segments.rows,
-                                                             grp->n_groups, q, nq, kind, normalize, mode, af, hq, scaling,
-                                                             jp, use_jitter, q64, stagger_ns);
-  } else {
-    *rc = set_smem(train_fast_kernel<false>, smem);
-    if (*rc) return true;
-    train_fast_kernel<false><<<grid, kFastThreads, smem, s>>>(ref, hist, n_pts, st, grp->segments.off, grp->segments.rows,
-                                                              grp->n_groups, q, nq, kind, normalize, mode, af, hq, scaling,
-                                                              jp, use_jitter, q64, stagger_ns);
-  }
+#define XS_TRAIN_FAST(J, N)                                                                                          \
+  do {                                                                                                               \
+    *rc = set_smem(train_fast_kernel<J, N>, smem);                                                                   \
+    if (*rc) return true;                                                                                            \
+    train_fast_kernel<J, N><<<grid, kFastThreads, smem, s>>>(ref, hist, n_pts, st, grp->segments.off,                \
+                                                             grp->segments.rows, grp->n_groups, q, nq, kind,        \
+                                                             normalize, mode, af, hq, scaling, jp, use_jitter, q64, \
+                                                             stagger_ns);                                           \
+  } while (0)
+  if (use_jitter && normalize) XS_TRAIN_FAST(true, true);
+  else if (use_jitter) XS_TRAIN_FAST(true, false);
+  else if (normalize) XS_TRAIN_FAST(false, true);
+  else XS_TRAIN_FAST(false, false);
+#undef XS_TRAIN_FAST
   ++g_launches;
   *rc = cuda_status(cudaGetLastError());
   return true;
@@ -2143,10 +2134,11 @@ template <typename T, int C>
 int launch_rank_c(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
                   const DevTable& seg, const T* af, const T* q, int nq, int interp, int extrap, int kind,
                   int do_adjust, T* scen, double* sim_q, int n_pad, cudaStream_t s, int rank_mode, const double* gcoord,
-                  const unsigned char* diag) {
+                  const unsigned char* diag, int slots) {
   const size_t head = (size_t)C * 28 + (((size_t)C * 28) % 8 ? 4 : 0);
   const size_t smem = head + (size_t)n_pad * C * sizeof(T) +
-                      (do_adjust ? ((tables_bytes<T, C>(nq) + 15) & ~(size_t)15) + stage_bytes<T, C>(nq) : tables_bytes<T, C>(0));
+                      (do_adjust ? ((tables_bytes<T, C>(nq, slots) + 15) & ~(size_t)15) + stage_bytes<T, C>(nq)
+                                 : tables_bytes<T, C>(0, slots));
   if (smem > 220 * 1024) return XSDBA_ERR_SEGMENT_TOO_LONG;
   auto kern = rank_kernel<T, C>;
   int rc = set_smem(kern, smem);
@@ -2154,7 +2146,7 @@ int launch_rank_c(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsd
   dim3 grid((unsigned)((n_pts + C - 1) / C), (unsigned)grp->n_groups);
   kern<<<grid, kThreads, smem, s>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows, seg.off, seg.rows,
                                     grp->n_groups, af, q, do_adjust ? nq : 0, interp, extrap, kind, do_adjust, scen,
-                                    sim_q, n_pad, rank_mode, gcoord, diag);
+                                    sim_q, n_pad, rank_mode, gcoord, diag, slots);
   ++g_launches;
   return cuda_status(cudaGetLastError());
 }
@@ -2179,18 +2171,22 @@ int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba
   const DevTable& seg = rank_window ? grp->segments : grp->members;
   const int n_pad = std::max(2, next_pow2(seg.max_len));
   int C = pick_cols<T>(n_pad);
+  // the linear rule interpolates between rows: it needs the three staged rows.  The nearest rule almost never
+  // leaves the centre row (quantile nodes are < 1 apart, neighbouring rows are 1 away), so it stages that row only
+  // and reads the neighbours from global memory in the rare case -- a third of the shared memory, 3x the occupancy
+  const int slots = (do_adjust && grp->n_groups > 1 && interp == XSDBA_INTERP_LINEAR) ? 3 : 1;
   // the staged lookup tables share the CTA's shared memory with the sort buffer: narrow the tile until both fit
   auto need = [&](int c) {
     size_t top = 1;
     while (top * 2 <= (size_t)nq) top *= 2;
-    const size_t tables = do_adjust ? ((size_t)6 * 2 * top * c + 4 * c) * sizeof(T) + 3 * c * sizeof(int) + 16 +
+    const size_t tables = do_adjust ? ((size_t)2 * slots * 2 * top * c + 4 * c) * sizeof(T) + 3 * c * sizeof(int) + 16 +
                                           (size_t)2 * c * (nq | 1) * sizeof(T)
                                     : 0;
     return (size_t)c * 28 + 8 + (size_t)n_pad * c * sizeof(T) + tables;
   };
   while (C > 1 && need(C) > 216 * 1024) C >>= 1;
   cudaStream_t s = (cudaStream_t)stream;
-#define XS_CASE(CC) case CC: return launch_rank_c<T, CC>(sim, n_pts, sp, st, grp, seg, af, q, nq, interp, extrap, kind, do_adjust, scen, sim_q, n_pad, s, rank_mode, gcoord, diag)
+#define XS_CASE(CC) case CC: return launch_rank_c<T, CC>(sim, n_pts, sp, st, grp, seg, af, q, nq, interp, extrap, kind, do_adjust, scen, sim_q, n_pad, s, rank_mode, gcoord, diag, slots)
   switch (C) {
     XS_CASE(32); XS_CASE(16); XS_CASE(8); XS_CASE(4); XS_CASE(2); XS_CASE(1);
     default: return XSDBA_ERR_SEGMENT_TOO_LONG;
