@@ -836,3 +836,27 @@ def test_adjust_periods_moving_windows():
         yr = tx_s.year[slc]
         sel = (yr >= ya) & (yr < yb)
         assert bits_equal(scen[slc][sel], full[sel])
+
+
+@pytest.mark.parametrize("years,dt", [(30, np.float32), (12, np.float64), (30, np.float64)])
+def test_long_segments_group_time(years, dt):
+    """group="time" over decades: 4k-11k-row segments, the narrow-tile sorter (C = 4, 2, 1 columns per CTA).
+    BASELINE.json config 0 is this shape (EQM, nquantiles=50, group='time', 30 years)."""
+    xs = _xs()
+    case = ("time", 1, "noleap", years, 50, "+", "tas", dt)
+    tx, to, ref, hist, sim = _make(case, n_pts=9, seed=4)
+    q = o.equally_spaced_nodes(50).astype(dt)
+    gidx, G, _ = o.group_index(to, "time")
+    af_o, hq_o = o.eqm_train(ref.T.copy(), hist.T.copy(), gidx, G, 1, q, "+")
+    ds = xs.eqm_train(xs.Dataset({"ref": ref, "hist": hist}, time=tx), group="time", kind="+", quantiles=q)
+    if dt == np.float32:
+        assert bits_equal(_np(ds.hist_q), hq_o) and bits_equal(_np(ds.af), af_o)
+    else:
+        np.testing.assert_allclose(_np(ds.hist_q), hq_o, rtol=1e-12, atol=0, equal_nan=True)
+    # QDM adjust ranks every sample inside the full series (rank kernel on the same sorter)
+    scen_o, simq_o = o.qdm_adjust(sim.T.copy(), af_o, q, group="time", time=to, window=1, interp="nearest",
+                                  extrapolation="constant", kind="+")
+    out = xs.qdm_adjust(xs.Dataset({"sim": sim, "af": af_o, "quantiles": q}, time=tx), group="time", interp="nearest",
+                        extrapolation="constant", kind="+")
+    assert bits_equal(_np(out.sim_q).T, simq_o)
+    assert bits_equal(_np(out.scen).T, scen_o)

@@ -196,10 +196,78 @@ __device__ void sort_columns_rb(T* sm, int n_pad) {
   }
 }
 
+// Narrow tiles (C < 8 columns: segments of 4k..32k rows).  The exchange bits 5 and above are register blocked
+// as above -- the lanes of a warp then take consecutive rows, which is conflict free for any C -- and the
+// stages of bits 4..0 run inside a warp on one 32-row block of all C columns: the block is 32*C contiguous
+// floats, lane l holds elements l, l+32, ... (row = element / C), so the low 5 - log2(C) row bits live in
+// the lane index (compare-exchange by __shfl_xor) and the remaining ones in the register index.
+template <typename T, int C, bool FIRST>
+__device__ __forceinline__ void warp_block_pass(T* sm, int n_pad, int L, int p) {
+  constexpr int LC = C == 1 ? 0 : (C == 2 ? 1 : (C == 4 ? 2 : (C == 8 ? 3 : (C == 16 ? 4 : 5))));
+  constexpr int LANE_BITS = 5 - LC;  // row bits held in the lane index (lane bit = row bit + LC)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  for (int blk = warp; blk < (n_pad >> 5); blk += n_warps) {
+    T* base = sm + (size_t)blk * 32 * C;
+    T v[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) v[k] = base[lane + 32 * k];
+    const bool blk_desc = p < L && (((blk << 5) >> p) & 1);
+#pragma unroll
+    for (int ph = FIRST ? 1 : 5; ph <= 5; ++ph) {
+#pragma unroll
+      for (int b = (FIRST ? ph : 5) - 1; b >= 0; --b) {
+        if (b < LANE_BITS) {
+          const bool upper = (lane >> (b + LC)) & 1;
+#pragma unroll
+          for (int k = 0; k < C; ++k) {
+            // direction of this element's sub-sequence: row bit ph inside the block, the block's own bit for ph == 5
+            const int row = (lane >> LC) + k * (32 >> LC);
+            const bool desc = (FIRST && ph < 5) ? ((row >> ph) & 1) : blk_desc;
+            const T o = __shfl_xor_sync(0xffffffffu, v[k], 1 << (b + LC));
+            const T lo = Num<T>::mn(v[k], o), hi = Num<T>::mx(v[k], o);
+            v[k] = (upper == desc) ? lo : hi;
+          }
+        } else {
+          const int kb = 1 << (b - LANE_BITS);
+#pragma unroll
+          for (int k = 0; k < C; ++k) {
+            if (k & kb) continue;
+            const int row = (lane >> LC) + k * (32 >> LC);
+            const bool desc = (FIRST && ph < 5) ? ((row >> ph) & 1) : blk_desc;
+            const T lo = Num<T>::mn(v[k], v[k | kb]), hi = Num<T>::mx(v[k], v[k | kb]);
+            v[k] = desc ? hi : lo;
+            v[k | kb] = desc ? lo : hi;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < C; ++k) base[lane + 32 * k] = v[k];
+  }
+  __syncthreads();
+}
+
+template <typename T, int C>
+__device__ void sort_columns_narrow(T* sm, int n_pad) {
+  int L = 0;
+  while ((1 << L) < n_pad) ++L;
+  warp_block_pass<T, C, true>(sm, n_pad, L, 5);  // phases 1..5: every 32-row block sorted
+  for (int p = 6; p <= L; ++p) {
+    int top = p;  // bits p-1 .. 5 register blocked in chunks of up to 5, then bits 4 .. 0 inside a warp
+    while (top > 5) {
+      const int R = top - 5 < 5 ? top - 5 : 5;
+      rb_pass_r<T, C, false>(sm, n_pad, L, top - R, p, R);
+      top -= R;
+    }
+    warp_block_pass<T, C, false>(sm, n_pad, L, p);
+  }
+}
+
 template <typename T, int C>
 __device__ void sort_columns(T* sm, int n_pad) {
-  if (C >= 8 && n_pad >= 32) sort_columns_rb<T, C>(sm, n_pad);
-  else sort_columns_v0<T, C>(sm, n_pad);
+  if (n_pad < 32) sort_columns_v0<T, C>(sm, n_pad);
+  else if (C >= 8) sort_columns_rb<T, C>(sm, n_pad);
+  else sort_columns_narrow<T, C>(sm, n_pad);
 }
 
 // Value at position i (may be negative, python-style) of the reference's sorted full-length row:
