@@ -1282,11 +1282,46 @@ __device__ double loess_one(const T* __restrict__ y, const int32_t* __restrict__
 // K6b: thread = (point, chunk of RO consecutive outputs).  A chunk that is interior for the thread's series
 // runs as a register-tiled FIR on the precomputed weights (every y / w value is loaded once per chunk and
 // feeds RO accumulators); edge chunks and short series use the literal per-output rule.
+// K6e: edge weights shared by every point WITHOUT missing values (n == n_time: the compacted axis is the full axis,
+// so the weights of the first HW+1 and the last HW outputs depend on (output, tap) only, loess.py:138-147).  One
+// table per call, tap-major: etab[j * NI + e] with e = i for the left outputs, HW+1 + (i - (n-HW)) for the right
+// ones, j relative to the shared window [0, R) / [n-R, n); esum[e] = the weights summed in tap order.  38 MB for
+// 30 years at f = 0.2 -- L2 resident -- against 10 float64 operations per (tap, output) to recompute them.
+__global__ void __launch_bounds__(kThreads)
+loess_edge_table_kernel(const double* __restrict__ xn, int n, double f, double* __restrict__ etab) {
+  const LoessGeom gm(n, f);
+  const int NI = 2 * gm.HW + 1;
+  const double dx = xn[1] - xn[0];
+  const long long total = (long long)gm.R * NI;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(idx % NI), j = (int)(idx / NI);
+    const bool left = e <= gm.HW;
+    const int i = left ? e : n - gm.HW + (e - gm.HW - 1);
+    const int lo = left ? 0 : n - gm.R;
+    double h;
+    if (i < gm.hw) h = (double)(gm.r - i) * dx;
+    else if (i >= n - gm.hw) h = (double)(i - (n - gm.r) + 1) * dx;
+    else h = (double)(gm.hw + 1) * dx;
+    etab[idx] = tricube_w(fabs(xn[lo + j] - xn[i]) * (1.0 / h));
+  }
+}
+__global__ void loess_edge_sum_kernel(int n, double f, const double* __restrict__ etab, double* __restrict__ esum) {
+  const LoessGeom gm(n, f);
+  const int NI = 2 * gm.HW + 1;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= NI) return;
+  double s = 0.0;
+  for (int j = 0; j < gm.R; ++j) s += etab[(long long)j * NI + e];
+  esum[e] = s;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, const int32_t* __restrict__ nvalid,
                     long long n_pts, long long sp, long long st, int n_time, const double* __restrict__ xn,
-                    double f, int degree, const double* __restrict__ wtab, double* __restrict__ trend) {
+                    double f, int degree, const double* __restrict__ wtab, const double* __restrict__ etab,
+                    const double* __restrict__ esum, double* __restrict__ trend) {
   constexpr int RO = 8;
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5, rows_per_cta = blockDim.x >> 5;
   const long long pt = (long long)blockIdx.x * 32 + lane;
@@ -1324,6 +1359,25 @@ loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, co
       // edge chunk: all RO outputs share the window [0, R) (left) or [n-R, n) (right) and recompute their weights
       // (loess.py:138-147): every y_j / x_j is loaded once and feeds RO (weight, sum) pairs.
       const int lo = (i0 + RO - 1 <= gm.HW) ? 0 : n - gm.R;
+      if (etab && n == n_time) {  // complete series: weights and their sums come from the shared table (K6e)
+        const int NI = 2 * gm.HW + 1;
+        const int e0 = lo == 0 ? i0 : gm.HW + 1 + (i0 - (n - gm.HW));
+        const double* et = etab + e0;
+        const T* yl = y + (long long)lo * n_pts;
+        double swy[RO];
+#pragma unroll
+        for (int r = 0; r < RO; ++r) swy[r] = 0;
+        for (int j = 0; j < gm.R; ++j) {
+          const double yj = (double)yl[(long long)j * n_pts];
+#pragma unroll
+          for (int r = 0; r < RO; ++r) swy[r] = fma(et[r], yj, swy[r]);
+          et += NI;
+        }
+#pragma unroll
+        for (int r = 0; r < RO; ++r)
+          trend[pt * sp + (long long)tcp[(long long)(i0 + r) * n_pts] * st] = swy[r] / esum[e0 + r];
+        continue;
+      }
       double xi[RO], ih[RO], sw[RO], swy[RO];
 #pragma unroll
       for (int r = 0; r < RO; ++r) {
@@ -2261,11 +2315,30 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
     return XSDBA_ERR_OUT_OF_MEMORY;
   }
   loess_weights_kernel<<<dim3((unsigned)((n_pts + 31) / 32), 16), kThreads, 0, s>>>(tc, nv, n_pts, n_time, xn, f, w_rows, wtab);
+  // edge weights of complete series (optional: without the table the kernel recomputes them per point)
+  double* etab = nullptr;
+  double* esum = nullptr;
+  if (degree == 0 && n_time >= 8) {
+    const int r_ = (int)(2.0 * std::floor(f * (double)n_time / 2.0) + 1.0);   // LoessGeom on the host
+    const int HW_ = (r_ - 1) / 2 + 2, R_ = std::min(r_ + 4, n_time), NI_ = 2 * HW_ + 1;
+    if (n_time >= R_ && n_time > 2 * HW_ + 2 &&
+        cudaMallocAsync(&etab, sizeof(double) * (size_t)R_ * NI_ + sizeof(double) * NI_, s) == cudaSuccess) {
+      esum = etab + (size_t)R_ * NI_;
+      loess_edge_table_kernel<<<148 * 8, kThreads, 0, s>>>(xn, n_time, f, etab);
+      loess_edge_sum_kernel<<<(unsigned)((NI_ + 127) / 128), 128, 0, s>>>(n_time, f, etab, esum);
+      g_launches += 2;
+    } else {
+      cudaGetLastError();
+      etab = nullptr;
+    }
+  }
   const unsigned chunks = (unsigned)std::min<int64_t>(std::max<int64_t>(1, (n_time + 63) / 64), 1024);
   loess_smooth_kernel<T><<<dim3((unsigned)((n_pts + 31) / 32), chunks), kThreads, 0, s>>>(yc, tc, nv, n_pts, sp, st, n_time,
-                                                                                          xn, f, degree, wtab, trend);
+                                                                                          xn, f, degree, wtab, etab, esum,
+                                                                                          trend);
   g_launches += 3;
   cudaFreeAsync(yc, s); cudaFreeAsync(tc, s); cudaFreeAsync(nv, s); cudaFreeAsync(wtab, s);
+  if (etab) cudaFreeAsync(etab, s);
   return cuda_status(cudaGetLastError());
 }
 
