@@ -276,6 +276,23 @@ def test_loess_trend_reference_golden(golden, d, f):
         np.testing.assert_allclose(got[:, j], wj, rtol=1e-11, atol=1e-12, equal_nan=True)
 
 
+def test_loess_complete_series_shared_tables():
+    """Complete (NaN-free) series take the shared-table paths of K6 (broadcast interior weights for a warp of 32
+    complete points, L2-resident edge-weight table); one column with a gap keeps its warp on the per-point path.
+    Both must reproduce the float64 restatement of _loess_nb to 1e-11."""
+    xs = _xs()
+    rng = np.random.default_rng(8)
+    t = xs.TimeAxis.daily(2001, 3, "noleap")
+    n = len(t)
+    x = np.arange(n, dtype=np.float64)
+    y = (280 + 5 * np.sin(2 * np.pi * x / 365)[:, None] + rng.standard_normal((n, 70))).astype(np.float32)
+    y[100:130, 65] = np.nan                      # points 64..69 share a warp with an incomplete column
+    got = _np(xs.loess_trend(y, time=t, f=0.2, niter=1, d=0))
+    for j in (0, 17, 31, 32, 63, 64, 65, 69):
+        want = o.loess_nb(x, y[:, j].astype(np.float64), f=0.2, niter=1, d=0, dx=1.0)
+        np.testing.assert_allclose(got[:, j], want, rtol=1e-11, atol=1e-12, equal_nan=True)
+
+
 def test_dqm_adjust_loess_matches_oracle():
     xs = _xs()
     case = ("time.month", 1, "noleap", 3, 20, "+", "tas", np.float32)

@@ -1234,9 +1234,40 @@ loess_weights_kernel(const int32_t* __restrict__ tc, const int32_t* __restrict__
   const double dx = xn[1] - xn[0];
   const double h = (double)(gm.hw + 1) * dx;
   const double xc = xn[tc[(long long)gm.HW * n_pts + pt]];
-  for (int k = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); k <= 2 * gm.HW && k < w_rows;
-       k += gridDim.y * (blockDim.x >> 5))
-    wtab[(long long)k * n_pts + pt] = tricube_w(fabs(xn[tc[(long long)k * n_pts + pt]] - xc) / h);
+  for (int k = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); k < w_rows; k += gridDim.y * (blockDim.x >> 5))
+    wtab[(long long)k * n_pts + pt] =
+        k <= 2 * gm.HW ? tricube_w(fabs(xn[tc[(long long)k * n_pts + pt]] - xc) / h) : 0.0;  // zero tail: K6 reads past K
+}
+
+// total interior weight of every point, summed in tap order like the reference's w.sum() (loess.py:38-39): all
+// interior outputs of a point share it.  Row w_rows of wtab; the complete-series value goes to wsh[w_rows].
+__global__ void loess_wsum_kernel(const int32_t* __restrict__ nvalid, long long n_pts, int n_time, double f, int w_rows,
+                                  double* __restrict__ wtab, double* __restrict__ wsh) {
+  const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pt == n_pts && wsh) {  // one extra thread sums the shared vector
+    double s = 0.0;
+    const LoessGeom gm(n_time, f);
+    for (int k = 0; k <= 2 * gm.HW && k < w_rows; ++k) s += wsh[k];
+    wsh[w_rows] = s;
+  }
+  if (pt >= n_pts) return;
+  const LoessGeom gm(nvalid[pt], f);
+  double s = 0.0;
+  if (nvalid[pt] >= 2 * gm.HW + 3)
+    for (int k = 0; k <= 2 * gm.HW && k < w_rows; ++k) s += wtab[(long long)k * n_pts + pt];
+  wtab[(long long)w_rows * n_pts + pt] = s;
+}
+
+// interior weights of a COMPLETE series (n == n_time): the same for every such point, so a warp whose 32 points are
+// all complete reads one broadcast value per tap instead of 32 per-point ones
+__global__ void loess_shared_weights_kernel(const double* __restrict__ xn, int n, double f, int w_rows,
+                                            double* __restrict__ wsh) {
+  const LoessGeom gm(n, f);
+  const double dx = xn[1] - xn[0];
+  const double h = (double)(gm.hw + 1) * dx;
+  const double xc = xn[gm.HW];
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < w_rows; k += gridDim.x * blockDim.x)
+    wsh[k] = (k <= 2 * gm.HW && n >= 2 * gm.HW + 3) ? tricube_w(fabs(xn[k] - xc) / h) : 0.0;
 }
 
 // one output by the literal rule (edges, short series)
@@ -1320,8 +1351,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, const int32_t* __restrict__ nvalid,
                     long long n_pts, long long sp, long long st, int n_time, const double* __restrict__ xn,
-                    double f, int degree, const double* __restrict__ wtab, const double* __restrict__ etab,
-                    const double* __restrict__ esum, double* __restrict__ trend) {
+                    double f, int degree, const double* __restrict__ wtab, int w_rows, const double* __restrict__ wsh,
+                    const double* __restrict__ etab, const double* __restrict__ esum, double* __restrict__ trend) {
   constexpr int RO = 8;
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5, rows_per_cta = blockDim.x >> 5;
   const long long pt = (long long)blockIdx.x * 32 + lane;
@@ -1333,27 +1364,49 @@ loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, co
   const T* y = yc + pt;
   const int32_t* tcp = tc + pt;
   const double* w = wtab + pt;
+  // (lanes past n_pts / empty columns have left: vote among the remaining ones)
+  const bool warp_complete = wsh != nullptr && __all_sync(__activemask(), n == n_time);
   for (int i0 = (blockIdx.y * rows_per_cta + row) * RO; i0 < n; i0 += gridDim.y * rows_per_cta * RO) {
     const bool fast = degree == 0 && gm.interior(i0, n) && gm.interior(i0 + RO - 1, n);
     if (fast) {
       // output i0+r sums w[k] * y[i0 + r - HW + k], k = 0..2HW.  With j = i0 - HW + m the pair (m, r) uses w[m - r].
-      double sw[RO], swy[RO], wr[RO];
-#pragma unroll
-      for (int r = 0; r < RO; ++r) { sw[r] = 0; swy[r] = 0; wr[r] = 0; }
+      // Blocks of RO taps: the loads of block b+1 are issued before block b is consumed (the loop is otherwise a
+      // chain load -> fma -> next load, one memory latency per tap).  The weights sit in a register ring: step u
+      // overwrites slot u, so w[m - r] is slot (u - r) mod RO, a compile-time index.  Indices past the last tap are
+      // clamped: the weight rows beyond K are zero, so those products vanish.  The denominator is the point's
+      // total weight (loess_wsum_kernel).
       const int K = 2 * gm.HW;  // last weight index
       const T* yb = y + (long long)(i0 - gm.HW) * n_pts;
-      for (int m = 0; m <= K + RO - 1; ++m) {
-        // shift the weight window: wr[r] = w[m - r] (0 outside [0, K])
+      const double* wp = warp_complete ? wsh : w;
+      const long long wstep = warp_complete ? 1 : n_pts;
+      const double sw_total = warp_complete ? wsh[w_rows] : wtab[(long long)w_rows * n_pts + pt];
+      const int m_last = K + RO - 1;
+      double swy[RO], wr[RO], wn[RO], yn[RO];
 #pragma unroll
-        for (int r = RO - 1; r > 0; --r) wr[r] = wr[r - 1];
-        wr[0] = m <= K ? w[(long long)m * n_pts] : 0.0;
-        const double yj = (double)yb[(long long)m * n_pts];
+      for (int r = 0; r < RO; ++r) {
+        swy[r] = 0; wr[r] = 0;
+        wn[r] = wp[(long long)min(r, w_rows - 1) * wstep];
+        yn[r] = (double)yb[(long long)min(r, m_last) * n_pts];
+      }
+      for (int mb = 0; mb <= m_last; mb += RO) {
+        double wc[RO], yc[RO];
 #pragma unroll
-        for (int r = 0; r < RO; ++r) { sw[r] += wr[r]; swy[r] = fma(wr[r], yj, swy[r]); }
+        for (int u = 0; u < RO; ++u) { wc[u] = wn[u]; yc[u] = yn[u]; }
+#pragma unroll
+        for (int u = 0; u < RO; ++u) {
+          wn[u] = wp[(long long)min(mb + RO + u, w_rows - 1) * wstep];
+          yn[u] = (double)yb[(long long)min(mb + RO + u, m_last) * n_pts];
+        }
+#pragma unroll
+        for (int u = 0; u < RO; ++u) {
+          wr[u] = wc[u];
+#pragma unroll
+          for (int r = 0; r < RO; ++r) swy[r] = fma(wr[(u - r + RO) % RO], yc[u], swy[r]);
+        }
       }
 #pragma unroll
       for (int r = 0; r < RO; ++r)
-        trend[pt * sp + (long long)tcp[(long long)(i0 + r) * n_pts] * st] = swy[r] / sw[r];
+        trend[pt * sp + (long long)tcp[(long long)(i0 + r) * n_pts] * st] = swy[r] / sw_total;
     } else if (degree == 0 && n >= gm.R && i0 + RO <= n &&
                ((i0 + RO - 1 <= gm.HW) || (i0 >= n - gm.HW))) {
       // edge chunk: all RO outputs share the window [0, R) (left) or [n-R, n) (right) and recompute their weights
@@ -2309,12 +2362,22 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
   // interior weight table: at most 2*HW+1 <= f*n_time + 6 rows per point
   const int w_rows = (int)std::min<double>((double)n_time, f * (double)n_time + 8.0);
   double* wtab = nullptr;
-  if (cudaMallocAsync(&wtab, sizeof(double) * n_pts * w_rows, s) != cudaSuccess) {
+  if (cudaMallocAsync(&wtab, sizeof(double) * n_pts * (w_rows + 1), s) != cudaSuccess) {
     cudaGetLastError();
     cudaFreeAsync(yc, s); cudaFreeAsync(tc, s); cudaFreeAsync(nv, s);
     return XSDBA_ERR_OUT_OF_MEMORY;
   }
   loess_weights_kernel<<<dim3((unsigned)((n_pts + 31) / 32), 16), kThreads, 0, s>>>(tc, nv, n_pts, n_time, xn, f, w_rows, wtab);
+  double* wsh = nullptr;
+  if (cudaMallocAsync(&wsh, sizeof(double) * (w_rows + 1), s) == cudaSuccess) {
+    loess_shared_weights_kernel<<<8, kThreads, 0, s>>>(xn, n_time, f, w_rows, wsh);
+    ++g_launches;
+  } else {
+    cudaGetLastError();
+    wsh = nullptr;
+  }
+  loess_wsum_kernel<<<(unsigned)((n_pts + 1 + 127) / 128), 128, 0, s>>>(nv, n_pts, n_time, f, w_rows, wtab, wsh);
+  ++g_launches;
   // edge weights of complete series (optional: without the table the kernel recomputes them per point)
   double* etab = nullptr;
   double* esum = nullptr;
@@ -2334,11 +2397,12 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
   }
   const unsigned chunks = (unsigned)std::min<int64_t>(std::max<int64_t>(1, (n_time + 63) / 64), 1024);
   loess_smooth_kernel<T><<<dim3((unsigned)((n_pts + 31) / 32), chunks), kThreads, 0, s>>>(yc, tc, nv, n_pts, sp, st, n_time,
-                                                                                          xn, f, degree, wtab, etab, esum,
-                                                                                          trend);
+                                                                                          xn, f, degree, wtab, w_rows, wsh,
+                                                                                          etab, esum, trend);
   g_launches += 3;
   cudaFreeAsync(yc, s); cudaFreeAsync(tc, s); cudaFreeAsync(nv, s); cudaFreeAsync(wtab, s);
   if (etab) cudaFreeAsync(etab, s);
+  if (wsh) cudaFreeAsync(wsh, s);
   return cuda_status(cudaGetLastError());
 }
 
