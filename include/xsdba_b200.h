@@ -344,8 +344,9 @@ int xsdba_poly_trend_f64(const double* x_dev, int64_t n_pts, int64_t stride_pt, 
 /*
  * LOESS trend over the whole series: replaces detrending.LoessDetrend(group="time").fit(...).ds.trend =
  * loess.loess_smoothing -> numba _loess_nb (loess.py:49-179, 182-279; detrending.py:211-296) in its
- * equal-spacing, tricube, skipna form with local degree d in {0, 1}; niter = 1 (robustness iterations
- * return XSDBA_ERR_UNSUPPORTED).  y = x (+|*) scaling[point][group(t)] when scaling_dev != NULL (grp
+ * equal-spacing, tricube, skipna form with local degree d in {0, 1}; niter >= 1 (iterations after the first
+ * re-weight every sample with the bisquare of its residual over 6 x the median absolute residual,
+ * loess.py:166-176).  y = x (+|*) scaling[point][group(t)] when scaling_dev != NULL (grp
  * supplies group(t); pass a single-group handle otherwise).  xn_dev[n_time] is the time coordinate
  * rescaled to [0, 1] (loess.py:244-245).  trend_dev is float64 with the strides of x; NaN where x is NaN.
  */

@@ -276,6 +276,25 @@ def test_loess_trend_reference_golden(golden, d, f):
         np.testing.assert_allclose(got[:, j], wj, rtol=1e-11, atol=1e-12, equal_nan=True)
 
 
+def test_loess_robust_iterations_reference_golden(golden):
+    """niter > 1 (loess.py:166-176): golden case 1 of the reference's numba _loess_nb is (d=1, f=0.5, niter=2, equal
+    spacing); d=0 / niter=3 against the float64 restatement."""
+    xs = _xs()
+    x, y = golden["loess_x"], golden["loess_y"]
+    n = x.size
+    t = xs.TimeAxis.daily(2001, 1, "noleap")[:n]
+    assert tuple(golden["loess_case1_params"][:3]) == (1, 0.5, 2)
+    series = np.stack([y, y[::-1].copy(), np.where(np.arange(n) % 17 == 3, np.nan, y)], axis=1)
+    got = _np(xs.loess_trend(series, time=t, f=0.5, niter=2, d=1))
+    np.testing.assert_allclose(got[:, 0], golden["loess_case1_out"], rtol=1e-9, atol=1e-10, equal_nan=True)
+    dx = float(x[1] - x[0])
+    for d, f, niter in ((0, 0.2, 3), (1, 0.3, 2)):
+        got = _np(xs.loess_trend(series, time=t, f=f, niter=niter, d=d))
+        for j in range(3):
+            want = o.loess_nb(x, series[:, j], f=f, niter=niter, d=d, dx=dx)
+            np.testing.assert_allclose(got[:, j], want, rtol=1e-9, atol=1e-10, equal_nan=True)
+
+
 def test_loess_complete_series_shared_tables():
     """Complete (NaN-free) series take the shared-table paths of K6 (broadcast interior weights for a warp of 32
     complete points, L2-resident edge-weight table); one column with a gap keeps its warp on the per-point path.

@@ -1273,7 +1273,8 @@ __global__ void loess_shared_weights_kernel(const double* __restrict__ xn, int n
 // one output by the literal rule (edges, short series)
 template <typename T>
 __device__ double loess_one(const T* __restrict__ y, const int32_t* __restrict__ tcp, long long n_pts, int n, int i,
-                            const LoessGeom& gm, const double* __restrict__ xn, double dx, int degree) {
+                            const LoessGeom& gm, const double* __restrict__ xn, double dx, int degree,
+                            const double* __restrict__ delta = nullptr) {
   int lo, hi;                                                 // loess.py:124-135
   if (i < gm.HW) { lo = 0; hi = gm.R; }
   else if (i >= n - gm.HW - 1) { lo = n - gm.R; hi = n; }
@@ -1292,7 +1293,8 @@ __device__ double loess_one(const T* __restrict__ y, const int32_t* __restrict__
   double sw = 0, swy = 0, swx = 0, swxx = 0, swxy = 0;
   for (int j = lo; j < hi; ++j) {
     const int k = wlo + (j - lo);
-    const double w = k < n ? tricube_w(fabs(xn[tcp[(long long)k * n_pts]] - xc) / h) : 0.0;
+    double w = k < n ? tricube_w(fabs(xn[tcp[(long long)k * n_pts]] - xc) / h) : 0.0;
+    if (delta) w = delta[(long long)j * n_pts] * w;            // robustness weights: w = di * wi (loess.py:150)
     const double yj = (double)y[(long long)j * n_pts];
     sw += w; swy += w * yj;
     if (degree == 1) {
@@ -1352,7 +1354,8 @@ __global__ void __launch_bounds__(kThreads)
 loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, const int32_t* __restrict__ nvalid,
                     long long n_pts, long long sp, long long st, int n_time, const double* __restrict__ xn,
                     double f, int degree, const double* __restrict__ wtab, int w_rows, const double* __restrict__ wsh,
-                    const double* __restrict__ etab, const double* __restrict__ esum, double* __restrict__ trend) {
+                    const double* __restrict__ etab, const double* __restrict__ esum, const double* __restrict__ delta,
+                    double* __restrict__ trend) {
   constexpr int RO = 8;
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5, rows_per_cta = blockDim.x >> 5;
   const long long pt = (long long)blockIdx.x * 32 + lane;
@@ -1367,7 +1370,8 @@ loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, co
   // (lanes past n_pts / empty columns have left: vote among the remaining ones)
   const bool warp_complete = wsh != nullptr && __all_sync(__activemask(), n == n_time);
   for (int i0 = (blockIdx.y * rows_per_cta + row) * RO; i0 < n; i0 += gridDim.y * rows_per_cta * RO) {
-    const bool fast = degree == 0 && gm.interior(i0, n) && gm.interior(i0 + RO - 1, n);
+    // robustness iterations (delta != null, niter > 1) take the plain per-output path: every weight is then di * wi
+    const bool fast = !delta && degree == 0 && gm.interior(i0, n) && gm.interior(i0 + RO - 1, n);
     if (fast) {
       // output i0+r sums w[k] * y[i0 + r - HW + k], k = 0..2HW.  With j = i0 - HW + m the pair (m, r) uses w[m - r].
       // Blocks of RO taps: the loads of block b+1 are issued before block b is consumed (the loop is otherwise a
@@ -1407,7 +1411,7 @@ loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, co
 #pragma unroll
       for (int r = 0; r < RO; ++r)
         trend[pt * sp + (long long)tcp[(long long)(i0 + r) * n_pts] * st] = swy[r] / sw_total;
-    } else if (degree == 0 && n >= gm.R && i0 + RO <= n &&
+    } else if (!delta && degree == 0 && n >= gm.R && i0 + RO <= n &&
                ((i0 + RO - 1 <= gm.HW) || (i0 >= n - gm.HW))) {
       // edge chunk: all RO outputs share the window [0, R) (left) or [n-R, n) (right) and recompute their weights
       // (loess.py:138-147): every y_j / x_j is loaded once and feeds RO (weight, sum) pairs.
@@ -1458,7 +1462,7 @@ loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, co
     } else {
       for (int r = 0; r < RO && i0 + r < n; ++r)
         trend[pt * sp + (long long)tcp[(long long)(i0 + r) * n_pts] * st] =
-            loess_one<T>(y, tcp, n_pts, n, i0 + r, gm, xn, dx, degree);
+            loess_one<T>(y, tcp, n_pts, n, i0 + r, gm, xn, dx, degree, delta ? delta + pt : nullptr);
     }
   }
 }
@@ -2339,11 +2343,45 @@ int launch_dqm_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const
   return cuda_status(cudaGetLastError());
 }
 
+// K6d: robustness weights between two LOESS iterations (loess.py:166-176): residuals of the compacted series,
+// s = median(|residuals|) (mean of the two middle values for an even count), xres = residuals / (6 s) -- or the
+// indicator of a non-zero residual when s == 0 -- delta = (1 - xres^2)^2, 0 where |xres| >= 1.
+// One CTA per point; |residuals| are sorted in shared memory (n_pad doubles).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+loess_delta_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, const int32_t* __restrict__ nvalid,
+                   long long n_pts, long long sp, long long st, int n_pad, const double* __restrict__ trend,
+                   double* __restrict__ delta) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* a = reinterpret_cast<double*>(smem_raw);
+  const long long pt = blockIdx.x;
+  const int n = nvalid[pt];
+  if (n == 0) return;
+  const double dinf = __longlong_as_double(0x7ff0000000000000LL);
+  for (int j = threadIdx.x; j < n_pad; j += blockDim.x) {
+    double v = dinf;
+    if (j < n) {
+      v = fabs((double)yc[(long long)j * n_pts + pt] - trend[pt * sp + (long long)tc[(long long)j * n_pts + pt] * st]);
+      if (v != v) v = dinf;
+    }
+    a[j] = v;
+  }
+  __syncthreads();
+  sort_columns<double, 1>(a, n_pad);
+  const double s = (n & 1) ? a[n >> 1] : (a[(n >> 1) - 1] + a[n >> 1]) / 2.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const double res = (double)yc[(long long)j * n_pts + pt] - trend[pt * sp + (long long)tc[(long long)j * n_pts + pt] * st];
+    const double xres = s == 0.0 ? (res != 0.0 ? 1.0 : 0.0) : res / (6.0 * s);
+    const double c = 1.0 - xres * xres;
+    delta[(long long)j * n_pts + pt] = fabs(xres) >= 1.0 ? 0.0 : c * c;
+  }
+}
+
 template <typename T>
 int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* scaling,
                        int kind, double f, int niter, int degree, const double* xn, double* trend, void* stream) {
   if ((n_pts > 0 && !x) || !grp || (n_pts > 0 && !xn) || (n_pts > 0 && !trend) || n_pts < 0 || !(f > 0.0) || degree < 0 || degree > 1) return XSDBA_ERR_INVALID_ARGUMENT;
-  if (niter != 1) return XSDBA_ERR_UNSUPPORTED;  // robustness iterations (median of residuals) not built yet
+  if (niter < 1) return XSDBA_ERR_INVALID_ARGUMENT;
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
   if (n_pts == 0) return XSDBA_OK;
   cudaStream_t s = (cudaStream_t)stream;
@@ -2396,13 +2434,35 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
     }
   }
   const unsigned chunks = (unsigned)std::min<int64_t>(std::max<int64_t>(1, (n_time + 63) / 64), 1024);
-  loess_smooth_kernel<T><<<dim3((unsigned)((n_pts + 31) / 32), chunks), kThreads, 0, s>>>(yc, tc, nv, n_pts, sp, st, n_time,
-                                                                                          xn, f, degree, wtab, w_rows, wsh,
-                                                                                          etab, esum, trend);
-  g_launches += 3;
+  double* delta = nullptr;
+  int rc_iter = XSDBA_OK;
+  if (niter > 1) {
+    const int n_pad = std::max(2, next_pow2(n_time));
+    auto dk = loess_delta_kernel<T>;
+    if ((size_t)n_pad * sizeof(double) > 200 * 1024) rc_iter = XSDBA_ERR_SEGMENT_TOO_LONG;
+    else if (cudaMallocAsync(&delta, sizeof(double) * n_pts * n_time, s) != cudaSuccess) {
+      cudaGetLastError();
+      delta = nullptr;
+      rc_iter = XSDBA_ERR_OUT_OF_MEMORY;
+    } else rc_iter = set_smem(dk, (size_t)n_pad * sizeof(double));
+  }
+  for (int it = 0; it < niter && rc_iter == XSDBA_OK; ++it) {
+    loess_smooth_kernel<T><<<dim3((unsigned)((n_pts + 31) / 32), chunks), kThreads, 0, s>>>(
+        yc, tc, nv, n_pts, sp, st, n_time, xn, f, degree, wtab, w_rows, wsh, etab, esum, it > 0 ? delta : nullptr, trend);
+    ++g_launches;
+    if (it + 1 < niter) {
+      const int n_pad = std::max(2, next_pow2(n_time));
+      loess_delta_kernel<T><<<(unsigned)n_pts, kThreads, (size_t)n_pad * sizeof(double), s>>>(yc, tc, nv, n_pts, sp, st, n_pad,
+                                                                                              trend, delta);
+      ++g_launches;
+    }
+  }
+  g_launches += 2;
+  if (delta) cudaFreeAsync(delta, s);
   cudaFreeAsync(yc, s); cudaFreeAsync(tc, s); cudaFreeAsync(nv, s); cudaFreeAsync(wtab, s);
   if (etab) cudaFreeAsync(etab, s);
   if (wsh) cudaFreeAsync(wsh, s);
+  if (rc_iter != XSDBA_OK) return rc_iter;
   return cuda_status(cudaGetLastError());
 }
 
