@@ -1355,10 +1355,12 @@ loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, co
                     long long n_pts, long long sp, long long st, int n_time, const double* __restrict__ xn,
                     double f, int degree, const double* __restrict__ wtab, int w_rows, const double* __restrict__ wsh,
                     const double* __restrict__ etab, const double* __restrict__ esum, const double* __restrict__ delta,
-                    double* __restrict__ trend) {
+                    int tiled, double* __restrict__ trend) {
   constexpr int RO = 8;
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5, rows_per_cta = blockDim.x >> 5;
   const long long pt = (long long)blockIdx.x * 32 + lane;
+  // a tile of 32 complete series has its interior outputs computed by K6t (loess_interior_tile_kernel): same vote there
+  const bool tile_done = __all_sync(0xffffffffu, pt < n_pts && nvalid[pt < n_pts ? pt : 0] == n_time) && tiled;
   if (pt >= n_pts) return;
   const int n = nvalid[pt];
   if (n == 0) return;
@@ -1372,6 +1374,7 @@ loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, co
   for (int i0 = (blockIdx.y * rows_per_cta + row) * RO; i0 < n; i0 += gridDim.y * rows_per_cta * RO) {
     // robustness iterations (delta != null, niter > 1) take the plain per-output path: every weight is then di * wi
     const bool fast = !delta && degree == 0 && gm.interior(i0, n) && gm.interior(i0 + RO - 1, n);
+    if (fast && tile_done) continue;
     if (fast) {
       // output i0+r sums w[k] * y[i0 + r - HW + k], k = 0..2HW.  With j = i0 - HW + m the pair (m, r) uses w[m - r].
       // Blocks of RO taps: the loads of block b+1 are issued before block b is consumed (the loop is otherwise a
@@ -2010,6 +2013,21 @@ template <typename K> int set_smem(K kernel, size_t bytes) {
   return XSDBA_OK;
 }
 
+// Scratch buffers come from the device's stream-ordered pool (cudaMallocAsync).  Its default release threshold of 0
+// hands the memory back to the driver at every synchronisation, which costs milliseconds per call (tens for the
+// gigabyte-sized LOESS scratch): keep it.  Called by every launcher that allocates scratch.
+void keep_pool_memory() {
+  static std::atomic<int> pool_ready{0};
+  if (pool_ready.exchange(1)) return;
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaGetLastError();
+}
+
 template <typename T, int C>
 int launch_train_c(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
                    const T* q, int nq, int kind, int normalize, int mode, T* af, T* hq, T* scaling, int n_pad,
@@ -2102,19 +2120,7 @@ bool launch_adjust_tile_t(const float* sim, int64_t n_pts, int64_t sp, int64_t s
   if (smem_t > 220 * 1024 || smem_p > 220 * 1024 || st < 0 || st > INT32_MAX / 4) return false;
   const int64_t tiles = (n_pts + 31) / 32;
   Slot* packed = nullptr;
-  {
-    // keep the stream-ordered pool's memory across calls (default threshold 0 returns it to the driver at
-    // every synchronisation, which costs milliseconds per call)
-    static std::atomic<int> pool_ready{0};
-    if (!pool_ready.exchange(1)) {
-      int dev = 0;
-      cudaMemPool_t pool;
-      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-      }
-    }
-  }
+  keep_pool_memory();
   if (cudaMallocAsync(&packed, (size_t)tiles * grp->n_groups * sizeof(Slot), s) != cudaSuccess) {
     cudaGetLastError();
     return false;  // not enough memory for the packed image: the caller falls back to the staging kernel
@@ -2343,6 +2349,69 @@ int launch_dqm_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const
   return cuda_status(cudaGetLastError());
 }
 
+// K6t: interior outputs (degree 0, first iteration) of a tile of 32 COMPLETE series.  K6b lets every warp stream its own
+// 2 HW + 1 taps from L2; here a CTA of 8 warps x 16 outputs = 128 consecutive outputs shares them: the union of the
+// windows goes through shared memory in tiles of 128 taps (loaded once per CTA, coalesced), the weights -- one vector
+// for all complete series -- sit in shared memory and are read as broadcasts, and each thread (lane = point) keeps 16
+// accumulators and a 16-slot weight ring in registers: 16 DFMA per tap and thread against 2 shared-memory loads.
+// Same summation order as K6b (taps ascending), same denominator (total weight in tap order).
+constexpr int kLoessTileOut = 16;    // outputs per warp
+constexpr int kLoessTileTaps = 128;  // taps per shared-memory tile
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+loess_interior_tile_kernel(const T* __restrict__ yc, const int32_t* __restrict__ nvalid, long long n_pts, long long sp,
+                           long long st, int n_time, double f, const double* __restrict__ wsh, int w_rows,
+                           double* __restrict__ trend) {
+  constexpr int RO = kLoessTileOut, TT = kLoessTileTaps;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* wsm = reinterpret_cast<double*>(smem_raw);                  // [w_rows + RO] (zero beyond the last weight)
+  T* ytile = reinterpret_cast<T*>(wsm + w_rows + RO);                 // [TT][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const long long pt = (long long)blockIdx.x * 32 + lane;
+  if (!__all_sync(0xffffffffu, pt < n_pts && nvalid[pt < n_pts ? pt : 0] == n_time)) return;  // K6b does this tile
+  const int n = n_time;
+  const LoessGeom gm(n, f);
+  const int K = 2 * gm.HW;
+  const int first = gm.HW + 1, last = n - gm.HW - 2;   // interior outputs (LoessGeom::interior)
+  const int o_base = first + blockIdx.y * (n_warps * RO);
+  if (o_base > last) return;
+  for (int k = threadIdx.x; k < w_rows + RO; k += blockDim.x) wsm[k] = k <= K && k < w_rows ? wsh[k] : 0.0;
+  const double sw_total = wsh[w_rows];
+  const int i0 = o_base + warp * RO;                   // this warp's outputs i0 .. i0 + RO - 1
+  const int jb = o_base - gm.HW;                       // first tap of the CTA's window union
+  const int je = min(o_base + n_warps * RO - 1, last) + gm.HW;
+  const T* y = yc + pt;
+  double swy[RO], wr[RO];
+#pragma unroll
+  for (int r = 0; r < RO; ++r) { swy[r] = 0; wr[r] = 0; }
+  for (int t0 = jb; t0 <= je; t0 += TT) {
+    __syncthreads();  // the previous tile has been consumed (and wsm is complete before the first use)
+    for (int tt = warp; tt < TT; tt += n_warps) ytile[tt * 32 + lane] = y[(long long)min(t0 + tt, n - 1) * n_pts];
+    __syncthreads();
+    // weight index of the tile's first tap for output i0: a multiple of RO by construction
+    const int m0 = t0 - (i0 - gm.HW);
+#pragma unroll 1
+    for (int b = 0; b < TT; b += RO) {
+      const int m = m0 + b;
+      if (m < 0 || m > K + RO - 1) continue;           // (warp-uniform) outside this warp's windows
+#pragma unroll
+      for (int u = 0; u < RO; ++u) {
+        wr[u] = wsm[min(m + u, w_rows + RO - 1)];
+        const double yj = (double)ytile[(b + u) * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < RO; ++r) swy[r] = fma(wr[(u - r + RO) % RO], yj, swy[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RO; ++r)
+  {
+    // only the outputs K6b skips: those of its 8-output chunks that lie entirely in the interior
+    const int i = i0 + r, c0 = i & ~7;
+    if (i <= last && gm.interior(c0, n) && gm.interior(c0 + 7, n)) trend[pt * sp + (long long)i * st] = swy[r] / sw_total;
+  }
+}
+
 // K6d: robustness weights between two LOESS iterations (loess.py:166-176): residuals of the compacted series,
 // s = median(|residuals|) (mean of the two middle values for an even count), xres = residuals / (6 s) -- or the
 // indicator of a non-zero residual when s == 0 -- delta = (1 - xres^2)^2, 0 where |xres| >= 1.
@@ -2384,6 +2453,7 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
   if (niter < 1) return XSDBA_ERR_INVALID_ARGUMENT;
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
   if (n_pts == 0) return XSDBA_OK;
+  keep_pool_memory();
   cudaStream_t s = (cudaStream_t)stream;
   const int n_time = (int)grp->n_time;
   T* yc = nullptr; int32_t* tc = nullptr; int32_t* nv = nullptr;
@@ -2446,9 +2516,23 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
       rc_iter = XSDBA_ERR_OUT_OF_MEMORY;
     } else rc_iter = set_smem(dk, (size_t)n_pad * sizeof(double));
   }
+  // K6t for the interior of complete tiles (first iteration, degree 0); K6b does everything else
+  int tiled = 0;
+  const size_t smem_t = sizeof(double) * (w_rows + kLoessTileOut) + sizeof(T) * kLoessTileTaps * 32;
+  if (degree == 0 && wsh && smem_t <= 200 * 1024 && set_smem(loess_interior_tile_kernel<T>, smem_t) == XSDBA_OK &&
+      !getenv("XSDBA_B200_NO_LOESS_TILE"))
+    tiled = 1;
   for (int it = 0; it < niter && rc_iter == XSDBA_OK; ++it) {
+    const int tiled_now = (it == 0) ? tiled : 0;
+    if (tiled_now) {
+      const int per_cta = (kThreads / 32) * kLoessTileOut;
+      loess_interior_tile_kernel<T><<<dim3((unsigned)((n_pts + 31) / 32), (unsigned)((n_time + per_cta - 1) / per_cta)),
+                                      kThreads, smem_t, s>>>(yc, nv, n_pts, sp, st, n_time, f, wsh, w_rows, trend);
+      ++g_launches;
+    }
     loess_smooth_kernel<T><<<dim3((unsigned)((n_pts + 31) / 32), chunks), kThreads, 0, s>>>(
-        yc, tc, nv, n_pts, sp, st, n_time, xn, f, degree, wtab, w_rows, wsh, etab, esum, it > 0 ? delta : nullptr, trend);
+        yc, tc, nv, n_pts, sp, st, n_time, xn, f, degree, wtab, w_rows, wsh, etab, esum, it > 0 ? delta : nullptr,
+        tiled_now, trend);
     ++g_launches;
     if (it + 1 < niter) {
       const int n_pad = std::max(2, next_pow2(n_time));
