@@ -1361,6 +1361,7 @@ loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, co
   const long long pt = (long long)blockIdx.x * 32 + lane;
   // a tile of 32 complete series has its interior outputs computed by K6t (loess_interior_tile_kernel): same vote there
   const bool tile_done = __all_sync(0xffffffffu, pt < n_pts && nvalid[pt < n_pts ? pt : 0] == n_time) && tiled;
+  if (tile_done) return;  // K6t + K6u cover every output of a complete tile
   if (pt >= n_pts) return;
   const int n = nvalid[pt];
   if (n == 0) return;
@@ -1374,7 +1375,6 @@ loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, co
   for (int i0 = (blockIdx.y * rows_per_cta + row) * RO; i0 < n; i0 += gridDim.y * rows_per_cta * RO) {
     // robustness iterations (delta != null, niter > 1) take the plain per-output path: every weight is then di * wi
     const bool fast = !delta && degree == 0 && gm.interior(i0, n) && gm.interior(i0 + RO - 1, n);
-    if (fast && tile_done) continue;
     if (fast) {
       // output i0+r sums w[k] * y[i0 + r - HW + k], k = 0..2HW.  With j = i0 - HW + m the pair (m, r) uses w[m - r].
       // Blocks of RO taps: the loads of block b+1 are issued before block b is consumed (the loop is otherwise a
@@ -2372,7 +2372,9 @@ loess_interior_tile_kernel(const T* __restrict__ yc, const int32_t* __restrict__
   const int n = n_time;
   const LoessGeom gm(n, f);
   const int K = 2 * gm.HW;
-  const int first = gm.HW + 1, last = n - gm.HW - 2;   // interior outputs (LoessGeom::interior)
+  // interior outputs (LoessGeom::interior) plus i = n-HW-1, which keeps the interior weights on the window
+  // [n-R, n) = [i-HW, i+HW] (loess.py:128-150: right-hand window, weights not recomputed)
+  const int first = gm.HW + 1, last = n - gm.HW - 1;
   const int o_base = first + blockIdx.y * (n_warps * RO);
   if (o_base > last) return;
   for (int k = threadIdx.x; k < w_rows + RO; k += blockDim.x) wsm[k] = k <= K && k < w_rows ? wsh[k] : 0.0;
@@ -2405,10 +2407,55 @@ loess_interior_tile_kernel(const T* __restrict__ yc, const int32_t* __restrict__
   }
 #pragma unroll
   for (int r = 0; r < RO; ++r)
-  {
-    // only the outputs K6b skips: those of its 8-output chunks that lie entirely in the interior
-    const int i = i0 + r, c0 = i & ~7;
-    if (i <= last && gm.interior(c0, n) && gm.interior(c0 + 7, n)) trend[pt * sp + (long long)i * st] = swy[r] / sw_total;
+    if (i0 + r <= last) trend[pt * sp + (long long)(i0 + r) * st] = swy[r] / sw_total;
+}
+
+// K6u: edge outputs (degree 0, first iteration) of a tile of 32 COMPLETE series.  The HW+1 left (HW right) outputs share
+// the window [0, R) ([n-R, n)); their weights come from the (tap, output) table of K6e.  Same structure as K6t: 8 warps
+// x 16 outputs per CTA, the window staged through shared memory in 128-tap tiles, 16 accumulators per thread; the 16
+// weights of a tap are warp-uniform loads of 128 contiguous bytes of the L2-resident table.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+loess_edge_tile_kernel(const T* __restrict__ yc, const int32_t* __restrict__ nvalid, long long n_pts, long long sp,
+                       long long st, int n_time, double f, const double* __restrict__ etab,
+                       const double* __restrict__ esum, int chunks_per_side, double* __restrict__ trend) {
+  constexpr int RO = kLoessTileOut, TT = kLoessTileTaps;
+  __shared__ T ytile[TT * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const long long pt = (long long)blockIdx.x * 32 + lane;
+  if (!__all_sync(0xffffffffu, pt < n_pts && nvalid[pt < n_pts ? pt : 0] == n_time)) return;  // K6b does this tile
+  const int n = n_time;
+  const LoessGeom gm(n, f);
+  const int NI = 2 * gm.HW + 1;
+  const int side = blockIdx.y / chunks_per_side, chunk = blockIdx.y % chunks_per_side;
+  const int n_edge = side == 0 ? gm.HW + 1 : gm.HW;          // outputs on this side
+  const int e_base = side == 0 ? 0 : gm.HW + 1;              // their first table column
+  const int i_base = side == 0 ? 0 : n - gm.HW;              // their first output index
+  const int lo = side == 0 ? 0 : n - gm.R;                   // the shared window
+  const int o0 = chunk * (n_warps * RO) + warp * RO;         // this warp's first output on the side
+  if (chunk * (n_warps * RO) >= n_edge) return;
+  const double* et = etab + e_base + min(o0, n_edge - 1);    // (warps past the end compute garbage they never write)
+  const int span = min(RO, max(n_edge - o0, 1));             // table columns this warp may read
+  const T* y = yc + pt + (long long)lo * n_pts;
+  double swy[RO];
+#pragma unroll
+  for (int r = 0; r < RO; ++r) swy[r] = 0;
+  for (int t0 = 0; t0 < gm.R; t0 += TT) {
+    __syncthreads();
+    for (int tt = warp; tt < TT; tt += n_warps) ytile[tt * 32 + lane] = y[(long long)min(t0 + tt, gm.R - 1) * n_pts];
+    __syncthreads();
+    const int nt = min(TT, gm.R - t0);
+    for (int tt = 0; tt < nt; ++tt) {
+      const double* row = et + (long long)(t0 + tt) * NI;
+      const double yj = (double)ytile[tt * 32 + lane];
+#pragma unroll
+      for (int r = 0; r < RO; ++r) swy[r] = fma(row[r < span ? r : 0], yj, swy[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RO; ++r) {
+    const int o = o0 + r;
+    if (o < n_edge) trend[pt * sp + (long long)(i_base + o) * st] = swy[r] / esum[e_base + o];
   }
 }
 
@@ -2519,7 +2566,7 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
   // K6t for the interior of complete tiles (first iteration, degree 0); K6b does everything else
   int tiled = 0;
   const size_t smem_t = sizeof(double) * (w_rows + kLoessTileOut) + sizeof(T) * kLoessTileTaps * 32;
-  if (degree == 0 && wsh && smem_t <= 200 * 1024 && set_smem(loess_interior_tile_kernel<T>, smem_t) == XSDBA_OK &&
+  if (degree == 0 && wsh && etab && smem_t <= 200 * 1024 && set_smem(loess_interior_tile_kernel<T>, smem_t) == XSDBA_OK &&
       !getenv("XSDBA_B200_NO_LOESS_TILE"))
     tiled = 1;
   for (int it = 0; it < niter && rc_iter == XSDBA_OK; ++it) {
@@ -2529,6 +2576,14 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
       loess_interior_tile_kernel<T><<<dim3((unsigned)((n_pts + 31) / 32), (unsigned)((n_time + per_cta - 1) / per_cta)),
                                       kThreads, smem_t, s>>>(yc, nv, n_pts, sp, st, n_time, f, wsh, w_rows, trend);
       ++g_launches;
+      {
+        const int r_ = (int)(2.0 * std::floor(f * (double)n_time / 2.0) + 1.0);
+        const int HW_ = (r_ - 1) / 2 + 2;
+        const int cps = (HW_ + 1 + per_cta - 1) / per_cta;
+        loess_edge_tile_kernel<T><<<dim3((unsigned)((n_pts + 31) / 32), (unsigned)(2 * cps)), kThreads, 0, s>>>(
+            yc, nv, n_pts, sp, st, n_time, f, etab, esum, cps, trend);
+        ++g_launches;
+      }
     }
     loess_smooth_kernel<T><<<dim3((unsigned)((n_pts + 31) / 32), chunks), kThreads, 0, s>>>(
         yc, tc, nv, n_pts, sp, st, n_time, xn, f, degree, wtab, w_rows, wsh, etab, esum, it > 0 ? delta : nullptr,
