@@ -21,6 +21,10 @@ namespace {
 std::atomic<long long> g_launches{0};
 
 constexpr int kThreads = 256;
+// Narrow tiles (C <= 4 columns: one CTA per SM because the segment fills the shared memory) run with twice the
+// threads so that the SM still has 16 warps to hide latencies with.
+template <int C>
+constexpr int threads_for_cols() { return C <= 4 ? 512 : kThreads; }
 constexpr int kSortBytes = 128 * 1024;  // shared-memory budget of the column sorter
 
 struct DevTable {
@@ -157,7 +161,7 @@ __device__ double numba_nanquantile_sorted(const T* col, int n, double q) {
 }
 
 template <typename T, int C>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(threads_for_cols<C>())
 train_kernel(const T* __restrict__ ref, const T* __restrict__ hist, long long n_pts, long long sp, long long st,
              const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
              const T* __restrict__ q, int nq, int kind, int normalize, int mode, T* __restrict__ af,
@@ -1478,7 +1482,7 @@ loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, co
 // With do_adjust: af lookup on the shared quantile axis and scen = sim (+|*) af (_adjustment.py:873-881).
 // =============================================================================================
 template <typename T, int C>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(threads_for_cols<C>())
 rank_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long st,
             const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows,
             const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
@@ -2037,8 +2041,9 @@ int launch_train_c(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64
   int rc = set_smem(kern, smem);
   if (rc) return rc;
   dim3 grid((unsigned)((n_pts + C - 1) / C), (unsigned)grp->n_groups);
-  kern<<<grid, kThreads, smem, s>>>(ref, hist, n_pts, sp, st, grp->segments.off, grp->segments.rows, grp->n_groups, q,
-                                    nq, kind, normalize, mode, af, hq, scaling, n_pad, jp, use_jitter, q64, ap);
+  kern<<<grid, threads_for_cols<C>(), smem, s>>>(ref, hist, n_pts, sp, st, grp->segments.off, grp->segments.rows,
+                                                 grp->n_groups, q, nq, kind, normalize, mode, af, hq, scaling, n_pad, jp,
+                                                 use_jitter, q64, ap);
   ++g_launches;
   return cuda_status(cudaGetLastError());
 }
@@ -2261,9 +2266,9 @@ int launch_rank_c(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsd
   int rc = set_smem(kern, smem);
   if (rc) return rc;
   dim3 grid((unsigned)((n_pts + C - 1) / C), (unsigned)grp->n_groups);
-  kern<<<grid, kThreads, smem, s>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows, seg.off, seg.rows,
-                                    grp->n_groups, af, q, do_adjust ? nq : 0, interp, extrap, kind, do_adjust, scen,
-                                    sim_q, n_pad, rank_mode, gcoord, diag, slots);
+  kern<<<grid, threads_for_cols<C>(), smem, s>>>(sim, n_pts, sp, st, grp->members.off, grp->members.rows, seg.off,
+                                                 seg.rows, grp->n_groups, af, q, do_adjust ? nq : 0, interp, extrap, kind,
+                                                 do_adjust, scen, sim_q, n_pad, rank_mode, gcoord, diag, slots);
   ++g_launches;
   return cuda_status(cudaGetLastError());
 }
