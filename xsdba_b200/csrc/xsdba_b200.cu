@@ -872,6 +872,75 @@ __global__ void adjust_fix_kernel(const FixEntry* __restrict__ fix, const unsign
   }
 }
 
+// The same second pass on the PACKED tables (K2p's output, still alive): every row there is compacted (NaN nodes
+// dropped), ascending and +inf padded, so the nearest node of a row is one of the two neighbours of a binary search
+// instead of a scan of all nq nodes -- about 20 scattered 32-byte sectors per sample instead of 56, and a tenth of the
+// instructions.  Tie rule of the scan kept: the first (lowest-index) node among equally near ones, i.e. the left
+// neighbour on a distance tie and the first element of a run of duplicated nodes.
+template <int LD>
+__device__ __forceinline__ void nearest_in_sorted_row(const float* __restrict__ xs, const float* __restrict__ ys, int n,
+                                                      double xd, double dg2, double& best_d2, float& best_y) {
+  if (n <= 0) return;
+  const float xf = (float)xd;  // (x is a float32 sample: exact)
+  int lo = 0, hi = n;          // lower bound: first node >= x
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (xs[mid * 32] < xf) lo = mid + 1; else hi = mid; }
+  const int i = lo;
+  double d = __longlong_as_double(0x7ff0000000000000LL);
+  int idx = -1;
+  if (i > 0) {
+    const float xl = xs[(i - 1) * 32];
+    d = fabs(xd - (double)xl);
+    idx = i - 1;
+    if (i > 1 && xs[(i - 2) * 32] == xl) {  // duplicated node: the scan keeps its first occurrence
+      int a = 0, b = i - 1;
+      while (a < b) { const int mid = (a + b) >> 1; if (xs[mid * 32] < xl) a = mid + 1; else b = mid; }
+      idx = a;
+    }
+  }
+  if (i < n) {
+    const double dr = fabs((double)xs[i * 32] - xd);
+    if (idx < 0 || dr < d) { d = dr; idx = i; }
+  }
+  const double d2 = __dadd_rn(__dmul_rn(d, d), dg2);
+  if (d2 < best_d2) { best_d2 = d2; best_y = ys[idx * 32]; }
+}
+
+template <int TOP>
+__global__ void adjust_fix_packed_kernel(const FixEntry* __restrict__ fix, const unsigned* __restrict__ count, unsigned cap,
+                                         const PackedSlot<2 * TOP>* __restrict__ packed, int G, int extrap, int kind,
+                                         float* __restrict__ scen) {
+  constexpr int LD = 2 * TOP;
+  const unsigned n_fix = min(*count, cap);
+  for (unsigned e_i = blockIdx.x * blockDim.x + threadIdx.x; e_i < n_fix; e_i += gridDim.x * blockDim.x) {
+    const FixEntry e = fix[e_i];
+    const int lane = (int)(e.pt & 31);
+    const PackedSlot<LD>* tile = packed + (size_t)(e.pt >> 5) * G;
+    const PackedSlot<LD>& c = tile[e.g];
+    const double xd = (double)e.x;
+    const float fnan = Num<float>::nan();
+    float f;
+    if (e.x != e.x) f = fnan;
+    else if (xd < (double)c.blo[lane]) f = extrap == 0 ? c.clo[lane] : fnan;
+    else if (xd > (double)c.bhi[lane]) f = extrap == 0 ? c.chi[lane] : fnan;
+    else {
+      double best_d2 = __longlong_as_double(0x7ff0000000000000LL);
+      f = fnan;
+      for (int dist = 0; dist <= G + 1; ++dist) {
+        const double dg2 = (double)dist * (double)dist;
+        if (dg2 >= best_d2) break;
+        for (int sgn = -1; sgn <= 1; sgn += 2) {
+          if (dist == 0 && sgn > 0) break;
+          const int pr = e.g + 1 + sgn * dist;  // padded row index in [0, G+1]
+          if (pr < 0 || pr > G + 1) continue;
+          const PackedSlot<LD>& r = tile[(pr - 1 + G) % G];
+          nearest_in_sorted_row<LD>(r.xs + lane, r.ys + lane, r.nv[lane], xd, dg2, best_d2, f);
+        }
+      }
+    }
+    scen[e.off] = kind == XSDBA_KIND_ADD ? __fadd_rn(e.x, f) : __fmul_rn(e.x, f);
+  }
+}
+
 // shared-memory load by 32-bit shared address (keeps the search pointer a plain 32-bit register: LDS [R + imm])
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
@@ -2153,7 +2222,9 @@ bool launch_adjust_tile_t(const float* sim, int64_t n_pts, int64_t sp, int64_t s
   adjust_tile_kernel<TOP><<<(unsigned)tiles, kThreads, smem_t, s>>>(sim, n_pts, sp, (int)st, grp->members.off,
                                                                     grp->members.rows, grp->n_groups, af, hq, nq, packed,
                                                                     extrap, kind, scen, fix, fix_count, fix_cap);
-  adjust_fix_kernel<<<148 * 4, 256, 0, s>>>(fix, fix_count, fix_cap, af, hq, grp->n_groups, nq, extrap, kind, scen);
+  static const bool fix_scan = getenv("XSDBA_B200_FIX_SCAN") != nullptr;  // (debug: the table-scanning second pass)
+  if (fix_scan) adjust_fix_kernel<<<148 * 4, 256, 0, s>>>(fix, fix_count, fix_cap, af, hq, grp->n_groups, nq, extrap, kind, scen);
+  else adjust_fix_packed_kernel<TOP><<<148 * 6, 256, 0, s>>>(fix, fix_count, fix_cap, packed, grp->n_groups, extrap, kind, scen);
   {
     const size_t smem_g = ((tables_bytes<float, 32>(nq) + 15) & ~(size_t)15) + stage_bytes<float, 32>(nq);
     auto kern = adjust_kernel<float, 32>;
