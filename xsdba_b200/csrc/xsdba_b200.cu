@@ -948,6 +948,7 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   return v;
 }
 
+constexpr int kFixStage = 192;     // deferred samples staged per CTA between two flushes (K2t)
 constexpr int kTileMaxRows = 1024;  // member rows of one group kept in shared memory by K2t (x2 buffers)
 
 template <int TOP>
@@ -963,6 +964,10 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
   Slot* ring = reinterpret_cast<Slot*>(smem_raw);
   int* rows_sm = reinterpret_cast<int*>(smem_raw + RING * sizeof(Slot));     // [2][kTileMaxRows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(rows_sm + 2 * kTileMaxRows);  // [RING]
+  // deferred samples are collected per CTA and appended to the global list once per group: one global atomic per
+  // flush instead of one per sample (a warp otherwise waits a global round trip for its slot number)
+  FixEntry* stage_fix = reinterpret_cast<FixEntry*>(bars + 4);               // [kFixStage]
+  unsigned* stage_n = reinterpret_cast<unsigned*>(stage_fix + kFixStage);    // [1] (+ [1] flush base)
 
   const int tile = blockIdx.x;
   const long long n0 = (long long)tile * C;
@@ -978,6 +983,7 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
   if (threadIdx.x == 0) {
     for (int i = 0; i < RING; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    stage_n[0] = 0;
   }
   __syncthreads();
   // the row of group e lives in ring slot e % RING (use number e / RING of that slot's mbarrier)
@@ -1065,8 +1071,14 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
               kind == XSDBA_KIND_ADD ? __fadd_rn(x[j], f) : __fmul_rn(x[j], f);
           if (!(sure || below || above)) {
             // float32 cannot decide (near-tie / far node / empty row): defer to the exact second pass
-            const unsigned slot = atomicAdd(fix_count, 1u);
-            if (slot < fix_cap) fix[slot] = FixEntry{(long long)(dst - scen) + (long long)ov[j] * st, pt, x[j], g};
+            const FixEntry en{(long long)(dst - scen) + (long long)ov[j] * st, pt, x[j], g};
+            const unsigned sl = atomicAdd(stage_n, 1u);
+            if (sl < kFixStage) {
+              stage_fix[sl] = en;
+            } else {  // staging list full until the next flush: straight to the global list
+              const unsigned slot = atomicAdd(fix_count, 1u);
+              if (slot < fix_cap) fix[slot] = en;
+            }
           }
         }
       }
@@ -1085,6 +1097,18 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
         if (m + stride < n_rows) load_batch(m + stride, xa, oa);
         process_batch(m, xbv, ob);
         m += stride;
+      }
+    }
+    __syncthreads();  // every sample of this group has been looked at: flush the staged deferred samples
+    {
+      const unsigned ns = min(stage_n[0], (unsigned)kFixStage);
+      if (ns > 0) {  // (CTA-uniform)
+        if (threadIdx.x == 0) stage_n[1] = atomicAdd(fix_count, ns);
+        __syncthreads();  // the base is visible, and everybody has read ns
+        const unsigned base = stage_n[1];
+        for (unsigned i = threadIdx.x; i < ns; i += blockDim.x)
+          if (base + i < fix_cap) fix[base + i] = stage_fix[i];
+        if (threadIdx.x == 0) stage_n[0] = 0;  // (the barrier at the top of the next group orders this reset)
       }
     }
     {
@@ -2189,7 +2213,8 @@ template <int TOP>
 bool launch_adjust_tile_t(const float* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
                           const float* af, const float* hq, int nq, int extrap, int kind, float* scen, cudaStream_t s) {
   typedef PackedSlot<2 * TOP> Slot;
-  const size_t smem_t = 2 * sizeof(Slot) + 2 * kTileMaxRows * sizeof(int) + 4 * sizeof(uint64_t) + 128;
+  const size_t smem_t = 2 * sizeof(Slot) + 2 * kTileMaxRows * sizeof(int) + 4 * sizeof(uint64_t) +
+                        kFixStage * sizeof(FixEntry) + 2 * sizeof(unsigned) + 128;
   const size_t smem_p = sizeof(Slot) + stage_bytes<float, 32>(nq);
   if (smem_t > 220 * 1024 || smem_p > 220 * 1024 || st < 0 || st > INT32_MAX / 4) return false;
   const int64_t tiles = (n_pts + 31) / 32;
