@@ -403,10 +403,19 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
       if (t >= 0) v[i] = *reinterpret_cast<const float*>(pa);
     }
     if (JITTER && use_jitter && pass == 1) {  // hist only, per window slot (_adjustment.py:58-67)
+      // The hash needs ~20 registers per value; unrolled over the 32 values of a thread it spilled 400-1000 bytes.
+      // The values take a round trip through the thread's own slots of the (free) sort buffer instead and are
+      // jittered one at a time in a rolled loop.
       const long long seg_base = seg_off[g];
+      float* own = buf + ((size_t)half * 512 + (warp >> 1)) * 32 + lane;
 #pragma unroll
+      for (int i = 0; i < 32; ++i) own[(size_t)i * 16 * 32] = v[i];
+#pragma unroll 1
       for (int i = 0; i < 32; ++i)
-        v[i] = jitter_value<float>(v[i], jp, (unsigned long long)((seg_base + warp + 32 * i) * n_pts + n0 + lane));
+        own[(size_t)i * 16 * 32] = jitter_value<float>(
+            own[(size_t)i * 16 * 32], jp, (unsigned long long)((seg_base + warp + 32 * i) * n_pts + n0 + lane));
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = own[(size_t)i * 16 * 32];
     }
     double my_sum = 0.0;
     if (normalize) {
