@@ -27,8 +27,10 @@ template <> struct Num<float> {
 template <> struct Num<double> {
   static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
   static __device__ __forceinline__ double nan() { return __longlong_as_double(0x7ff8000000000000LL); }
-  static __device__ __forceinline__ double mn(double a, double b) { return fmin(a, b); }
-  static __device__ __forceinline__ double mx(double a, double b) { return fmax(a, b); }
+  // sort keys are NaN-free (NaN -> +inf before sorting), so one compare + selects will do: fmin / fmax on doubles
+  // expand to ~13 instructions each (IEEE NaN handling in integer arithmetic) and were 61 % of the float64 sorter
+  static __device__ __forceinline__ double mn(double a, double b) { return b < a ? b : a; }
+  static __device__ __forceinline__ double mx(double a, double b) { return b < a ? a : b; }
   static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
   static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
   static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
@@ -224,7 +226,10 @@ __device__ __forceinline__ void warp_block_pass(T* sm, int n_pad, int L, int p) 
             const int row = (lane >> LC) + k * (32 >> LC);
             const bool desc = (FIRST && ph < 5) ? ((row >> ph) & 1) : blk_desc;
             const T o = __shfl_xor_sync(0xffffffffu, v[k], 1 << (b + LC));
-            const T lo = Num<T>::mn(v[k], o), hi = Num<T>::mx(v[k], o);
+            // both lanes evaluate the same ordered pair (lower lane's value, upper lane's value), so that values
+            // that compare equal but differ in bits (+-0) are neither duplicated nor lost
+            const T p = upper ? o : v[k], q = upper ? v[k] : o;
+            const T lo = Num<T>::mn(p, q), hi = Num<T>::mx(p, q);
             v[k] = (upper == desc) ? lo : hi;
           }
         } else {
