@@ -60,16 +60,35 @@ __device__ void load_segment(T* sm, const T* __restrict__ src, long long n0, lon
                              long long st, const int32_t* __restrict__ rows, int S, int n_pad,
                              const JitterParams* jp = nullptr, long long seg_base = 0) {
   const int total = n_pad * C;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int r = idx / C;
-    const int c = idx % C;
-    T v = Num<T>::nan();
-    if (r < S && n0 + c < n_pts) {
-      const int t = rows[r];
-      if (t >= 0) v = src[(n0 + c) * sp + (long long)t * st];
-      if (jp) v = jitter_value<T>(v, *jp, (unsigned long long)((seg_base + r) * n_pts + n0 + c));
+  // batches of UL elements per thread: first the row numbers, then the samples, so that UL independent loads are
+  // in flight (one element at a time is a chain of two dependent global loads per iteration)
+  constexpr int UL = 8;
+  for (int base = threadIdx.x; base < total; base += blockDim.x * UL) {
+    int t[UL];
+#pragma unroll
+    for (int u = 0; u < UL; ++u) {
+      const int idx = base + u * blockDim.x;
+      const int r = idx / C, c = idx % C;
+      t[u] = (idx < total && r < S && n0 + c < n_pts) ? rows[r] : -1;
     }
-    sm[idx] = v;
+    T v[UL];
+#pragma unroll
+    for (int u = 0; u < UL; ++u) {
+      const int idx = base + u * blockDim.x;
+      const int r = idx / C, c = idx % C;
+      v[u] = t[u] >= 0 ? src[(n0 + c) * sp + (long long)t[u] * st] : Num<T>::nan();
+      (void)r;
+    }
+#pragma unroll
+    for (int u = 0; u < UL; ++u) {
+      const int idx = base + u * blockDim.x;
+      if (idx >= total) continue;
+      const int r = idx / C, c = idx % C;
+      T x = v[u];
+      if (jp && r < S && n0 + c < n_pts)
+        x = jitter_value<T>(x, *jp, (unsigned long long)((seg_base + r) * n_pts + n0 + c));
+      sm[idx] = x;
+    }
   }
 }
 
