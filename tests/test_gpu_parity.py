@@ -896,3 +896,35 @@ def test_long_segments_group_time(years, dt):
                         extrapolation="constant", kind="+")
     assert bits_equal(_np(out.sim_q).T, simq_o)
     assert bits_equal(_np(out.scen).T, scen_o)
+
+
+def test_generic_train_kernel_jitter_and_signed_zeros():
+    """The generic (float64 / point-major) train kernel: jitter through its batched segment load, and signed zeros
+    through the compare + select exchanges of the float64 sorter (no value may be lost or duplicated)."""
+    xs = _xs()
+    rng = np.random.default_rng(12)
+    to = o.daily_time_axis(1981, 10, "noleap"); tx = xs.TimeAxis.daily(1981, 10, "noleap")
+    ref, hist = (synth.pr(rng, to, 6, w, jitter=False, nan_frac=0).astype(np.float64) for w in ("ref", "hist"))
+    q = o.equally_spaced_nodes(20)
+    gidx, G, _ = o.group_index(to, "time.month")
+    # 1. float64 + jitter: statistically the oracle's, exactly the oracle's above the threshold
+    ds = xs.eqm_train(xs.Dataset({"ref": ref, "hist": hist}, time=tx), group="time.month", kind="*", quantiles=q,
+                      jitter_under_thresh_value="0.01 mm/d")
+    hist_j = np.where(hist < 0.01, rng.uniform(1e-45, 0.01, hist.shape), hist)
+    _, hq_o = o.eqm_train(ref.T.copy(), hist_j.T.copy(), gidx, G, 1, q, "*")
+    hq = _np(ds.hist_q)
+    np.testing.assert_allclose(hq, hq_o, atol=2e-3, rtol=0.02)
+    wet = hq_o > 0.1    # (a node just above the threshold may still interpolate towards a jittered neighbour)
+    np.testing.assert_allclose(hq[wet], hq_o[wet], rtol=1e-12)
+    # 2. signed zeros (dry days as +0.0 and -0.0 mixed): same quantiles as the oracle, zeros counted once each
+    z = hist.copy()
+    z[(z < 0.01) & (rng.random(z.shape) < 0.5)] = -0.0
+    z[(z < 0.01) & (z != 0)] = 0.0
+    ds = xs.eqm_train(xs.Dataset({"ref": ref, "hist": z}, time=tx), group="time.month", kind="+", quantiles=q)
+    _, hq_o = o.eqm_train(ref.T.copy(), z.T.copy(), gidx, G, 1, q, "+")
+    np.testing.assert_allclose(_np(ds.hist_q), hq_o, rtol=1e-12, atol=0)
+    # long segment (narrow tile, warp-shuffle exchanges) with the same data
+    ds = xs.eqm_train(xs.Dataset({"ref": ref, "hist": z}, time=tx), group="time", kind="+", quantiles=q)
+    gidx1, G1, _ = o.group_index(to, "time")
+    _, hq_o = o.eqm_train(ref.T.copy(), z.T.copy(), gidx1, G1, 1, q, "+")
+    np.testing.assert_allclose(_np(ds.hist_q), hq_o, rtol=1e-12, atol=0)
