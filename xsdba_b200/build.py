@@ -15,6 +15,7 @@ OUT = os.path.join(HERE, "libxsdba_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
+    "--split-compile=0",  # ptxas of the ~100 kernel instantiations in parallel on all host cores (2.5 min -> 1 min)
 ]
 
 

@@ -535,6 +535,8 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
   }
 }
 
+#include "train_bucket.cuh"
+
 // =============================================================================================
 // Table staging shared by the adjust kernels: rows r-1, r, r+1 (cyclic) of the tile's tables into
 // shared memory as xs/ys[slot][k][C] (column = point), NaN nodes dropped, bounds / constants of the
@@ -2177,8 +2179,30 @@ bool launch_train_fast(const float* ref, const float* hist, int64_t n_pts, int64
   if (sp != 1 || st < 0 || st > INT32_MAX / 4 || grp->segments.max_len > 1024 || nq > kFastMaxNq ||
       getenv("XSDBA_B200_NO_FAST"))
     return false;
-  const size_t smem = FastSmem::total(nq);
   dim3 grid((unsigned)((n_pts + 31) / 32), (unsigned)grp->n_groups);
+  // K1b (bucket select) is the default; XSDBA_B200_TRAIN_ALGO=sort keeps K1f's sorting network for A/B runs
+  const char* algo = getenv("XSDBA_B200_TRAIN_ALGO");
+  if (!(algo && strcmp(algo, "sort") == 0)) {
+    const size_t smem_b = BktSmem::total(nq);
+#define XS_TRAIN_BKT(J, N)                                                                                            \
+  do {                                                                                                               \
+    *rc = set_smem(train_bucket_kernel<J, N>, smem_b);                                                               \
+    if (*rc) return true;                                                                                            \
+    train_bucket_kernel<J, N><<<grid, kFastThreads, smem_b, s>>>(ref, hist, n_pts, st, grp->segments.off,            \
+                                                                 grp->segments.rows, grp->n_groups, q, nq, kind,    \
+                                                                 normalize, mode, af, hq, scaling, jp, use_jitter,  \
+                                                                 q64);                                              \
+  } while (0)
+    if (use_jitter && normalize) XS_TRAIN_BKT(true, true);
+    else if (use_jitter) XS_TRAIN_BKT(true, false);
+    else if (normalize) XS_TRAIN_BKT(false, true);
+    else XS_TRAIN_BKT(false, false);
+#undef XS_TRAIN_BKT
+    ++g_launches;
+    *rc = cuda_status(cudaGetLastError());
+    return true;
+  }
+  const size_t smem = FastSmem::total(nq);
   static const int stagger_ns = getenv("XSDBA_B200_STAGGER_NS") ? atoi(getenv("XSDBA_B200_STAGGER_NS")) : 0;
 #define XS_TRAIN_FAST(J, N)                                                                                          \
   do {                                                                                                               \
