@@ -3,14 +3,26 @@
 
 One "step" = one pass of the hot path (train(ref, hist) + adjust(sim)) over the whole 0.25 degree
 global grid (1440 x 721 gridpoints x 30 years daily, float32, group="time.month", nq=50, kind="+",
-interp="nearest", extrapolation="constant"), streamed through HBM as lat-band slabs because the four
-arrays (182 GB) do not fit next to each other in 180 GB.  Every slab's synthetic ref/hist/sim is
+interp="nearest", extrapolation="constant").  The four arrays (182 GB) do not fit next to each other
+in 180 GB, so the grid streams through HBM as lat-band slabs; every slab's synthetic ref/hist/sim is
 generated on the device OUTSIDE the timed region; the timed region (CUDA events on the launching
 stream) is train + adjust of the slab with inputs resident in HBM; a step's time is the sum over its
-slabs.  Multi-GPU: one process per GPU, every rank processes its own full grid (weak scaling, no
-data-path collective), time = max over ranks.
+slabs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+Multi-GPU (--gpus N under torchrun): STRONG scaling -- the ONE 721-row grid is cut into N lat bands
+(`xsdba_b200.sharding.lat_band`), one process per GPU, no data-path collective; `value` = gridpoint*days of
+the whole grid / max over ranks of the device time.  `weak` (every rank a full grid) is an extra key.
+
+Besides the headline the JSON line carries
+  roofline      dominant kernel: algorithmic bytes / its CUDA-event time vs the measured HBM peak
+  cpu_baseline  the oracle port on the host cores (rank 0, N = 1)
+  e2e           the same metric through the host-buffer C ABI entry (pinned host ref/hist/sim -> scen,
+                copies inside the timed region), MEAN over the timed calls, one full slab per rank
+  pcie          concurrent pinned H2D bandwidth per rank: the ceiling e2e scales against
+  configs       BASELINE.json configs[2..4] (QDM doy x 31, DQM + LOESS, MBCn): device-resident value,
+                roofline fraction on SURVEY 8d's algorithmic bytes, e2e / cpu_baseline for cfg3
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--configs cfg3,cfg4,cfg5|none]
 """
 from __future__ import annotations
 
@@ -20,6 +32,7 @@ import os
 import sys
 import threading
 import time
+import warnings
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -37,21 +50,25 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--lat-rows", type=int, default=NLAT, help="lat rows per rank per step (default: full grid)")
+    ap.add_argument("--lat-rows", type=int, default=NLAT, help="lat rows of the whole grid (default: 721)")
     ap.add_argument("--slab-rows", type=int, default=48, help="lat rows per slab")
-    ap.add_argument("--e2e-rows", type=int, default=8, help="lat rows of the host-buffer end-to-end sample")
+    ap.add_argument("--e2e-rows", type=int, default=48, help="lat rows of the host-buffer end-to-end sample per rank")
     ap.add_argument("--cpu-points", type=int, default=0, help="gridpoints of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="cfg3,cfg4,cfg5", help="other BASELINE configs to measure (or 'none')")
+    ap.add_argument("--cfg-rows", type=int, default=8, help="lat rows per rank of the cfg3 / cfg4 samples")
+    ap.add_argument("--no-weak", action="store_true")
     return ap.parse_args()
 
 
-def workload_config(args):
+def workload_config(args, world):
     return {
         "workload": "EQM nquantiles=50 group=time.month kind=+ interp=nearest extrapolation=constant, "
                     f"synthetic tas f32, {NLON}x{args.lat_rows} gridpoints x {NYEARS}-year daily ref/hist/sim (noleap)",
         "grid": [args.lat_rows, NLON], "n_time": 365 * NYEARS, "nquantiles": NQ, "group": GROUP,
-        "slab_lat_rows": args.slab_rows, "parallelism": f"lat-band slabs, {args.gpus} rank(s), no collective",
-        "l2": "inputs of every timed region (>= 4 GB per slab) exceed the 126 MB L2; no flush needed",
+        "slab_lat_rows": args.slab_rows,
+        "parallelism": f"one grid cut into {world} lat band(s), one rank per GPU, no collective",
+        "l2": "inputs of every timed region (>= 2.5 GB per slab) exceed the 126 MB L2; no flush needed",
     }
 
 
@@ -76,11 +93,11 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "host_cores": cores, "gpu_launches": 0,
     }
     print(json.dumps(line))
 
@@ -124,10 +141,10 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# B200 arm
+# synthetic inputs (SURVEY.md 8d generators, torch Philox on the device)
 # ------------------------------------------------------------------------------------------------
 def synth_slab(torch, gen, T, n_lat, lat0, which, doy, year, device):
-    """Synthetic tas slab, time-major (T, n_lat*NLON) f32 (SURVEY.md 8d generator, torch Philox)."""
+    """Synthetic tas slab, time-major (T, n_lat*NLON) f32, NaN-seeded."""
     A, sigma, k, off = {"ref": (12.0, 3.0, 1.0, 0.0), "hist": (10.0, 3.5, 1.0, 1.5), "sim": (10.0, 3.5, 1.1, 3.5)}[which]
     n = n_lat * NLON
     x = torch.empty((T, n), dtype=torch.float32, device=device)
@@ -145,6 +162,178 @@ def synth_slab(torch, gen, T, n_lat, lat0, which, doy, year, device):
     return x
 
 
+def synth_pr(torch, gen, T, n, which, device):
+    """Synthetic pr [mm/d]: Bernoulli(p_wet) * Gamma(shape, scale), dry days exactly 0, 0.1 % NaNs + an all-NaN
+    block of gridpoints (land / sea mask).  The Gamma variates come from torch's global CUDA generator."""
+    p_wet, shape, scale = {"ref": (0.45, 0.8, 7.5), "hist": (0.60, 0.9, 5.0), "sim": (0.60, 0.9, 5.5)}[which]
+    conc = torch.full((T, n), shape, dtype=torch.float32, device=device)
+    x = torch._standard_gamma(conc) * scale
+    del conc
+    wet = torch.empty((T, n), dtype=torch.float32, device=device).uniform_(0, 1, generator=gen) < p_wet
+    x *= wet
+    m = torch.empty((T, n), dtype=torch.int16, device=device).random_(0, 1000, generator=gen)
+    x[m == 0] = float("nan")
+    del m, wet
+    x[:, n // 2: n // 2 + 16] = float("nan")
+    return x
+
+
+def time_device(torch, fn, steps, warmup=1):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2..4]: rank-local samples, device-resident (weak over ranks)
+# ------------------------------------------------------------------------------------------------
+def run_other_configs(args, torch, dist, xs, lib, dev, rank, world, peak, want):
+    import numpy as np
+
+    out = {}
+    tt = xs.TimeAxis.daily(1981, NYEARS, "noleap")
+    ts = xs.TimeAxis.daily(2041, NYEARS, "noleap")
+    T = len(tt)
+    n = args.cfg_rows * NLON
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(777 + rank)
+    torch.manual_seed(4242 + rank)
+    steps = max(1, min(args.steps, 2))
+
+    def reduce_max(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.cpu())
+
+    warnings.simplefilter("ignore")
+    if "cfg3" in want:
+        # QDM kind='*' pr, Grouper('time.dayofyear', 31), nq=100, nearest / constant; pr jittered once before timing
+        g = xs.Grouper("time.dayofyear", 31)
+        ref, hist, sim = (xs.jitter_under_thresh(synth_pr(torch, gen, T, n, w, dev), "0.01 mm/d", seed=11 + i)
+                          for i, w in enumerate(("ref", "hist", "sim")))
+        res = {"workload": f"QDM kind=* pr f32, Grouper(time.dayofyear, window=31), nq=100, nearest/constant, "
+                           f"{n} gridpoints x {T} days per rank (weak over ranks)"}
+        for rw in (False, True):
+            state = {}
+
+            def train():
+                state["obj"] = xs.QuantileDeltaMapping.train(ref, hist, time=tt, nquantiles=100, group=g, kind="*")
+
+            def adjust():
+                state["scen"] = state["obj"].adjust(sim, time=ts, interp="nearest", extrapolation="constant", rank_window=rw)
+            tr = reduce_max(time_device(torch, train, steps))
+            ad = reduce_max(time_device(torch, adjust, steps))
+            key = "rank_window_true" if rw else "rank_window_false"
+            # SURVEY 8d: 56.0 B per gp*day for cfg3 with the factors materialised (af + hist_q written, af read)
+            bytes_step = n * (3 * T * 4 + T * 4 + 3 * 365 * 100 * 4)
+            res[key] = {"train_ms": tr, "adjust_ms": ad, "value": world * n * T / ((tr + ad) * 1e-3), "unit": UNIT,
+                        "roofline": {"bound": "hbm", "achieved": bytes_step / ((tr + ad) * 1e-3) / 1e9, "peak": peak,
+                                     "unit": "GB/s", "frac": bytes_step / ((tr + ad) * 1e-3) / 1e9 / peak,
+                                     "algorithmic_bytes_per_gp_day": bytes_step / (n * T)}}
+            del state
+        # end to end through the host entry (QDM mode), 2 lat rows per rank
+        n_e = 2 * NLON
+        hb = [t[:, :n_e].contiguous().cpu().pin_memory() for t in (ref, hist, sim)]
+        out_h = torch.empty((T, n_e), dtype=torch.float32).pin_memory()
+        ts_e = []
+        for i in range(1 + steps):
+            t0 = time.perf_counter()
+            xs.train_adjust_host(hb[0].numpy(), hb[1].numpy(), hb[2].numpy(), time=tt, sim_time=ts, nquantiles=100,
+                                 group="time.dayofyear", window=31, kind="*", method="qdm", slab_points=1024,
+                                 out=out_h.numpy())
+            _ = float(out_h[::997, ::101].nansum())
+            if i:
+                ts_e.append(time.perf_counter() - t0)
+        res["e2e"] = {"value": world * n_e * T / (reduce_max(1e3 * sum(ts_e) / len(ts_e)) * 1e-3), "unit": UNIT,
+                      "h2d_bytes_per_step": 3 * n_e * T * 4, "d2h_bytes_per_step": n_e * T * 4,
+                      "sample": f"{n_e} gridpoints per rank, mean of {len(ts_e)} calls"}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import cpu_baseline
+            cores = os.cpu_count() or 1
+            r = cpu_baseline.run_cfg3(4 * cores, cores)
+            res["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "seconds")}
+        out["cfg3"] = res
+        del ref, hist, sim, hb, out_h
+        torch.cuda.empty_cache()
+
+    if "cfg4" in want:
+        g = xs.Grouper("time.dayofyear", 31)
+        doy = torch.from_numpy(tt.dayofyear.astype(np.float32)).to(dev)
+        year = torch.from_numpy((tt.year - tt.year[0]).astype(np.float32)).to(dev)
+        ref, hist, sim = (synth_slab(torch, gen, T, args.cfg_rows, 300, w, doy, year, dev) for w in ("ref", "hist", "sim"))
+        state = {}
+        loess = xs.LoessDetrend(group="time", f=0.2, niter=1, d=0)
+
+        def train():
+            state["obj"] = xs.DetrendedQuantileMapping.train(ref, hist, time=tt, nquantiles=50, group=g, kind="+")
+
+        def adjust():
+            state["scen"] = state["obj"].adjust(sim, time=ts, detrend=loess)
+        tr = reduce_max(time_device(torch, train, steps))
+        ad = reduce_max(time_device(torch, adjust, steps))
+        res = {"workload": f"DQM kind=+ tas f32, Grouper(time.dayofyear, 31), nq=50, LoessDetrend(group=time, f=0.2, "
+                           f"niter=1, d=0), {n} gridpoints x {T} days per rank (weak over ranks)",
+               "tas": {"train_ms": tr, "adjust_ms": ad, "value": world * n * T / ((tr + ad) * 1e-3), "unit": UNIT}}
+        del ref, hist, sim, state
+        torch.cuda.empty_cache()
+        ref, hist, sim = (synth_pr(torch, gen, T, n, w, dev) for w in ("ref", "hist", "sim"))
+        state = {}
+
+        def train_pr():
+            state["obj"] = xs.DetrendedQuantileMapping.train(ref, hist, time=tt, nquantiles=50, group=g, kind="*",
+                                                             jitter_under_thresh_value="0.01 mm/d")
+
+        def adjust_pr():
+            state["scen"] = state["obj"].adjust(sim, time=ts, detrend=loess)
+        tr = reduce_max(time_device(torch, train_pr, steps))
+        ad = reduce_max(time_device(torch, adjust_pr, steps))
+        res["pr_jitter_under_thresh"] = {"train_ms": tr, "adjust_ms": ad, "value": world * n * T / ((tr + ad) * 1e-3),
+                                         "unit": UNIT}
+        out["cfg4"] = res
+        del ref, hist, sim, state
+        torch.cuda.empty_cache()
+
+    if "cfg5" in want:
+        # MBCn, 5 variables, n_iter=20; the reference refuses group='time.month' for MBCn (adjustment.py:1851-1852), so
+        # the block structure is group='time' (SURVEY section 8 note)
+        nm = NLON
+        doy = torch.from_numpy(tt.dayofyear.astype(np.float32)).to(dev)
+        year = torch.from_numpy((tt.year - tt.year[0]).astype(np.float32)).to(dev)
+
+        def mk(which):
+            return torch.stack([synth_slab(torch, gen, T, 1, 300 + v, which, doy, year, dev).nan_to_num_(280.0)
+                                for v in range(5)])
+        ref5, hist5, sim5 = mk("ref"), mk("hist"), mk("sim")
+        state = {}
+
+        def train():
+            state["obj"] = xs.MBCn.train(ref5, hist5, time=tt, base_kws={"nquantiles": 20, "group": "time"}, n_iter=20,
+                                         seed=1)
+
+        def adjust():
+            state["scen"] = state["obj"].adjust(sim5, ref5, hist5, time=tt)
+        tr = reduce_max(time_device(torch, train, 1))
+        ad = reduce_max(time_device(torch, adjust, 1))
+        out["cfg5"] = {"workload": f"MBCn 5 variables f32, n_iter=20, nq=20, group=time, {nm} gridpoints x {T} days per "
+                                   "rank (weak over ranks)",
+                       "train_ms": tr, "adjust_ms": ad, "value": world * nm * T / ((tr + ad) * 1e-3), "unit": UNIT}
+        del ref5, hist5, sim5, state
+        torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
 def run_b200(args):
     import numpy as np
     import torch
@@ -152,6 +341,7 @@ def run_b200(args):
 
     import xsdba_b200 as xs
     from xsdba_b200 import _lib
+    from xsdba_b200.sharding import lat_band, slabs as slab_list
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -180,14 +370,16 @@ def run_b200(args):
     gen.manual_seed(20260117 + rank)
     stream = torch.cuda.current_stream().cuda_stream
 
-    slabs = [(r0, min(args.slab_rows, args.lat_rows - r0)) for r0 in range(0, args.lat_rows, args.slab_rows)]
-    max_pts = max(n for _, n in slabs) * NLON
+    row_lo, row_hi = lat_band(args.lat_rows, rank, world)              # this rank's band of the ONE grid
+    band = [(row_lo + r0, nr) for r0, nr in slab_list(row_hi - row_lo, args.slab_rows)]
+    full = slab_list(args.lat_rows, args.slab_rows)                     # (weak figure: every rank the full grid)
+    max_pts = args.slab_rows * NLON
     af = torch.empty((max_pts, G, NQ), dtype=torch.float32, device=dev)
     hq = torch.empty_like(af)
     scen = torch.empty((T, max_pts), dtype=torch.float32, device=dev)
 
-    def one_step(timed):
-        """-> (train_ms, adjust_ms, checksum) summed over the slabs of this rank's grid."""
+    def one_step(slabs, timed):
+        """-> (train_ms, adjust_ms, checksum) summed over the given slabs."""
         tr_ms = ad_ms = 0.0
         chk = 0.0
         for r0, nrow in slabs:
@@ -209,7 +401,7 @@ def run_b200(args):
             tr_ms += e0.elapsed_time(e1)
             ad_ms += e1.elapsed_time(e2)
             if timed:
-                chk += float(torch.nansum(scen[:, :n][:: 997, :: 101]))
+                chk += float(torch.nansum(scen.view(-1)[: T * n].view(T, n)[:: 997, :: 101]))
             del ref, hist, sim
         return tr_ms, ad_ms, chk
 
@@ -219,8 +411,14 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()]
+
     for _ in range(args.warmup):
-        one_step(False)
+        one_step(band, False)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -228,80 +426,112 @@ def run_b200(args):
     sampler.active = True
     wall0 = time.perf_counter()
     tr_tot = ad_tot = 0.0
+    chk = 0.0
     for _ in range(args.steps):
-        a, b, chk = one_step(True)
+        a, b, chk = one_step(band, True)
         tr_tot += a
         ad_tot += b
     barrier()
     wall = time.perf_counter() - wall0
     sampler.active = False
     launches = lib.xsdba_launch_count() - l0
-    dev_ms = torch.tensor([tr_tot + ad_tot, tr_tot, ad_tot], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
-    tot_ms, tr_ms, ad_ms = (float(v) for v in dev_ms.cpu())
-    n_pts_rank = args.lat_rows * NLON
-    units = world * n_pts_rank * T * args.steps
-    value = units / (tot_ms * 1e-3)
+    tot_ms, tr_ms, ad_ms = reduce_max([tr_tot + ad_tot, tr_tot, ad_tot])
+    n_pts_grid = args.lat_rows * NLON
+    n_pts_rank = (row_hi - row_lo) * NLON
+    value = n_pts_grid * T * args.steps / (tot_ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (train: group-segmented sort + quantiles) ----------------
-    sys.path.insert(0, ROOT)
+    weak = None
+    if world > 1 and not args.no_weak:
+        barrier()
+        a, b, _ = one_step(full, False)
+        (w_ms,) = reduce_max([a + b])
+        weak = {"value": world * n_pts_grid * T / (w_ms * 1e-3), "unit": UNIT, "ms_per_step": w_ms,
+                "what": "every rank processes its own full 721-row grid (one step)"}
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    n_launch = len(slabs) * args.steps
+    n_launch = len(band) * args.steps
     train_bytes_step = n_pts_rank * (2 * T * 4 + 2 * G * NQ * 4)          # reads ref+hist, writes af+hist_q
     adjust_bytes_step = n_pts_rank * (2 * T * 4 + 2 * G * NQ * 4)         # reads sim+tables, writes scen
     dom = "train" if tr_ms >= ad_ms else "adjust"
     dom_bytes = train_bytes_step if dom == "train" else adjust_bytes_step
     dom_ms = max(tr_ms, ad_ms)
     achieved = dom_bytes * args.steps / (dom_ms * 1e-3) / 1e9
+    train_kernel = "train_fast_kernel<false, false>" if os.environ.get("XSDBA_B200_TRAIN_ALGO") == "sort" \
+        else "train_bucket_kernel<false, false>"
     roofline = {
-        "bound": "hbm", "kernel": "train_fast_kernel<false, false>" if dom == "train" else "pack_tables_kernel + adjust_tile_kernel",
+        "bound": "hbm", "kernel": train_kernel if dom == "train" else "pack_tables_kernel + adjust_tile_kernel",
         "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
-        # dram__bytes_read+write per launch from the ncu --set full capture in profiles/r01_ncu_final.txt:
-        # 6.505 GB for a 69 120-point launch whose algorithmic bytes are 6.387 GB (x1.0185: no re-reads)
-        "traffic": (dom_bytes * args.steps / n_launch) * 1.0185 if dom == "train" else None,
-        "traffic_source": "ncu dram__bytes_{read,write}.sum of profiles/r01_ncu_final.txt scaled to this launch size",
+        # not measured in this run: see the ncu --set full capture of the same kernel under profiles/
+        # (dram__bytes_read.sum + dram__bytes_write.sum per launch)
+        "traffic": None, "traffic_source": "profiles/r02_ncu_train_bucket.txt",
         "launches": n_launch, "avg_launch_ms": dom_ms / n_launch,
         "algorithmic_bytes_per_launch": dom_bytes * args.steps / n_launch,
         "step": {"train_ms": tr_ms / args.steps, "adjust_ms": ad_ms / args.steps,
                  "train_GBps": train_bytes_step * args.steps / (tr_ms * 1e-3) / 1e9,
                  "adjust_GBps": adjust_bytes_step * args.steps / (ad_ms * 1e-3) / 1e9,
-                 "whole_step_frac_of_peak": (train_bytes_step + adjust_bytes_step) * args.steps / (tot_ms * 1e-3) / 1e9 / peak},
+                 "whole_step_frac_of_peak": (train_bytes_step + adjust_bytes_step) * args.steps / (tot_ms * 1e-3) / 1e9 / peak,
+                 "fused_floor_frac_of_peak": n_pts_rank * 16 * T * args.steps / (tot_ms * 1e-3) / 1e9 / peak},
     }
 
+    # ---- PCIe ceiling: concurrent pinned host -> device copies on all ranks -----------------------
+    pin = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    dst.copy_(pin, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        dst.copy_(pin, non_blocking=True)
+    torch.cuda.synchronize()
+    (h2d_s,) = reduce_max([time.perf_counter() - t0])
+    pcie = {"h2d_GBps_per_rank_concurrent": 4 * (256 << 20) / h2d_s / 1e9, "ranks": world,
+            "what": "4 x 256 MiB pinned host -> device copies issued by all ranks at once (slowest rank)"}
+    del pin, dst
+
     # ---- end to end through the host C ABI (pinned host buffers, copies inside the timed region) ---
-    n_e2e = args.e2e_rows * NLON
+    mem_gb = 0.0
+    try:
+        mem_gb = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_AVPHYS_PAGES") / 2**30
+    except (ValueError, OSError):
+        pass
+    e2e_rows = args.e2e_rows
+    while e2e_rows > 1 and 4 * e2e_rows * NLON * T * 4 * world / 2**30 > 0.5 * mem_gb:
+        e2e_rows //= 2   # pinned ref/hist/sim/scen of all ranks must fit comfortably in host memory
+    n_e2e = e2e_rows * NLON
     e2e = None
     if n_e2e > 0:
-        hostgen = torch.Generator().manual_seed(7 + rank)
         hb = []
-        for A_, s_, off_ in ((12.0, 3.0, 0.0), (10.0, 3.5, 1.5), (10.0, 3.5, 3.5)):
-            t = torch.empty((T, n_e2e), dtype=torch.float32).normal_(0, s_, generator=hostgen)
-            t += (273.15 + off_ - A_ * torch.cos(2 * torch.pi * (doy.cpu() - 15.0) / 365.0))[:, None]
-            hb.append(t.pin_memory())
+        for w in ("ref", "hist", "sim"):      # the NaN-seeded generator of the device path, copied to pinned memory
+            t = torch.empty((T, n_e2e), dtype=torch.float32).pin_memory()
+            for r0 in range(0, e2e_rows, 8):
+                nr = min(8, e2e_rows - r0)
+                t[:, r0 * NLON:(r0 + nr) * NLON].copy_(synth_slab(torch, gen, T, nr, 300 + r0, w, doy, year, dev))
+            hb.append(t)
         out_h = torch.empty((T, n_e2e), dtype=torch.float32).pin_memory()
         ref_h, hist_h, sim_h = (t.numpy() for t in hb)
         e2e_times = []
-        for i in range(2 + max(1, args.steps)):
+        for i in range(1 + max(1, args.steps)):
             barrier()
             t0 = time.perf_counter()
             xs.train_adjust_host(ref_h, hist_h, sim_h, time=t_train, sim_time=t_sim, nquantiles=NQ, group=GROUP,
                                  kind="+", method="eqm", slab_points=2048, out=out_h.numpy())
-            chk_e2e = float(out_h[::997, ::101].sum())  # the device->host result is read
-            e2e_times.append(time.perf_counter() - t0)
-        e2e_t = torch.tensor([min(e2e_times[2:])], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n_e2e * T / float(e2e_t.cpu()), "unit": UNIT,
+            chk_e2e = float(out_h[::997, ::101].nansum())  # the device->host result is read
+            if i:
+                e2e_times.append(time.perf_counter() - t0)
+        (e2e_s,) = reduce_max([sum(e2e_times) / len(e2e_times)])
+        e2e = {"value": world * n_e2e * T / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": 3 * n_e2e * T * 4, "d2h_bytes_per_step": n_e2e * T * 4,
-               "sample": f"{n_e2e} gridpoints x {T} days per rank through xsdba_qm_train_adjust_host_f32 "
-                         "(pinned host ref/hist/sim -> scen), best of the timed calls"}
+               "sample": f"{n_e2e} gridpoints x {T} days per rank (NaN-seeded) through xsdba_qm_train_adjust_host_f32 "
+                         f"(pinned host ref/hist/sim -> scen), mean of {len(e2e_times)} timed calls after 1 warm-up",
+               "pcie_floor_value": world * n_e2e * T / (3 * n_e2e * T * 4 / (pcie["h2d_GBps_per_rank_concurrent"] * 1e9)),
+               "checksum": chk_e2e}
+        del hb, out_h
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -312,13 +542,19 @@ def run_b200(args):
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                "seconds": r["seconds"]}
 
+    del af, hq, scen
+    torch.cuda.empty_cache()
+    want = [] if args.configs in ("", "none") else args.configs.split(",")
+    configs = run_other_configs(args, torch, dist, xs, lib, dev, rank, world, peak, want) if want else None
+
     sampler.stop_flag = True
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args), "roofline": roofline,
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "roofline": roofline,
+            "cpu_baseline": cpu, "e2e": e2e, "pcie": pcie, "weak": weak, "configs": configs,
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "host_cores": os.cpu_count(),
             "wall_ms_per_step_incl_generation": 1e3 * wall / args.steps, "checksum": chk,
         }
         print(json.dumps(line))

@@ -283,6 +283,13 @@ int xsdba_rotate_f32(const float* x_dev, int64_t n_elem, int32_t n_var, const fl
                      void* cuda_stream);
 int xsdba_rotate_f64(const double* x_dev, int64_t n_elem, int32_t n_var, const float* rot_host, double* y_dev,
                      void* cuda_stream);
+/* The same product with the multiply and the add rounded separately, terms in ascending order: numpy's
+ * einsum("ij,j...->i...") as _npdft_adjust calls it (_adjustment.py:449, 462); xsdba_rotate_* is the fused chain of
+ * `rot @ x` in _npdft_train (_adjustment.py:311).  The N-pdf iteration amplifies one-ulp differences, so both exist. */
+int xsdba_rotate_unfused_f32(const float* x_dev, int64_t n_elem, int32_t n_var, const float* rot_host, float* y_dev,
+                             void* cuda_stream);
+int xsdba_rotate_unfused_f64(const double* x_dev, int64_t n_elem, int32_t n_var, const float* rot_host, double* y_dev,
+                             void* cuda_stream);
 int xsdba_standardize_f32(const float* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
                           int64_t n_time, int32_t n_var, int64_t var_stride, float* y_dev, void* cuda_stream);
 int xsdba_standardize_f64(const double* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,

@@ -837,6 +837,13 @@ def mbcn_blocks(time: TimeAxis, group: str, window: int):
 
 
 def _standardize(x):
+    """``(x - nanmean) / nanstd`` along the last axis as ``_npdft_train`` computes it (_adjustment.py:303-305).  The
+    rows are made C-contiguous first: numpy sums a contiguous axis pairwise and any other layout sequentially (the
+    float32 mean of a 30-year series then differs by ~1e-5 relative), and ``x[:, i, idx]`` -- basic and advanced
+    indexing mixed -- silently returns a Fortran-ordered array.  The N-pdf iteration amplifies such differences by
+    orders of magnitude, so the layout is pinned here.  (``mbcn_adjust`` standardises ``sim`` through xarray's
+    mean / std, i.e. bottleneck when installed -- absent from this image, unpinned; this is the stand-in.)"""
+    x = np.ascontiguousarray(x)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         return ((x - np.nanmean(x, axis=-1, keepdims=True)) / np.nanstd(x, axis=-1, keepdims=True)).astype(x.dtype)

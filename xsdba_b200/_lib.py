@@ -49,6 +49,7 @@ for _t in ("f32", "f64"):
     SIGNATURES[f"xsdba_dqm_adjust_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp])
     SIGNATURES[f"xsdba_rank_lookup_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp])
     SIGNATURES[f"xsdba_rotate_{_t}"] = (C.c_int, [vp, i64, i32, c_f32p, vp, vp])
+    SIGNATURES[f"xsdba_rotate_unfused_{_t}"] = (C.c_int, [vp, i64, i32, c_f32p, vp, vp])
     SIGNATURES[f"xsdba_standardize_{_t}"] = (C.c_int, [vp, i64, i64, i64, i64, i32, i64, vp, vp])
     SIGNATURES[f"xsdba_reorder_{_t}"] = (C.c_int, [vp, vp, i64, i64, i64, vp, vp, vp])
     SIGNATURES[f"xsdba_group_vecquantile_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp])

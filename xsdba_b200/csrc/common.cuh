@@ -23,6 +23,7 @@ template <> struct Num<float> {
   static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
   static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
   static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
 };
 template <> struct Num<double> {
   static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
@@ -36,6 +37,7 @@ template <> struct Num<double> {
   static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
   static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
   static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
 };
 
 template <typename T> __device__ __forceinline__ bool is_nan(T v) { return v != v; }

@@ -1738,7 +1738,13 @@ copy_rows_kernel(const float* __restrict__ src, long long n_pts, long long st, c
 constexpr int kMaxVar = 8;
 struct RotMat { float r[kMaxVar * kMaxVar]; };
 
-template <typename T>
+// FUSED = true: acc = fma(R[v][w], x[w], acc), w ascending from acc = 0 -- what `rot @ x` computes through
+// OpenBLAS's sgemm / dgemm micro-kernels (_adjustment.py:311).  FUSED = false: acc = acc + R[v][w] * x[w] with the
+// product rounded first -- numpy's einsum("ij,j...->i...") sum-of-products loop (_adjustment.py:449, 462), which is
+// compiled for the SSE2 baseline (no FMA).  Both were pinned bit for bit against numpy 2.3 / OpenBLAS 0.3.30
+// (tests/golden, test_mbcn_*); the N-pdf iteration is chaotic (one ulp here moves af_q by 1e-3 after 15 iterations), so
+// the distinction matters.
+template <typename T, bool FUSED>
 __global__ void rotate_kernel(const T* __restrict__ x, long long n_elem, int n_var, RotMat R, T* __restrict__ y) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_elem; e += (long long)gridDim.x * blockDim.x) {
     T in[kMaxVar];
@@ -1749,13 +1755,74 @@ __global__ void rotate_kernel(const T* __restrict__ x, long long n_elem, int n_v
       if (v >= n_var) break;
       T acc = (T)0;
 #pragma unroll
-      for (int w = 0; w < kMaxVar; ++w) if (w < n_var) acc = Num<T>::fma((T)R.r[v * kMaxVar + w], in[w], acc);
+      for (int w = 0; w < kMaxVar; ++w)
+        if (w < n_var)
+          acc = FUSED ? Num<T>::fma((T)R.r[v * kMaxVar + w], in[w], acc)
+                      : Num<T>::add(acc, Num<T>::mul((T)R.r[v * kMaxVar + w], in[w]));
       y[(long long)v * n_elem + e] = acc;
     }
   }
 }
 
-// one thread per (variable, point): two passes over time (mean, then variance), float64 accumulation
+// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, @TYPE@_pairwise_sum) of f(x[t]) over
+// t in [t0, t0 + n): < 8 terms sequentially, <= 128 terms with 8 interleaved accumulators combined as a tree, longer
+// runs split at n/2 rounded down to a multiple of 8.  Rounded in T after every operation.
+template <typename T, class F>
+__device__ T np_pairwise_leaf(const T* __restrict__ x, long long st, int t0, int n, F f) {
+  if (n < 8) {
+    T res = (T)0;
+    for (int i = 0; i < n; ++i) res = Num<T>::add(res, f(x[(long long)(t0 + i) * st]));
+    return res;
+  }
+  T r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = f(x[(long long)(t0 + j) * st]);
+  int i = 8;
+  for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = Num<T>::add(r[j], f(x[(long long)(t0 + i + j) * st]));
+  }
+  T res = Num<T>::add(Num<T>::add(Num<T>::add(r[0], r[1]), Num<T>::add(r[2], r[3])),
+                      Num<T>::add(Num<T>::add(r[4], r[5]), Num<T>::add(r[6], r[7])));
+  for (; i < n; ++i) res = Num<T>::add(res, f(x[(long long)(t0 + i) * st]));
+  return res;
+}
+// (the recursion of the original, unrolled into an explicit stack: depth log2(n / 128) + 1)
+template <typename T, class F>
+__device__ T np_pairwise_sum(const T* __restrict__ x, long long st, int n_total, F f) {
+  struct Frame { int t0, n, state; T left; };
+  Frame stk[24];
+  int sp = 1;
+  stk[0].t0 = 0; stk[0].n = n_total; stk[0].state = 0; stk[0].left = (T)0;
+  T result = (T)0;
+  while (sp > 0) {
+    Frame& fr = stk[sp - 1];
+    if (fr.state == 0) {
+      if (fr.n <= 128) { result = np_pairwise_leaf<T>(x, st, fr.t0, fr.n, f); --sp; continue; }
+      int n2 = fr.n / 2;
+      n2 -= n2 % 8;
+      fr.state = 1;
+      stk[sp].t0 = fr.t0; stk[sp].n = n2; stk[sp].state = 0; stk[sp].left = (T)0;
+      ++sp;
+    } else if (fr.state == 1) {
+      int n2 = fr.n / 2;
+      n2 -= n2 % 8;
+      fr.left = result;
+      fr.state = 2;
+      stk[sp].t0 = fr.t0 + n2; stk[sp].n = fr.n - n2; stk[sp].state = 0; stk[sp].left = (T)0;
+      ++sp;
+    } else {
+      result = Num<T>::add(fr.left, result);
+      --sp;
+    }
+  }
+  return result;
+}
+
+// (x - nanmean(x)) / nanstd(x) along time, one thread per (variable, point), with numpy's arithmetic
+// (processing.standardize is not used by _npdft_train: it calls np.nanmean / np.nanstd itself, _adjustment.py:303-305;
+// numpy/lib/_nanfunctions_impl.py: NaNs replaced by 0, pairwise sums in the data dtype, the division by the count done
+// in float64 and rounded to the data dtype, deviations and squares rounded to the data dtype).
 template <typename T>
 __global__ void standardize_kernel(const T* __restrict__ x, long long n_pts, long long sp, long long st, int n_time,
                                    int n_var, long long var_stride, T* __restrict__ y) {
@@ -1765,15 +1832,18 @@ __global__ void standardize_kernel(const T* __restrict__ x, long long n_pts, lon
   const int v = (int)(id / n_pts);
   const T* xv = x + v * var_stride + pt * sp;
   T* yv = y + v * var_stride + pt * sp;
-  double s = 0; int n = 0;
-  for (int t = 0; t < n_time; ++t) { const T a = xv[(long long)t * st]; if (!is_nan(a)) { s += (double)a; ++n; } }
-  const T mean = (T)(s / (double)n);
-  double ss = 0;
-  for (int t = 0; t < n_time; ++t) {
-    const T a = xv[(long long)t * st];
-    if (!is_nan(a)) { const double d = (double)(T)(a - mean); ss += d * d; }
-  }
-  const T sd = (T)sqrt(ss / (double)n);
+  int n = 0;
+  for (int t = 0; t < n_time; ++t) n += is_nan(xv[(long long)t * st]) ? 0 : 1;
+  const T tot = np_pairwise_sum<T>(xv, st, n_time, [](T a) { return is_nan(a) ? (T)0 : a; });
+  const T mean = (T)((double)tot / (double)n);
+  const T ssq = np_pairwise_sum<T>(xv, st, n_time, [mean](T a) {
+    if (is_nan(a)) return (T)0;
+    const T d = Num<T>::sub(a, mean);
+    return Num<T>::mul(d, d);
+  });
+  T var = (T)((double)ssq / (double)n);
+  if (n <= 0) var = Num<T>::nan();
+  const T sd = Num<T>::sqrt(var);
   for (int t = 0; t < n_time; ++t) yv[(long long)t * st] = Num<T>::div(Num<T>::sub(xv[(long long)t * st], mean), sd);
 }
 
@@ -2898,14 +2968,15 @@ int launch_escore(const T* tgt, const T* sim, int64_t n_pts, int64_t sp, int64_t
 }
 
 template <typename T>
-int launch_rotate(const T* x, int64_t n_elem, int n_var, const float* rot_host, T* y, void* stream) {
+int launch_rotate(const T* x, int64_t n_elem, int n_var, const float* rot_host, T* y, void* stream, bool fused = true) {
   if ((n_elem > 0 && !x) || (n_elem > 0 && !y) || (n_elem > 0 && !rot_host) || n_var < 1 || n_var > kMaxVar || n_elem < 0 || (n_elem > 0 && x == y)) return XSDBA_ERR_INVALID_ARGUMENT;
   if (n_elem == 0) return XSDBA_OK;
   RotMat R;
   for (int v = 0; v < kMaxVar; ++v) for (int w = 0; w < kMaxVar; ++w)
     R.r[v * kMaxVar + w] = (v < n_var && w < n_var) ? rot_host[v * n_var + w] : 0.f;
   const unsigned blocks = (unsigned)std::min<int64_t>((n_elem + 255) / 256, 148 * 32);
-  rotate_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n_elem, n_var, R, y);
+  if (fused) rotate_kernel<T, true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n_elem, n_var, R, y);
+  else rotate_kernel<T, false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n_elem, n_var, R, y);
   ++g_launches;
   return cuda_status(cudaGetLastError());
 }
@@ -3146,6 +3217,12 @@ int xsdba_rotate_f32(const float* x, int64_t n_elem, int32_t n_var, const float*
 }
 int xsdba_rotate_f64(const double* x, int64_t n_elem, int32_t n_var, const float* rot_host, double* y, void* stream) {
   return launch_rotate<double>(x, n_elem, n_var, rot_host, y, stream);
+}
+int xsdba_rotate_unfused_f32(const float* x, int64_t n_elem, int32_t n_var, const float* rot_host, float* y, void* stream) {
+  return launch_rotate<float>(x, n_elem, n_var, rot_host, y, stream, false);
+}
+int xsdba_rotate_unfused_f64(const double* x, int64_t n_elem, int32_t n_var, const float* rot_host, double* y, void* stream) {
+  return launch_rotate<double>(x, n_elem, n_var, rot_host, y, stream, false);
 }
 int xsdba_standardize_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, int64_t n_time, int32_t n_var,
                           int64_t var_stride, float* y, void* stream) {

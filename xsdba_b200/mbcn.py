@@ -77,11 +77,13 @@ class _Block:
         _lib.check(fn(x.data_ptr(), self.N, 1, self.N, self.Tb, V, self.Tb * self.N, y.data_ptr(), self.stream), "standardize")
         return y
 
-    def rotate(self, x, rot: np.ndarray):
+    def rotate(self, x, rot: np.ndarray, fused: bool = True):
+        """``rot @ x`` (fused multiply-add chain, _adjustment.py:311) or ``einsum("ij,j...->i...", rot, x)`` (separately
+        rounded products and sums, _adjustment.py:449, 462)."""
         V = x.shape[0]
         y = torch.empty_like(x)
         rot = np.ascontiguousarray(rot, np.float32)
-        fn = getattr(self.lib, f"xsdba_rotate_{_sfx(self.dt)}")
+        fn = getattr(self.lib, f"xsdba_rotate_{'' if fused else 'unfused_'}{_sfx(self.dt)}")
         _lib.check(fn(x.data_ptr(), self.Tb * self.N, V, rot.ctypes.data_as(_lib.c_f32p), y.data_ptr(), self.stream), "rotate")
         return y
 
@@ -199,11 +201,11 @@ def mbcn_adjust(ref, hist, sim, *, time, af_q, rot_matrices, quantiles, group, k
         # 2. N-pdf transform of the standardised block (_adjustment.py:561-586)
         x = blk.standardize(sb)
         for ii in range(len(rots)):
-            x = blk.rotate(x, _iter_rot(rots, ii))
+            x = blk.rotate(x, _iter_rot(rots, ii), fused=False)
             for iv in range(V):
                 x[iv] = blk.add_factor_at_rank(x[iv], af_q[ib, :, ii, iv, :].reshape(N, 1, -1).contiguous(), q64, interp,
                                                extrapolation)
-        x = blk.rotate(x, rots[-1].T)
+        x = blk.rotate(x, rots[-1].T, fused=False)
         # 3. reorder the univariate scenario by the ranks of the transformed block, keep the exact-group days
         keep = torch.as_tensor(np.nonzero(np.isin(gw, g))[0], device=sim.device)
         gi = torch.as_tensor(g, device=sim.device)
