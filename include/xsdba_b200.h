@@ -19,7 +19,10 @@
  *  - kind: '+' (43) or '*' (42), as in utils.get_correction / apply_correction (utils.py:130-162).
  *  - Every function returns 0 on success, a negative XSDBA_ERR_* for argument errors, or a
  *    positive cudaError_t.  Nothing throws across the ABI.  Functions are re-entrant; the only
- *    state is the caller-owned grouping handle (immutable after creation) and the caller's stream.
+ *    state is the caller-owned grouping handle (immutable after creation, bound to the device it was
+ *    created on: calls from another current device return XSDBA_ERR_INVALID_ARGUMENT), the caller's
+ *    stream and caller-owned workspaces.  Per-call scratch of the device entry points comes from the
+ *    stream-ordered memory pool of the current device (cudaMallocAsync on the caller's stream).
  *  - Inputs are never modified (the reference's numba quantile sorts its input in place when the
  *    reshape is a view; this library does not).
  */
@@ -238,13 +241,38 @@ int xsdba_group_rank_f64(const double* x_dev, int64_t n_pts, int64_t stride_pt, 
                          void* cuda_stream);
 
 /*
- * End-to-end host entry point (what the xarray-facing layer calls with numpy buffers): EQM
- * train(ref, hist) + adjust(sim) on HOST arrays in the reference's (time, points) C order
- * (time-major, contiguous).  Points are streamed through the GPU in slabs on internal streams
- * (H2D copy, train, adjust, D2H copy overlapped); af/hist_q (point-major, may be NULL) and scen
- * (time-major) are written back to host.  Pinned host memory gives full PCIe rate; pageable works.
- * grp_train carries the Grouper window; grp_sim the sim time axis.  mode: 0 = EQM, 1 = QDM.
+ * End-to-end host entry points (what the xarray-facing layer calls with numpy buffers; they stand for
+ * TrainAdjust.train + .adjust on in-memory data, adjustment.py:226-316): train(ref, hist) + adjust(sim) on HOST
+ * arrays in the reference's (time, points) C order (time-major, contiguous).  Points are streamed through the GPU in
+ * slabs on three streams created by the call (H2D copy, train, adjust, D2H copy overlapped); af / hist_q / scaling
+ * (point-major, may be NULL) and scen (time-major) are written back to host.  Pinned host memory gives full PCIe
+ * rate; pageable works.
+ *   method 0 = EQM (eqm_train + qm_adjust), 1 = QDM (eqm_train + qdm_adjust; ranks over the window when grp_sim
+ *   carries one, i.e. rank_window=True), 2 = DQM (dqm_train + dqm_adjust with PolyDetrend(detrend_degree) on the
+ *   adjustment group; grp_sim then carries the Grouper window, sim_tcoord_host the sim time coordinate in days).
+ * grp_train carries the Grouper window of the training step; grp_sim describes the sim time axis.
+ * State: none.  The staging buffers live in a caller-owned DEVICE workspace of at least
+ * xsdba_qm_train_adjust_host_workspace_bytes(...) bytes (any device allocation, e.g. a torch tensor); concurrent
+ * calls need distinct workspaces.  xsdba_qm_train_adjust_host_f32 is the convenience form (EQM / QDM, float32) that
+ * allocates and frees its workspace itself.
  */
+int64_t xsdba_qm_train_adjust_host_workspace_bytes(int64_t n_pts, const xsdba_grouping_t* grp_train,
+                                                   const xsdba_grouping_t* grp_sim, int32_t nq, int32_t elem_size,
+                                                   int32_t method, int64_t slab_pts);
+int xsdba_qm_train_adjust_host_ws_f32(const float* ref_host, const float* hist_host, const float* sim_host,
+                                      int64_t n_pts, const xsdba_grouping_t* grp_train,
+                                      const xsdba_grouping_t* grp_sim, const float* q_host, int32_t nq, int32_t kind,
+                                      int32_t method, int32_t interp, int32_t extrap, int32_t detrend_degree,
+                                      const double* sim_tcoord_host, float* scen_host, float* af_host,
+                                      float* hist_q_host, float* scaling_host, int64_t slab_pts, void* workspace_dev,
+                                      int64_t workspace_bytes);
+int xsdba_qm_train_adjust_host_ws_f64(const double* ref_host, const double* hist_host, const double* sim_host,
+                                      int64_t n_pts, const xsdba_grouping_t* grp_train,
+                                      const xsdba_grouping_t* grp_sim, const double* q_host, int32_t nq, int32_t kind,
+                                      int32_t method, int32_t interp, int32_t extrap, int32_t detrend_degree,
+                                      const double* sim_tcoord_host, double* scen_host, double* af_host,
+                                      double* hist_q_host, double* scaling_host, int64_t slab_pts,
+                                      void* workspace_dev, int64_t workspace_bytes);
 int xsdba_qm_train_adjust_host_f32(const float* ref_host, const float* hist_host, const float* sim_host,
                                    int64_t n_pts, const xsdba_grouping_t* grp_train,
                                    const xsdba_grouping_t* grp_sim, const float* q_host, int32_t nq,

@@ -9,7 +9,8 @@ from xsdba_b200 import _lib
 
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 48
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-with_adjust = len(sys.argv) > 3
+with_adjust = len(sys.argv) > 3 and sys.argv[3] in ("adjust", "fresh")
+fresh = len(sys.argv) > 3 and sys.argv[3] == "fresh"   # regenerate the inputs before every repetition, like bench.py
 dev = torch.device("cuda", 0)
 lib = _lib.load()
 tt = xs.TimeAxis.daily(1981, 30, "noleap"); ts = xs.TimeAxis.daily(2041, 30, "noleap")
@@ -25,6 +26,9 @@ af = torch.empty((n, 12, 50), device=dev); hq = torch.empty_like(af); scen = tor
 s = torch.cuda.current_stream().cuda_stream
 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 for i in range(reps):
+    if fresh and i:
+        del ref, hist, sim
+        ref, hist, sim = (bench.synth_slab(torch, gen, T, rows, 300 + i, w, doy, year, dev) for w in ("ref", "hist", "sim"))
     e0.record()
     _lib.check(lib.xsdba_qm_train_f32(ref.data_ptr(), hist.data_ptr(), n, 1, n, ht.ptr, q.data_ptr(), 50, 43, 0,
                                       af.data_ptr(), hq.data_ptr(), None, s))

@@ -565,6 +565,23 @@ def test_adapt_freq_adjust_and_tail_factor():
         n_ora += (sa != sim[sel].T).sum() - np.isnan(sim[sel]).sum()
         n_gpu += (ad[sel] != sim[sel]).sum() - np.isnan(sim[sel]).sum()
     assert abs(n_gpu - n_ora) < 0.03 * n_ora
+    # the tied (dry) values take DISTINCT positions of their tie block (a permutation, like the reference's random
+    # tie-break followed by a re-rank), so the number of replaced values of every (point, group) is deterministic:
+    # the count of sorted positions r with  P0_ref / P0_hist * P0_sim <= r / (n - 1) <= P0_sim
+    for g in range(G):
+        sel = gidx == g
+        for p in range(sim.shape[1]):
+            x = sim[sel, p]
+            x = x[~np.isnan(x)]
+            n = x.size
+            dp0 = (p0h[p, g] - p0r[p, g]) / p0h[p, g] if p0h[p, g] else np.nan
+            if not (dp0 > 0) or n < 2:
+                continue
+            p0s = (x <= 0.05).sum() / n
+            rk = np.arange(n) / (n - 1)
+            expect = int((~((rk < (p0r[p, g] / p0h[p, g]) * p0s) | (rk > p0s))).sum())
+            got = int((ad[sel, p] != sim[sel, p]).sum() - np.isnan(sim[sel, p]).sum())
+            assert got == expect, (g, p, got, expect)
     # max_tail_factor: values above 1.5 x the last raw hist quantile are passed through un-adjusted
     hq_raw = _np(obj.ds["hist_q_raw"])
     lastq = hq_raw[:, gidx, -1].T                                                       # (time, points)

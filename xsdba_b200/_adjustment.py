@@ -59,8 +59,15 @@ def _as_device(x, dtype=None):
     return x
 
 
+class _Series(tuple):
+    """(tensor, n_pts, stride_pt, stride_time, points_shape) plus ``.axis``: the resolved time axis of the tensor (0 or
+    -1), so that outputs are labelled by what was done rather than by what the strides suggest -- a (T, 1) array has
+    stride_time == n_pts == 1 and is still time-major."""
+    axis = 0
+
+
 def _series(x, time_axis, n_time, dtype=None):
-    """-> (tensor, n_pts, stride_pt, stride_time, points_shape)."""
+    """-> (tensor, n_pts, stride_pt, stride_time, points_shape), with ``.axis``."""
     x = _as_device(x, dtype)
     if x.dtype not in (torch.float32, torch.float64):
         x = x.to(torch.float32)
@@ -74,10 +81,14 @@ def _series(x, time_axis, n_time, dtype=None):
     if ax == 0:
         pts_shape = tuple(x.shape[1:])
         n_pts = int(np.prod(pts_shape)) if pts_shape else 1
-        return x, n_pts, 1, n_pts, pts_shape
+        out = _Series((x, n_pts, 1, n_pts, pts_shape))
+        out.axis = 0
+        return out
     pts_shape = tuple(x.shape[:-1])
     n_pts = int(np.prod(pts_shape)) if pts_shape else 1
-    return x, n_pts, n_time, 1, pts_shape
+    out = _Series((x, n_pts, n_time, 1, pts_shape))
+    out.axis = -1
+    return out
 
 
 def _widest(*xs):
@@ -261,7 +272,8 @@ def qm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None,
     lib = _lib.load()
     time = ds.time
     dt = _widest(ds["sim"], ds["af"])
-    sim, n_pts, sp, st, pshape = _series(ds["sim"], ds.time_axis, len(time), dt)
+    ser = _series(ds["sim"], ds.time_axis, len(time), dt)
+    sim, n_pts, sp, st, pshape = ser
     h = group.handle(time, with_window=False)
     af, hq = _tables(ds, n_pts, h.n_groups, dt, ("af", "hist_q"))
     nq = af.shape[-1]
@@ -274,7 +286,7 @@ def qm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None,
     _lib.check(status, "qm_adjust")
     if max_tail_factor is not None:
         scen = _apply_tail_mask(ds, sim, scen, n_pts, sp, st, group, time, dt, max_tail_factor)
-    return Dataset({"scen": scen}, time=time, time_axis=0 if st != 1 or sim.ndim == 1 else -1)
+    return Dataset({"scen": scen}, time=time, time_axis=ser.axis)
 
 
 _GEOM_CACHE: dict = {}
@@ -288,7 +300,7 @@ def _qdm_linear_geometry(group, time, q, n_groups):
     if group.prop not in ("month", "dayofyear"):
         raise NotImplementedError(f"linear interpolation over time.{group.prop} groups is not built yet")
     qn = q.detach().cpu().numpy().astype(np.float64)
-    key = (group.prop, n_groups, qn.tobytes())
+    key = (group.prop, n_groups, qn.tobytes(), torch.cuda.current_device())
     if key not in _GEOM_CACHE:
         from scipy.spatial import Delaunay  # SciPy is the reference's own dependency for this step
         gg = np.arange(n_groups + 2, dtype=np.float64)
@@ -324,7 +336,12 @@ def qdm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None
     lib = _lib.load()
     time = ds.time
     dt = _widest(ds["sim"], ds["af"])
-    sim, n_pts, sp, st, pshape = _series(ds["sim"], ds.time_axis, len(time), dt)
+    ser = _series(ds["sim"], ds.time_axis, len(time), dt)
+    sim, n_pts, sp, st, pshape = ser
+    if max_tail_factor is not None and interp != "nearest" and group.prop in ("month", "season"):
+        # the reference interpolates the last raw quantile between months for the mask (_adjustment.py:847-858,
+        # u.broadcast(..., interp=interp)); only the nearest-group broadcast is built here
+        raise NotImplementedError("max_tail_factor with a month-interpolated last quantile is not built yet")
     h = group.handle(time, with_window=bool(rank_window))
     (af,) = _tables(ds, n_pts, h.n_groups, dt, ("af",))
     q = _as_device(ds["quantiles"], dt).contiguous()
@@ -349,7 +366,7 @@ def qdm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None
     _lib.check(status, "qdm_adjust")
     if max_tail_factor is not None:
         scen = _apply_tail_mask(ds, sim, scen, n_pts, sp, st, group, time, dt, max_tail_factor)
-    return Dataset({"scen": scen, "sim_q": sim_q}, time=time, time_axis=0 if st != 1 or sim.ndim == 1 else -1)
+    return Dataset({"scen": scen, "sim_q": sim_q}, time=time, time_axis=ser.axis)
 
 
 def group_rank(x, *, time, group, rank_window=False, time_axis=0):
@@ -427,7 +444,9 @@ def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_
     lib = _lib.load()
     time = ds.time
     dt = _widest(ds["sim"], ds["af"])
-    sim, n_pts, sp, st, pshape = _series(ds["sim"], ds.time_axis, len(time), dt)
+    ser = _series(ds["sim"], ds.time_axis, len(time), dt)
+    sim, n_pts, sp, st, pshape = ser
+    ta = ser.axis
     h = group.handle(time)
     af, hq = _tables(ds, n_pts, h.n_groups, dt, ("af", "hist_q"))
     scaling = _as_device(ds["scaling"], dt).contiguous()
@@ -443,13 +462,12 @@ def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_
     if isinstance(detrend, PolyDetrend):
         trend = poly_trend(sim, time=time, group=detrend.group, degree=detrend.degree, kind=kind,
                            scaling=scaling if detrend.group.name == group.name and detrend.group.window == group.window else None,
-                           time_axis=0 if st != 1 or sim.ndim == 1 else -1)
+                           time_axis=ta)
         if not (detrend.group.name == group.name and detrend.group.window == group.window):
             raise NotImplementedError("a PolyDetrend with a group different from the adjustment group is not built yet")
     elif isinstance(detrend, LoessDetrend):
         trend = loess_trend(sim, time=time, f=detrend.f, niter=detrend.niter, d=detrend.d, kind=kind, scaling=scaling,
-                            scaling_group=group, loess_group=detrend.group,
-                            time_axis=0 if st != 1 or sim.ndim == 1 else -1)
+                            scaling_group=group, loess_group=detrend.group, time_axis=ta)
     else:
         raise TypeError("detrend must be an int, a PolyDetrend or a LoessDetrend")
     nq = af.shape[-1]
@@ -461,7 +479,6 @@ def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_
     _lib.check(status, "dqm_adjust")
     if max_tail_factor is not None:     # _adjustment.py:734-746, 776-777
         scen = _apply_tail_mask(ds, adapted, scen, n_pts, sp, st, group, time, dt, max_tail_factor)
-    ta = 0 if st != 1 or sim.ndim == 1 else -1
     return Dataset({"scen": scen, "trend": trend}, time=time, time_axis=ta)
 
 

@@ -67,6 +67,10 @@ SIGNATURES["xsdba_qm_train_q64_f32"] = (C.c_int, [vp, vp, i64, i64, i64, vp, vp,
 SIGNATURES["xsdba_debug_copy_rows_f32"] = (C.c_int, [vp, i64, i64, vp, vp, i32, vp])
 SIGNATURES["xsdba_qm_train_adjust_host_f32"] = (
     C.c_int, [vp, vp, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, i64])
+SIGNATURES["xsdba_qm_train_adjust_host_workspace_bytes"] = (i64, [i64, vp, vp, i32, i32, i32, i64])
+for _t in ("f32", "f64"):
+    SIGNATURES[f"xsdba_qm_train_adjust_host_ws_{_t}"] = (
+        C.c_int, [vp, vp, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, c_f64p, vp, vp, vp, vp, i64, vp, i64])
 
 
 class XsdbaB200Error(RuntimeError):

@@ -110,32 +110,67 @@ class DetrendedQuantileMapping(_TrainAdjust):
                              max_tail_factor=self.max_tail_factor)["scen"]
 
 
+_WORKSPACES = __import__("threading").local()   # caller-owned device workspaces, one per (host thread, device)
+
+
+def _host_workspace(nbytes: int):
+    import torch
+    dev = torch.cuda.current_device()
+    cache = getattr(_WORKSPACES, "cache", None)
+    if cache is None:
+        cache = _WORKSPACES.cache = {}
+    ws = cache.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        cache[dev] = ws = None            # release before growing
+        cache[dev] = ws = torch.empty(int(nbytes), dtype=torch.uint8, device=torch.device("cuda", dev))
+    return ws
+
+
 def train_adjust_host(ref: np.ndarray, hist: np.ndarray, sim: np.ndarray, *, time, sim_time, nquantiles=50,
                       group="time.month", window=1, kind="+", method="eqm", interp="nearest",
-                      extrapolation="constant", slab_points=16384, out=None, return_tables=False):
-    """EQM / QDM train + adjust on HOST (numpy, time-major ``(time, *points)``, float32) arrays through
-    the C ABI's end-to-end entry point: slabs of points are streamed H2D -> kernels -> D2H on two streams.
-    This is the call the xarray-facing Adjustment classes make for in-memory data."""
+                      extrapolation="constant", detrend=1, rank_window=False, slab_points=16384, out=None,
+                      return_tables=False):
+    """EQM / QDM / DQM train + adjust on HOST (numpy, time-major ``(time, *points)``, float32 or float64) arrays
+    through the C ABI's end-to-end entry point: slabs of points are streamed H2D -> kernels -> D2H on three streams.
+    This is the call the xarray-facing Adjustment classes make for in-memory data.  The device staging workspace is
+    owned by this (host thread, device) and reused between calls; ``detrend`` is the PolyDetrend degree of DQM."""
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.XsdbaB200Error("xsdba_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     lib = _lib.load()
     group = parse_group(group, window)
+    dt = ref.dtype
+    if dt not in (np.float32, np.float64):
+        raise ValueError("train_adjust_host takes float32 or float64 arrays")
     for a in (ref, hist, sim):
-        if a.dtype != np.float32 or not a.flags.c_contiguous:
-            raise ValueError("train_adjust_host takes C-contiguous float32 arrays")
+        if a.dtype != dt or not a.flags.c_contiguous:
+            raise ValueError("train_adjust_host takes C-contiguous arrays of one dtype")
     pshape = ref.shape[1:]
     n_pts = int(np.prod(pshape)) if pshape else 1
     if ref.shape[0] != len(time) or hist.shape != ref.shape or sim.shape[0] != len(sim_time) or sim.shape[1:] != pshape:
         raise ValueError("shape mismatch between ref / hist / sim and their time coordinates")
+    m = {"eqm": 0, "qdm": 1, "dqm": 2}[method]
     ht = group.handle(time)
-    hs = group.handle(sim_time, with_window=False)
-    q = equally_spaced_nodes(nquantiles).astype(np.float32) if np.isscalar(nquantiles) else np.asarray(nquantiles, np.float32)
+    hs = group.handle(sim_time, with_window=(m == 2) or (m == 1 and bool(rank_window)))
+    q = equally_spaced_nodes(nquantiles).astype(dt) if np.isscalar(nquantiles) else np.asarray(nquantiles, dt)
     scen = np.empty_like(sim) if out is None else out
-    af = hq = None
+    af = hq = sc = None
     if return_tables:
-        af = np.empty(pshape + (ht.n_groups, q.size), np.float32)
+        af = np.empty(pshape + (ht.n_groups, q.size), dt)
         hq = np.empty_like(af)
+        sc = np.empty(pshape + (ht.n_groups,), dt) if m == 2 else None
+    tc = np.ascontiguousarray(sim_time.ordinal, np.float64) if m == 2 else None
     p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
-    st = lib.xsdba_qm_train_adjust_host_f32(p(ref), p(hist), p(sim), n_pts, ht.ptr, hs.ptr, p(q), q.size,
-                                            _lib.KIND[kind], {"eqm": 0, "qdm": 1}[method], _lib.INTERP[interp],
-                                            _lib.EXTRAP[extrapolation], p(scen), p(af), p(hq), int(slab_points))
+    es = 4 if dt == np.float32 else 8
+    nbytes = lib.xsdba_qm_train_adjust_host_workspace_bytes(n_pts, ht.ptr, hs.ptr, q.size, es, m, int(slab_points))
+    if nbytes < 0:
+        _lib.check(int(nbytes), "train_adjust_host workspace")
+    ws = _host_workspace(nbytes)
+    fn = lib.xsdba_qm_train_adjust_host_ws_f32 if dt == np.float32 else lib.xsdba_qm_train_adjust_host_ws_f64
+    st = fn(p(ref), p(hist), p(sim), n_pts, ht.ptr, hs.ptr, p(q), q.size, _lib.KIND[kind], m, _lib.INTERP[interp],
+            _lib.EXTRAP[extrapolation], int(detrend), None if tc is None else tc.ctypes.data_as(_lib.c_f64p), p(scen),
+            p(af), p(hq), p(sc), int(slab_points), ws.data_ptr(), ws.numel())
     _lib.check(st, "train_adjust_host")
-    return (scen, af, hq) if return_tables else scen
+    if return_tables:
+        return (scen, af, hq, sc) if m == 2 else (scen, af, hq)
+    return scen

@@ -34,19 +34,23 @@ class GroupingHandle:
 
 
 _HANDLES: "OrderedDict[tuple, GroupingHandle]" = OrderedDict()
+_HANDLES_LOCK = __import__("threading").Lock()   # dask may call blocks from several threads (base.py:715)
 
 
 def grouping_handle(gidx: np.ndarray, n_groups: int, window: int) -> GroupingHandle:
-    key = (gidx.astype(np.int32).tobytes(), int(n_groups), int(window))
-    h = _HANDLES.get(key)
-    if h is None:
-        h = GroupingHandle(gidx, n_groups, window)
-        _HANDLES[key] = h
-        while len(_HANDLES) > 16:
-            _HANDLES.popitem(last=False)
-    else:
-        _HANDLES.move_to_end(key)
-    return h
+    import torch
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else -1   # the tables live on one device
+    key = (gidx.astype(np.int32).tobytes(), int(n_groups), int(window), dev)
+    with _HANDLES_LOCK:
+        h = _HANDLES.get(key)
+        if h is None:
+            h = GroupingHandle(gidx, n_groups, window)
+            _HANDLES[key] = h
+            while len(_HANDLES) > 16:
+                _HANDLES.popitem(last=False)
+        else:
+            _HANDLES.move_to_end(key)
+        return h
 
 
 class Grouper:

@@ -2057,12 +2057,32 @@ adapt_apply_kernel(const T* __restrict__ sim, long long n_pts, long long sp, lon
       hi = n;
       while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[(size_t)mid * C] <= x) lo = mid + 1; else hi = mid; }
       const int ub = lo;
-      // random tie-break: a uniformly drawn position inside the tie block (utils.py:618-627)
+      // Random tie-break (utils.py:618-627: ranks of the values plus a small noise, i.e. the tied values take the
+      // positions lb .. ub-1 in a random order -- a permutation, every position exactly once).  The position of
+      // this sample inside its tie block is its rank among the tied samples ordered by their hash draw (then by
+      // address); it only matters when the block straddles a keep / replace boundary, which is checked first.
       const unsigned long long id = (unsigned long long)o;
-      int r0 = lb + (int)(hash_uniform(seed, 2 * id) * (double)(ub - lb));
-      r0 = r0 > ub - 1 ? ub - 1 : r0;
-      const double rnk = (double)r0 / (double)(n - 1);
-      const bool keep = (rnk < (p0r / p0h) * p0s) || (rnk > p0s);
+      const double lim_lo = (p0r / p0h) * p0s;
+      auto kept = [&](int r) { const double rk = (double)r / (double)(n - 1); return (rk < lim_lo) || (rk > p0s); };
+      bool keep = kept(lb);
+      bool mixed = ub - lb > 1 && kept(ub - 1) != keep;
+      if (!mixed && keep && ub - lb > 2) {
+        // both ends kept: the block may still contain the whole replaced interval [lim_lo, P0_sim] (the rule is
+        // "replace" on one interval of positions, so two replaced ends do prove a replaced middle)
+        const int r_first = (int)ceil(lim_lo * (double)(n - 1));
+        mixed = r_first > lb && r_first < ub - 1 && !kept(r_first);
+      }
+      if (mixed) {
+        const double h_me = hash_uniform(seed, 2 * id);
+        int before = 0;
+        for (int m2 = 0; m2 < n_mem; ++m2) {
+          const long long o2 = pt * sp + (long long)mem_rows[m0 + m2] * st;
+          if (o2 == o || !(sim[o2] == x)) continue;
+          const double h2 = hash_uniform(seed, 2 * (unsigned long long)o2);
+          before += (h2 < h_me || (h2 == h_me && o2 < o)) ? 1 : 0;
+        }
+        keep = kept(lb + before);
+      }
       if (!keep) res = (T)(((double)pth[og] - thresh) * (double)(T)hash_uniform(seed, 2 * id + 1) + thresh);
     }
     out[o] = res;
@@ -2213,16 +2233,39 @@ template <typename K> int set_smem(K kernel, size_t bytes) {
 // Scratch buffers come from the device's stream-ordered pool (cudaMallocAsync).  Its default release threshold of 0
 // hands the memory back to the driver at every synchronisation, which costs milliseconds per call (tens for the
 // gigabyte-sized LOESS scratch): keep it.  Called by every launcher that allocates scratch.
+// The threshold is set once per DEVICE (a process may drive several) and is bounded: up to 8 GiB of freed scratch
+// stays in the pool, anything above goes back to the driver so that other allocators of the process (PyTorch's caching
+// allocator does not draw from this pool) are not starved after one large call.  xsdba_trim_pool() returns the rest.
 void keep_pool_memory() {
-  static std::atomic<int> pool_ready{0};
-  if (pool_ready.exchange(1)) return;
+  static std::atomic<int> pool_ready[64];
   int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return; }
+  if (pool_ready[dev].exchange(1)) return;
   cudaMemPool_t pool;
-  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-    uint64_t thr = UINT64_MAX;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = 8ull << 30;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   cudaGetLastError();
+}
+
+// number of SMs of the current device (grid sizing of the grid-stride kernels)
+int sm_count() {
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return 148; }
+  int n = cached[dev].load();
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+    cached[dev].store(n);
+  }
+  return n;
+}
+
+// every launcher checks that the grouping handle lives on the current device
+inline bool wrong_device(const xsdba_grouping* grp) {
+  int dev = -1;
+  return grp && (cudaGetDevice(&dev) != cudaSuccess || dev != grp->device);
 }
 
 template <typename T, int C>
@@ -2303,6 +2346,7 @@ int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t
                  const T* q, int nq, int kind, int normalize, int mode, T* af, T* hq, T* scaling, void* stream,
                  const double* jitter = nullptr, unsigned long long seed = 0, const double* q64 = nullptr,
                  const AdaptParams* adapt = nullptr) {
+  if (wrong_device(grp)) return XSDBA_ERR_INVALID_ARGUMENT;  // the handle's tables live on another device
   int fast_rc = 0;
   JitterParams jp;
   const double dnan = __builtin_nan("");
@@ -2363,15 +2407,19 @@ bool launch_adjust_tile_t(const float* sim, int64_t n_pts, int64_t sp, int64_t s
     cudaFreeAsync(packed, s);
     return false;
   }
-  cudaMemsetAsync(fix_count, 0, sizeof(unsigned), s);
+  if (cudaMemsetAsync(fix_count, 0, sizeof(unsigned), s) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFreeAsync(packed, s); cudaFreeAsync(fix, s); cudaFreeAsync(fix_count, s);
+    return false;
+  }
   pack_tables_kernel<TOP><<<dim3((unsigned)tiles, (unsigned)grp->n_groups), kThreads, smem_p, s>>>(af, hq, n_pts,
                                                                                                    grp->n_groups, nq, packed);
   adjust_tile_kernel<TOP><<<(unsigned)tiles, kThreads, smem_t, s>>>(sim, n_pts, sp, (int)st, grp->members.off,
                                                                     grp->members.rows, grp->n_groups, af, hq, nq, packed,
                                                                     extrap, kind, scen, fix, fix_count, fix_cap);
   static const bool fix_scan = getenv("XSDBA_B200_FIX_SCAN") != nullptr;  // (debug: the table-scanning second pass)
-  if (fix_scan) adjust_fix_kernel<<<148 * 4, 256, 0, s>>>(fix, fix_count, fix_cap, af, hq, grp->n_groups, nq, extrap, kind, scen);
-  else adjust_fix_packed_kernel<TOP><<<148 * 6, 256, 0, s>>>(fix, fix_count, fix_cap, packed, grp->n_groups, extrap, kind, scen);
+  if (fix_scan) adjust_fix_kernel<<<sm_count() * 4, 256, 0, s>>>(fix, fix_count, fix_cap, af, hq, grp->n_groups, nq, extrap, kind, scen);
+  else adjust_fix_packed_kernel<TOP><<<sm_count() * 6, 256, 0, s>>>(fix, fix_count, fix_cap, packed, grp->n_groups, extrap, kind, scen);
   {
     const size_t smem_g = ((tables_bytes<float, 32>(nq) + 15) & ~(size_t)15) + stage_bytes<float, 32>(nq);
     auto kern = adjust_kernel<float, 32>;
@@ -2441,6 +2489,7 @@ bool launch_adjust_narrow(const T* sim, int64_t n_pts, int64_t sp, int64_t st, c
 template <typename T>
 int launch_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* af,
                   const T* hq, int nq, int interp, int extrap, int kind, T* scen, void* stream) {
+  if (wrong_device(grp)) return XSDBA_ERR_INVALID_ARGUMENT;  // the handle's tables live on another device
   if ((n_pts > 0 && !sim) || !grp || (n_pts > 0 && !af) || (n_pts > 0 && !hq) || (n_pts > 0 && !scen) || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
   if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR) return XSDBA_ERR_INVALID_ARGUMENT;
@@ -2496,6 +2545,7 @@ int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba
                 const T* q, int nq, int interp, int extrap, int kind, int rank_window, int do_adjust, T* scen,
                 double* sim_q, void* stream, int rank_mode = 0, const double* gcoord = nullptr,
                 const unsigned char* diag = nullptr) {
+  if (wrong_device(grp)) return XSDBA_ERR_INVALID_ARGUMENT;  // the handle's tables live on another device
   if ((n_pts > 0 && !sim) || !grp || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (do_adjust) {
     if ((n_pts > 0 && !af) || (n_pts > 0 && !q) || (n_pts > 0 && !scen) || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
@@ -2537,6 +2587,7 @@ int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba
 template <typename T>
 int launch_poly_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* scaling,
                       int kind, int degree, const double* tcoord, double* trend, void* stream) {
+  if (wrong_device(grp)) return XSDBA_ERR_INVALID_ARGUMENT;  // the handle's tables live on another device
   if ((n_pts > 0 && !x) || !grp || (n_pts > 0 && !tcoord) || (n_pts > 0 && !trend) || n_pts < 0 || degree < 0 || degree > kMaxDeg) return XSDBA_ERR_INVALID_ARGUMENT;
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
   if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
@@ -2553,6 +2604,7 @@ template <typename T>
 int launch_dqm_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* af,
                       const T* hq, const T* scaling, const double* trend, int nq, int interp, int extrap, int kind,
                       T* scen, void* stream) {
+  if (wrong_device(grp)) return XSDBA_ERR_INVALID_ARGUMENT;  // the handle's tables live on another device
   if ((n_pts > 0 && !sim) || !grp || (n_pts > 0 && !af) || (n_pts > 0 && !hq) || (n_pts > 0 && !scaling) || (n_pts > 0 && !trend) || (n_pts > 0 && !scen) || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
   if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR) return XSDBA_ERR_INVALID_ARGUMENT;
@@ -2719,6 +2771,7 @@ loess_delta_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, con
 template <typename T>
 int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* scaling,
                        int kind, double f, int niter, int degree, const double* xn, double* trend, void* stream) {
+  if (wrong_device(grp)) return XSDBA_ERR_INVALID_ARGUMENT;  // the handle's tables live on another device
   if ((n_pts > 0 && !x) || !grp || (n_pts > 0 && !xn) || (n_pts > 0 && !trend) || n_pts < 0 || !(f > 0.0) || degree < 0 || degree > 1) return XSDBA_ERR_INVALID_ARGUMENT;
   if (niter < 1) return XSDBA_ERR_INVALID_ARGUMENT;
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
@@ -2765,7 +2818,7 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
     if (n_time >= R_ && n_time > 2 * HW_ + 2 &&
         cudaMallocAsync(&etab, sizeof(double) * (size_t)R_ * NI_ + sizeof(double) * NI_, s) == cudaSuccess) {
       esum = etab + (size_t)R_ * NI_;
-      loess_edge_table_kernel<<<148 * 8, kThreads, 0, s>>>(xn, n_time, f, etab);
+      loess_edge_table_kernel<<<sm_count() * 8, kThreads, 0, s>>>(xn, n_time, f, etab);
       loess_edge_sum_kernel<<<(unsigned)((NI_ + 127) / 128), 128, 0, s>>>(n_time, f, etab, esum);
       g_launches += 2;
     } else {
@@ -2833,7 +2886,7 @@ int launch_jitter(const T* x, int64_t n, const double* j4, uint64_t seed, T* out
   if ((n > 0 && !x) || (n > 0 && !out) || (n > 0 && !j4) || n < 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (n == 0) return XSDBA_OK;
   JitterParams jp{j4[0], j4[1], j4[2], j4[3], seed};
-  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 16);
   jitter_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, jp, out);
   ++g_launches;
   return cuda_status(cudaGetLastError());
@@ -2855,6 +2908,7 @@ int launch_reorder_c(const T* sim, const T* ref, int64_t n_pts, int64_t sp, int6
 template <typename T>
 int launch_reorder(const T* sim, const T* ref, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, T* out,
                    void* stream) {
+  if (wrong_device(grp)) return XSDBA_ERR_INVALID_ARGUMENT;  // the handle's tables live on another device
   if ((n_pts > 0 && !sim) || (n_pts > 0 && !ref) || !grp || (n_pts > 0 && !out) || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
   if (n_pts == 0) return XSDBA_OK;
@@ -2886,6 +2940,7 @@ int launch_select_c(const T* x, const T* y, int64_t n_pts, int64_t sp, int64_t s
 template <typename T>
 int launch_select(const T* x, const T* y, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, int mode,
                   const T* rnk, const double* yvals, int nv, T* out, void* stream) {
+  if (wrong_device(grp)) return XSDBA_ERR_INVALID_ARGUMENT;  // the handle's tables live on another device
   if ((n_pts > 0 && !x) || !grp || (n_pts > 0 && !out) || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (mode == 0 && !rnk) return XSDBA_ERR_INVALID_ARGUMENT;
   if (mode == 1 && (!y || !yvals || nv <= 0)) return XSDBA_ERR_INVALID_ARGUMENT;
@@ -2920,6 +2975,7 @@ int launch_adapt_apply_c(const T* sim, int64_t n_pts, int64_t sp, int64_t st, co
 template <typename T>
 int launch_adapt_apply(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, double thresh,
                        const double* p0r, const double* p0h, const T* pth, unsigned long long seed, T* out, void* stream) {
+  if (wrong_device(grp)) return XSDBA_ERR_INVALID_ARGUMENT;  // the handle's tables live on another device
   if ((n_pts > 0 && !sim) || !grp || (n_pts > 0 && !p0r) || (n_pts > 0 && !p0h) || (n_pts > 0 && !pth) || (n_pts > 0 && !out) || n_pts < 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
   if (n_pts == 0) return XSDBA_OK;
@@ -2937,11 +2993,12 @@ int launch_adapt_apply(const T* sim, int64_t n_pts, int64_t sp, int64_t st, cons
 template <typename T>
 int launch_tail_mask(const T* adapted, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* hq_raw,
                      int nq, double factor, T* scen, void* stream) {
+  if (wrong_device(grp)) return XSDBA_ERR_INVALID_ARGUMENT;  // the handle's tables live on another device
   if ((n_pts > 0 && !adapted) || !grp || (n_pts > 0 && !hq_raw) || (n_pts > 0 && !scen) || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (sp != 1 && st != 1) return XSDBA_ERR_UNSUPPORTED;
   if (n_pts == 0) return XSDBA_OK;
   const int64_t total = n_pts * grp->n_time;
-  const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 32);
+  const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 32);
   tail_mask_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(adapted, n_pts, sp, st, (int)grp->n_time, grp->gidx,
                                                                 grp->n_groups, hq_raw, nq, factor, scen);
   ++g_launches;
@@ -2974,7 +3031,7 @@ int launch_rotate(const T* x, int64_t n_elem, int n_var, const float* rot_host, 
   RotMat R;
   for (int v = 0; v < kMaxVar; ++v) for (int w = 0; w < kMaxVar; ++w)
     R.r[v * kMaxVar + w] = (v < n_var && w < n_var) ? rot_host[v * n_var + w] : 0.f;
-  const unsigned blocks = (unsigned)std::min<int64_t>((n_elem + 255) / 256, 148 * 32);
+  const unsigned blocks = (unsigned)std::min<int64_t>((n_elem + 255) / 256, (int64_t)sm_count() * 32);
   if (fused) rotate_kernel<T, true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n_elem, n_var, R, y);
   else rotate_kernel<T, false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n_elem, n_var, R, y);
   ++g_launches;
