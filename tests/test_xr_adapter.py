@@ -150,8 +150,9 @@ def test_adapter_end_to_end_matches_oracle(dt):
     out = A.dqm_adjust(trd.drop_vars(["P0_ref", "P0_hist", "pth"]).assign(sim=da(sim, ("time", "lat", "lon"))), group=grp,
                        interp="nearest", extrapolation="constant", kind="+", detrend=1)
     assert out["scen"].dims == ("time", "lat", "lon") and out["trend"].shape == out["scen"].shape
-    poly = types.SimpleNamespace(parameters={"degree": 1, "kind": "+", "group": grp})
-    poly.__class__ = type("PolyDetrend", (), {})
+    class PolyDetrend:   # what a reference detrend object looks like from outside: class name + parameters dict
+        parameters = {"degree": 1, "kind": "+", "group": grp}
+    poly = PolyDetrend()
     out2 = A.dqm_adjust(trd.drop_vars(["P0_ref", "P0_hist", "pth"]).assign(sim=da(sim, ("time", "lat", "lon"))), group=grp,
                         interp="nearest", extrapolation="constant", kind="+", detrend=poly)
     assert bits_equal(out2["scen"].values, out["scen"].values)
