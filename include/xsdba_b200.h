@@ -299,6 +299,14 @@ int xsdba_qm_train_adjust_host_f32(const float* ref_host, const float* hist_host
 int xsdba_qm_train_q64_f32(const float* ref_dev, const float* hist_dev, int64_t n_pts, int64_t stride_pt,
                            int64_t stride_time, const xsdba_grouping_t* grp, const double* q64_dev, int32_t nq,
                            int32_t kind, float* af_dev, float* hist_q_dev, void* cuda_stream);
+/* One variable of one N-pdf iteration, fused (float32 series, one group = one block of time steps):
+ *   ref_dev != NULL (_npdft_train, _adjustment.py:313-324): af = quantile(ref) - quantile(x) at the float64 nodes is
+ *   WRITTEN to af_io_dev [n_pts][nq], then x += interp1d(rank_bn(x), q, af) in place;
+ *   ref_dev == NULL (_npdft_adjust, _adjustment.py:451-460): af is READ from af_io_dev, x updated in place.
+ * The lookup and the sum run in float64 like the reference's (float64 af_q and nodes), the keys stay float32. */
+int xsdba_npdft_step_f32(const float* ref_dev, float* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                         const xsdba_grouping_t* grp, const double* q64_dev, int32_t nq, int32_t interp,
+                         int32_t extrap, float* af_io_dev, void* cuda_stream);
 int xsdba_rank_lookup_f32(const float* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
                           const xsdba_grouping_t* grp, const float* af_dev, const float* q_dev, int32_t nq,
                           int32_t interp, int32_t extrap, int32_t kind, int32_t rank_window, int32_t rank_mode,

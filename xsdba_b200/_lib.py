@@ -64,6 +64,7 @@ for _t in ("f32", "f64"):
     SIGNATURES[f"xsdba_escore_{_t}"] = (C.c_int, [vp, vp, i64, i64, i64, i64, i64, i32, i64, i64, i32, vp, vp])
     SIGNATURES[f"xsdba_group_rank_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, i32, vp, vp])
 SIGNATURES["xsdba_qm_train_q64_f32"] = (C.c_int, [vp, vp, i64, i64, i64, vp, vp, i32, i32, vp, vp, vp])
+SIGNATURES["xsdba_npdft_step_f32"] = (C.c_int, [vp, vp, i64, i64, i64, vp, vp, i32, i32, i32, vp, vp])
 SIGNATURES["xsdba_debug_copy_rows_f32"] = (C.c_int, [vp, i64, i64, vp, vp, i32, vp])
 SIGNATURES["xsdba_qm_train_adjust_host_f32"] = (
     C.c_int, [vp, vp, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, i64])

@@ -27,6 +27,7 @@
 constexpr int kBktN = 1024;       // buckets per column
 constexpr int kBktW = kBktN / 2;  // counter words per column: bucket b lives in half b / 512 of word b % 512
 constexpr int kBktLoopMax = 64;   // largest bucket selected by counting; larger ones -> sorter fallback
+constexpr int kBktAbort = 24;     // a bucket with more keys than this (seen in the histogram) sends the tile to the sorter
 
 struct BktSmem {
   static constexpr size_t buf = 0;                                   // float    [1024][32] scattered / sorted column
@@ -162,6 +163,36 @@ __device__ __forceinline__ float bucket_quantile_node(const unsigned* __restrict
   float r = gamma >= 0.5f ? __fmaf_rn(-diff, 1.0f - gamma, right) : __fmaf_rn(diff, gamma, left);
   if (r != r) r = cmax;  // nbutils.py:146
   return r;
+}
+
+// The sorter path of one pass (heavy buckets / degenerate columns): K1f's sorting network on the 1024 keys of every
+// column in buf, quantiles from the two sorted runs.  One out-of-line copy: its register needs (32 keys per thread in
+// flight) must not leak into the allocation of the bucket path.
+struct BktOut {
+  float* af; float* hist_q; float* refq; const double* qs;
+  long long o_col; int n_items, nq, S, mode, pass, kind; bool col_ok;
+};
+__device__ __noinline__ void bucket_sorter_select(float* buf, const BktOut& o, int n, float cmin, float cmax) {
+  sort_halves_512(buf, 0);
+  const int lane = threadIdx.x & 31;
+  const float* colp = buf + lane;
+  int fb_unused = 0;
+#pragma unroll 1
+  for (int item = threadIdx.x; item < o.n_items; item += kFastThreads) {
+    const int k = item >> 5;
+    float r = Num<float>::nan();
+    if (n > 0) r = bucket_quantile_node<false>(nullptr, colp, o.qs[k], n, o.S, cmin, cmax, 0.0f, false, fb_unused);
+    if (o.mode == 1) {
+      if (o.col_ok) o.af[o.o_col + k] = r;
+    } else if (o.pass == 0) {
+      o.refq[k * 33 + lane] = r;
+    } else if (o.col_ok) {
+      const float rq = o.refq[k * 33 + lane];
+      o.hist_q[o.o_col + k] = r;
+      o.af[o.o_col + k] = o.kind == XSDBA_KIND_ADD ? __fsub_rn(rq, r) : __fdiv_rn(rq, r);
+    }
+  }
+  __syncthreads();
 }
 
 template <bool JITTER, bool NORM>
@@ -344,11 +375,29 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
     //      halves of a word are prefixed independently by the packed adds (no carry: totals <= 1024); the upper
     //      halves (buckets 512..1023) then start at the number of keys in buckets 0..511 ----------------------
     {
-      unsigned sum = 0;
+      unsigned sum = 0, mxc = 0;
 #pragma unroll
-      for (int j = 0; j < kBktW / 32; ++j) sum += hist[(warp * (kBktW / 32) + j) * 32 + lane];
+      for (int j = 0; j < kBktW / 32; ++j) {
+        const unsigned w = hist[(warp * (kBktW / 32) + j) * 32 + lane];
+        sum += w;
+        // largest bucket of the column, the two single-valued buckets (0: column minimum, 1023: +inf keys) aside
+        const unsigned lo = (warp == 0 && j == 0) ? 0u : (w & 0xffffu);
+        const unsigned hi = (warp == 31 && j == kBktW / 32 - 1) ? 0u : (w >> 16);
+        mxc = max(mxc, max(lo, hi));
+      }
       tot[warp * 32 + lane] = sum;
-      __syncthreads();
+      // Heavy buckets (ties away from the minimum, multi-scale data such as jittered precipitation) or a degenerate
+      // column: selecting inside such buckets would cost more than sorting, so the whole tile goes to K1f's sorter
+      // now -- keys stored in slot order, no prefix, no scatter.  (The barrier is the one the prefix needs anyway.)
+      if (__syncthreads_or((mxc > (unsigned)kBktAbort || degenerate) ? 1 : 0)) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) buf[(warp + 32 * i) * 32 + lane] = v[i];
+        __syncthreads();
+        const BktOut bo{af, hist_q, refq, qs, (n0 + lane) * out_stride + (long long)g * nq, n_items, nq, S, mode, pass, kind,
+                        col_ok};
+        bucket_sorter_select(buf, bo, n, cmin, cmax);
+        continue;
+      }
       if (warp == 0) {  // one warp scans the 32 chunk totals of every column
         unsigned all = 0;  // (two sweeps over shared memory: 32 more registers next to v[] would spill)
 #pragma unroll 8
@@ -409,25 +458,8 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
     if (__syncthreads_or(fb)) {
       // a bucket too large to select from (heavy ties, multi-scale data) or a degenerate column: the scattered
       // column holds all 1024 keys (valid values, then +inf) -- run K1f's sorter on it, select from the two runs
-      sort_halves_512(buf, 0);
-#pragma unroll 1
-      for (int item = tid; item < n_items; item += kFastThreads) {
-        const int k = item >> 5;
-        float r = fnan;
-        if (n > 0) r = bucket_quantile_node<false>(endp, colp, qs[k], n, S, cmin, cmax, scale, degenerate, fb);
-        if (mode == 1) {
-          if (col_ok) af[o_col + k] = r;
-        } else if (pass == 0) {
-          refq[k * 33 + lane] = r;
-        } else if (col_ok) {
-          const float rq = refq[k * 33 + lane];
-          hist_q[o_col + k] = r;
-          af[o_col + k] = kind == XSDBA_KIND_ADD ? __fsub_rn(rq, r) : __fdiv_rn(rq, r);
-        }
-      }
-      __syncthreads();
-      // (reloaded rather than kept: the sorter needs the registers, and a value that is live across this branch
-      //  would be spilled on every path)
+      const BktOut bo{af, hist_q, refq, qs, o_col, n_items, nq, S, mode, pass, kind, col_ok};
+      bucket_sorter_select(buf, bo, n, cmin, cmax);
       }
   }
   if (normalize && mode == 0 && scaling && tid < 32 && n0 + tid < n_pts) {

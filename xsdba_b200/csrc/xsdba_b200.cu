@@ -2206,6 +2206,119 @@ __global__ void jitter_kernel(const T* __restrict__ x, long long n, JitterParams
     out[i] = jitter_value<T>(x[i], jp, (unsigned long long)i);
 }
 
+
+// =============================================================================================
+// K7n: one variable of one N-pdf iteration, fused (float32 data, one "time" group per block of time steps).
+//   train  (ref given):   ref_q, hist_q = quantiles at the float64 nodes (nbutils._quantile, _adjustment.py:315),
+//                         af = ref_q - hist_q (:316), hist += interp1d(rank_bn(hist), q, af) (:317-324)
+//   adjust (ref == NULL): x += interp1d(rank_bn(x), q, af) with the stored af (_adjustment.py:453-460)
+// The reference runs the lookup in float64 (af_q is a float64 array, the nodes are float64) and stores the sum
+// into the float32 series.  Before this kernel the step took three launches and three segment sorts (ref, hist,
+// and hist again, as float64, for the ranks); here the sorted hist serves quantiles and ranks, the keys stay
+// float32 (exact: the data are float32) and only the tables are float64.  grid = ceil(n_pts / C), C columns per CTA.
+// =============================================================================================
+template <int C>
+__global__ void __launch_bounds__(threads_for_cols<C>())
+npdft_step_kernel(const float* __restrict__ ref, float* __restrict__ hist, long long n_pts, long long sp, long long st,
+                  const int32_t* __restrict__ seg_rows, int S, const double* __restrict__ q64, int nq, int interp,
+                  int extrap, float* __restrict__ af_io /*[n_pts][nq]: written (train) or read (adjust)*/, int n_pad) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sum = reinterpret_cast<double*>(smem_raw);       // [C] (count_columns scratch), then max average rank
+  double* mnv = sum + C;                                   // [C] smallest normalised rank
+  int* cnt = reinterpret_cast<int*>(mnv + C);              // [C]
+  unsigned char* p = smem_raw + C * 24;
+  float* refq = reinterpret_cast<float*>(p);               // [nq][C]
+  float* sm = refq + (size_t)nq * C;                       // [n_pad][C] sort keys
+  unsigned char* tp = reinterpret_cast<unsigned char*>(sm + (size_t)n_pad * C);
+  tp += (8 - (reinterpret_cast<size_t>(tp) & 7)) & 7;
+  Tables<double, C> tb = carve_tables<double, C>(tp, nq, 1);
+  const long long n0 = (long long)blockIdx.x * C;
+  const bool train = ref != nullptr;
+
+  if (train) {
+    load_segment<float, C>(sm, ref, n0, n_pts, sp, st, seg_rows, S, n_pad);
+    __syncthreads();
+    count_columns<float, C>(sm, n_pad, cnt, sum, false);
+    make_keys<float, C>(sm, n_pad, cnt, sum, 0, XSDBA_KIND_ADD);
+    sort_columns<float, C>(sm, n_pad);
+    for (int item = threadIdx.x; item < C * nq; item += blockDim.x) {
+      const int c = item % C, k = item / C;
+      refq[k * C + c] = quantile_sorted<float, C>(sm + c, cnt[c], S, q64[k]);
+    }
+    __syncthreads();
+  }
+  load_segment<float, C>(sm, hist, n0, n_pts, sp, st, seg_rows, S, n_pad);
+  __syncthreads();
+  count_columns<float, C>(sm, n_pad, cnt, sum, false);
+  make_keys<float, C>(sm, n_pad, cnt, sum, 0, XSDBA_KIND_ADD);
+  sort_columns<float, C>(sm, n_pad);
+  // factors of this (point, variable): computed and stored (train) or loaded (adjust); staged as float64 tables
+  for (int item = threadIdx.x; item < C * nq; item += blockDim.x) {
+    const int c = item % C, k = item / C;
+    if (n0 + c >= n_pts) { refq[k * C + c] = Num<float>::nan(); continue; }
+    float a;
+    if (train) {
+      a = __fsub_rn(refq[k * C + c], quantile_sorted<float, C>(sm + c, cnt[c], S, q64[k]));
+      af_io[(n0 + c) * nq + k] = a;
+    } else {
+      a = af_io[(n0 + c) * nq + k];
+    }
+    refq[k * C + c] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x, n = cnt[c];
+    // NaN nodes dropped (utils.py:351-352), first / last non-NaN factor for the constant extrapolation (:362-368)
+    double clo = Num<double>::nan(), chi = clo;
+    bool have = false;
+    int w = 0;
+    double* xs = tb.xsl[1];
+    double* ys = tb.ysl[1];
+    for (int k = 0; k < nq; ++k) {
+      const double y = (double)refq[k * C + c], x = q64[k];
+      if (y == y) { if (!have) { clo = y; have = true; } chi = y; }
+      if (y == y && x == x) { xs[(size_t)w * C + c] = x; ys[(size_t)w * C + c] = y; ++w; }
+    }
+    for (int k = w; k < tb.ld; ++k) xs[(size_t)k * C + c] = Num<double>::inf();
+    tb.nvl[1][c] = w;
+    tb.blo[c] = q64[0]; tb.bhi[c] = q64[nq - 1]; tb.clo[c] = clo; tb.chi[c] = chi;
+    // _rank_bn (utils.py:641-646): rnk / nanmax(rnk), then (rnk - mn) / (1 - mn)
+    double mx_rank = Num<double>::nan(), mn = mx_rank;
+    if (n > 0) {
+      const float* col = sm + c;
+      const float vmin = col[0], vmax = col[(size_t)(n - 1) * C];
+      int ub = 1; while (ub < n && col[(size_t)ub * C] == vmin) ++ub;
+      int lb = n - 1; while (lb > 0 && col[(size_t)(lb - 1) * C] == vmax) --lb;
+      mx_rank = (double)(lb + n + 1) * 0.5;
+      mn = ((double)(ub + 1) * 0.5) / mx_rank;
+    }
+    sum[c] = mx_rank; mnv[c] = mn;
+  }
+  __syncthreads();
+  for (int item = threadIdx.x; item < S * C; item += blockDim.x) {
+    const int c = item % C;
+    const long long pt = n0 + c;
+    const int t = seg_rows[item / C];
+    if (pt >= n_pts || t < 0) continue;
+    const long long o = pt * sp + (long long)t * st;
+    const float x = hist[o];
+    double sq = Num<double>::nan();
+    const int n = cnt[c];
+    if (x == x && n > 0) {
+      const float* col = sm + c;
+      int lo = 0, hi = n;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[(size_t)mid * C] < x) lo = mid + 1; else hi = mid; }
+      const int lb = lo;
+      hi = n;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[(size_t)mid * C] <= x) lo = mid + 1; else hi = mid; }
+      const double r = ((double)(lb + lo + 1) * 0.5) / sum[c];
+      sq = __ddiv_rn(__dsub_rn(r, mnv[c]), __dsub_rn(1.0, mnv[c]));
+    }
+    const double f = lookup_1d<double, double, C>(tb, c, sq, interp, extrap);
+    hist[o] = (float)__dadd_rn((double)x, f);   // float32 + float64 -> float64, stored into the float32 series
+  }
+}
+
 // =============================================================================================
 // host side
 // =============================================================================================
@@ -3050,6 +3163,49 @@ int launch_standardize(const T* x, int64_t n_pts, int64_t sp, int64_t st, int64_
   return cuda_status(cudaGetLastError());
 }
 
+template <int C>
+int launch_npdft_step_c(const float* ref, float* hist, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
+                        const double* q64, int nq, int interp, int extrap, float* af_io, int n_pad, cudaStream_t s) {
+  const size_t smem = (size_t)C * 24 + ((size_t)nq * C + (size_t)n_pad * C) * sizeof(float) + 8 +
+                      ((tables_bytes<double, C>(nq, 1) + 15) & ~(size_t)15);
+  if (smem > 220 * 1024) return XSDBA_ERR_SEGMENT_TOO_LONG;
+  auto kern = npdft_step_kernel<C>;
+  int rc = set_smem(kern, smem);
+  if (rc) return rc;
+  kern<<<(unsigned)((n_pts + C - 1) / C), threads_for_cols<C>(), smem, s>>>(ref, hist, n_pts, sp, st, grp->segments.rows,
+                                                                             (int)grp->segments.total, q64, nq, interp,
+                                                                             extrap, af_io, n_pad);
+  ++g_launches;
+  return cuda_status(cudaGetLastError());
+}
+
+int launch_npdft_step(const float* ref, float* hist, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
+                      const double* q64, int nq, int interp, int extrap, float* af_io, void* stream) {
+  if (wrong_device(grp)) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n_pts > 0 && !hist) || !grp || (n_pts > 0 && !q64) || (n_pts > 0 && !af_io) || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (grp->n_groups != 1 || grp->window != 1) return XSDBA_ERR_INVALID_ARGUMENT;  // a block of time steps is one group
+  if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (extrap != XSDBA_EXTRAP_CONSTANT && extrap != XSDBA_EXTRAP_NAN) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (n_pts == 0) return XSDBA_OK;
+  const int n_pad = std::max(2, next_pow2(grp->segments.max_len));
+  cudaStream_t s = (cudaStream_t)stream;
+  // columns per CTA: the keys plus the float64 tables must fit
+  for (int C = 32; C >= 1; C >>= 1) {
+    const size_t need = (size_t)C * 24 + ((size_t)nq * C + (size_t)n_pad * C) * sizeof(float) + 8 +
+                        (size_t)(2 * 2 * 128 * C + 4 * C) * 8 + 64;
+    if ((size_t)n_pad * C * sizeof(float) > (size_t)kSortBytes || need > 200 * 1024) continue;
+    switch (C) {
+      case 32: return launch_npdft_step_c<32>(ref, hist, n_pts, sp, st, grp, q64, nq, interp, extrap, af_io, n_pad, s);
+      case 16: return launch_npdft_step_c<16>(ref, hist, n_pts, sp, st, grp, q64, nq, interp, extrap, af_io, n_pad, s);
+      case 8: return launch_npdft_step_c<8>(ref, hist, n_pts, sp, st, grp, q64, nq, interp, extrap, af_io, n_pad, s);
+      case 4: return launch_npdft_step_c<4>(ref, hist, n_pts, sp, st, grp, q64, nq, interp, extrap, af_io, n_pad, s);
+      case 2: return launch_npdft_step_c<2>(ref, hist, n_pts, sp, st, grp, q64, nq, interp, extrap, af_io, n_pad, s);
+      default: return launch_npdft_step_c<1>(ref, hist, n_pts, sp, st, grp, q64, nq, interp, extrap, af_io, n_pad, s);
+    }
+  }
+  return XSDBA_ERR_SEGMENT_TOO_LONG;
+}
+
 int upload_table(const std::vector<int32_t>& off, const std::vector<int32_t>& rows, DevTable& t) {
   XS_CUDA(cudaMalloc(&t.off, off.size() * sizeof(int32_t)));
   XS_CUDA(cudaMalloc(&t.rows, std::max<size_t>(rows.size(), 1) * sizeof(int32_t)));
@@ -3228,6 +3384,10 @@ int xsdba_qm_train_q64_f32(const float* ref, const float* hist, int64_t n_pts, i
   if (!q64) return XSDBA_ERR_INVALID_ARGUMENT;
   return launch_train<float>(ref, hist, n_pts, sp, st, grp, reinterpret_cast<const float*>(q64), nq, kind, 0, 0, af, hq,
                              nullptr, stream, nullptr, 0, q64);
+}
+int xsdba_npdft_step_f32(const float* ref, float* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                         const double* q64, int32_t nq, int32_t interp, int32_t extrap, float* af_io, void* stream) {
+  return launch_npdft_step(ref, x, n_pts, sp, st, grp, q64, nq, interp, extrap, af_io, stream);
 }
 int xsdba_rank_lookup_f32(const float* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
                           const float* af, const float* q, int32_t nq, int32_t interp, int32_t extrap, int32_t kind,

@@ -113,6 +113,18 @@ class _Block:
         _lib.check(st, "npdft rank lookup")
         return out.to(self.dt)
 
+    def step(self, ref_v, x_v, q64, interp, extrap, af=None):
+        """One variable of one N-pdf iteration in ONE launch (float32): quantiles of ref_v / x_v at the float64 nodes,
+        af = ref_q - x_q (returned; or ``af`` given when ref_v is None), x_v += af looked up at rank_bn(x_v), in place."""
+        nq = q64.numel()
+        if af is None:
+            af = torch.empty((self.N, nq), dtype=self.dt, device=x_v.device)
+        st = self.lib.xsdba_npdft_step_f32(None if ref_v is None else ref_v.data_ptr(), x_v.data_ptr(), self.N, 1, self.N,
+                                           self.h.ptr, q64.data_ptr(), nq, _lib.INTERP[interp], _lib.EXTRAP[extrap],
+                                           af.data_ptr(), self.stream)
+        _lib.check(st, "npdft step")
+        return af
+
     def reorder(self, sim_v, ref_v):
         out = torch.empty_like(sim_v)
         fn = getattr(self.lib, f"xsdba_reorder_{_sfx(self.dt)}")
@@ -157,6 +169,9 @@ def mbcn_train(ref, hist, *, time, rot_matrices, quantiles, group, interp="neare
             rot = _iter_rot(rots, ii)
             r, h = blk.rotate(r, rot), blk.rotate(h, rot)
             for iv in range(V):
+                if dt == torch.float32:   # fused: two sorts and one launch instead of three and three
+                    af_q[ib, :, ii, iv, :] = blk.step(r[iv], h[iv], q64, interp, extrapolation)
+                    continue
                 af = blk.factors(r[iv], h[iv], q64)
                 af_q[ib, :, ii, iv, :] = af[:, 0, :]
                 h[iv] = blk.add_factor_at_rank(h[iv], af, q64, interp, extrapolation)
@@ -203,6 +218,9 @@ def mbcn_adjust(ref, hist, sim, *, time, af_q, rot_matrices, quantiles, group, k
         for ii in range(len(rots)):
             x = blk.rotate(x, _iter_rot(rots, ii), fused=False)
             for iv in range(V):
+                if dt == torch.float32:
+                    blk.step(None, x[iv], q64, interp, extrapolation, af=af_q[ib, :, ii, iv, :].contiguous())
+                    continue
                 x[iv] = blk.add_factor_at_rank(x[iv], af_q[ib, :, ii, iv, :].reshape(N, 1, -1).contiguous(), q64, interp,
                                                extrapolation)
         x = blk.rotate(x, rots[-1].T, fused=False)
