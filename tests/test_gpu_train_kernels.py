@@ -160,3 +160,69 @@ def test_group_without_members_and_short_groups():
             assert bits_equal(hq[:, g], hq_o), (algo, g)
             assert bits_equal(af[:, g], (rq_o - hq_o).astype(np.float32)), (algo, g)
     del to_full
+
+
+def _train_window(xs, ref, hist, tx, group, q, kind, window_kernel, mode="train"):
+    old = os.environ.pop("XSDBA_B200_NO_WINDOW_KERNEL", None)
+    if not window_kernel:
+        os.environ["XSDBA_B200_NO_WINDOW_KERNEL"] = "1"
+    try:
+        if mode == "quantile":
+            out = xs.group_quantile(hist, time=tx, group=group, quantiles=q)
+            torch.cuda.synchronize()
+            return out
+        ds = xs.eqm_train(xs.Dataset({"ref": ref, "hist": hist}, time=tx), group=group, kind=kind, quantiles=q)
+        torch.cuda.synchronize()
+        return ds
+    finally:
+        os.environ.pop("XSDBA_B200_NO_WINDOW_KERNEL", None)
+        if old is not None:
+            os.environ["XSDBA_B200_NO_WINDOW_KERNEL"] = old
+
+
+@pytest.mark.parametrize("cal,years,window,nq,var,kind", [
+    ("noleap", 30, 31, 100, "pr", "*"),
+    ("noleap", 30, 31, 50, "tas", "+"),
+    ("standard", 12, 31, 50, "tas", "+"),      # day 366: a sparse group, windows shifted after Feb 29
+    ("360_day", 5, 7, 20, "pr", "*"),
+    ("noleap", 3, 5, 200, "tas", "+"),          # more nodes than samples in a window
+    ("noleap", 30, 15, 30, "pr", "*"),
+])
+def test_window_kernel_equals_per_group_kernels(cal, years, window, nq, var, kind):
+    """K1w (one ordering per chunk of day-of-year groups) against the per-group kernels: every group, bit for bit."""
+    xs = _xs()
+    rng = np.random.default_rng(77)
+    to = o.daily_time_axis(1981, years, cal); tx = xs.TimeAxis.daily(1981, years, cal)
+    P = 21  # two full tiles of 8 and a ragged one
+    ref, hist = _stress_inputs(rng, to, P, var)
+    q = o.equally_spaced_nodes(nq).astype(np.float32)
+    grp = xs.Grouper("time.dayofyear", window)
+    a = _train_window(xs, ref, hist, tx, grp, q, kind, True)
+    b = _train_window(xs, ref, hist, tx, grp, q, kind, False)
+    hq_a, hq_b, af_a, af_b = _np(a.hist_q), _np(b.hist_q), _np(a.af), _np(b.af)
+    zero_node = (hq_a == 0) & (hq_b == 0)
+    for x, y in ((hq_a, hq_b), (af_a, af_b)):
+        both_zero = ((x == 0) & (y == 0)) | zero_node
+        assert bits_equal(np.where(both_zero, 0, x), np.where(both_zero, 0, y))
+    assert np.array_equal(np.abs(af_a[zero_node]), np.abs(af_b[zero_node]), equal_nan=True)
+    qa = _np(_train_window(xs, ref, hist, tx, grp, q, kind, True, mode="quantile"))
+    z = (qa == 0) & (hq_b == 0)
+    assert bits_equal(np.where(z, 0, qa), np.where(z, 0, hq_b))
+
+
+def test_window_kernel_matches_oracle_sampled_groups():
+    xs = _xs()
+    rng = np.random.default_rng(78)
+    to = o.daily_time_axis(1981, 30, "noleap"); tx = xs.TimeAxis.daily(1981, 30, "noleap")
+    ref, hist = (synth.pr(rng, to, 19, w) for w in ("ref", "hist"))
+    hist[:400, 3] = np.nan
+    q = o.equally_spaced_nodes(100).astype(np.float32)
+    gidx, G, _ = o.group_index(to, "time.dayofyear")
+    ds = _train_window(xs, ref, hist, tx, xs.Grouper("time.dayofyear", 31), q, "*", True)
+    af, hq = _np(ds.af), _np(ds.hist_q)
+    with np.errstate(all="ignore"):
+        for g in (0, 1, 14, 15, 16, 37, 38, 39, 180, 349, 350, 363, 364):   # series ends, chunk seams, the middle
+            ref_q = o.nan_quantile(o.group_segment(ref.T.copy(), gidx, g, 31), q)
+            hist_q = o.nan_quantile(o.group_segment(hist.T.copy(), gidx, g, 31), q)
+            assert bits_equal(hq[:, g], hist_q), g
+            assert bits_equal(af[:, g], o.get_correction(hist_q, ref_q, "*").astype(np.float32)), g

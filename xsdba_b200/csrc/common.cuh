@@ -40,6 +40,11 @@ template <> struct Num<double> {
   static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
 };
 
+// monotone uint32 sort keys of the window trainer (K1w): only the column sorter's min / max
+template <> struct Num<unsigned> {
+  static __device__ __forceinline__ unsigned mn(unsigned a, unsigned b) { return a < b ? a : b; }
+  static __device__ __forceinline__ unsigned mx(unsigned a, unsigned b) { return a < b ? b : a; }
+};
 template <typename T> __device__ __forceinline__ bool is_nan(T v) { return v != v; }
 
 // ---------------------------------------------------------------------------------------------

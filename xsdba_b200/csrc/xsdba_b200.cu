@@ -36,6 +36,17 @@ struct DevTable {
 
 }  // namespace
 
+// Chunks of consecutive groups whose windows share most of their rows (day-of-year groups with a 31-day window share
+// 30/31 with their neighbours): the window trainer K1w loads and orders the UNION of a chunk's rows once.
+struct WinTables {
+  int32_t n_chunks = 0;
+  int32_t* chunk_g = nullptr;   // [n_chunks + 1] first group of every chunk
+  int32_t* urow_off = nullptr;  // [n_chunks + 1] offsets into urows
+  int32_t* urows = nullptr;     // union of the chunk's window rows (time indices, ascending)
+  uint16_t* lseg = nullptr;     // [segments.total] position of every segment slot in its chunk's union, 0xFFFF: missing
+  int32_t max_union = 0, max_groups = 0;
+};
+
 struct xsdba_grouping {
   int64_t n_time = 0;
   int32_t n_groups = 0;
@@ -44,6 +55,7 @@ struct xsdba_grouping {
   DevTable members;   // exact group members (window = 1), ascending time
   DevTable segments;  // members x window slots (aliases `members` when window == 1)
   int32_t* gidx = nullptr;  // [n_time] group of every time step (-1: none)
+  WinTables win;      // only when window > 1 and the sharing pays (else n_chunks == 0)
 };
 
 namespace {
@@ -536,6 +548,7 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
 }
 
 #include "train_bucket.cuh"
+#include "train_window.cuh"
 
 // =============================================================================================
 // Table staging shared by the adjust kernels: rows r-1, r, r+1 (cyclic) of the tile's tables into
@@ -2454,6 +2467,27 @@ bool launch_train_fast(const double*, const double*, int64_t, int64_t, int64_t, 
   return false;
 }
 
+// groupings with heavily overlapping windows (day-of-year x 31): one ordering per chunk of groups (K1w)
+bool launch_train_window(const float* ref, const float* hist, int64_t n_pts, int64_t sp, int64_t st,
+                         const xsdba_grouping* grp, const float* q, int nq, int kind, int mode, float* af, float* hq,
+                         cudaStream_t s, int* rc) {
+  if (sp != 1 || st < 0 || grp->win.n_chunks <= 0 || getenv("XSDBA_B200_NO_WINDOW_KERNEL") || getenv("XSDBA_B200_NO_FAST"))
+    return false;
+  *rc = set_smem(train_window_kernel, WinSmem::total);
+  if (*rc) return true;
+  dim3 grid((unsigned)((n_pts + kWinCols - 1) / kWinCols), (unsigned)grp->win.n_chunks);
+  train_window_kernel<<<grid, kWinThreads, WinSmem::total, s>>>(ref, hist, n_pts, st, grp->segments.off, grp->win.lseg,
+                                                                grp->win.chunk_g, grp->win.urow_off, grp->win.urows,
+                                                                grp->n_groups, q, nq, kind, mode, af, hq);
+  ++g_launches;
+  *rc = cuda_status(cudaGetLastError());
+  return true;
+}
+bool launch_train_window(const double*, const double*, int64_t, int64_t, int64_t, const xsdba_grouping*, const double*, int,
+                         int, int, double*, double*, cudaStream_t, int*) {
+  return false;
+}
+
 template <typename T>
 int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
                  const T* q, int nq, int kind, int normalize, int mode, T* af, T* hq, T* scaling, void* stream,
@@ -2477,6 +2511,9 @@ int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t
   cudaStream_t s = (cudaStream_t)stream;
   AdaptParams ap{};
   if (adapt) ap = *adapt;
+  if (!ap.on && !use_jitter && !normalize && !q64 &&
+      launch_train_window(ref, hist, n_pts, sp, st, grp, q, nq, kind, mode, af, hq, s, &fast_rc))
+    return fast_rc;
   if (!ap.on &&
       launch_train_fast(ref, hist, n_pts, sp, st, grp, q, nq, kind, normalize, mode, af, hq, scaling, s, &fast_rc, jp, use_jitter, q64))
     return fast_rc;
@@ -3217,6 +3254,65 @@ int upload_table(const std::vector<int32_t>& off, const std::vector<int32_t>& ro
   return XSDBA_OK;
 }
 
+// Greedy chunking of consecutive groups for K1w.  Leaves win.n_chunks == 0 (kernel not used) when a group repeats a
+// row, a single group exceeds the row budget, or the sharing is below 2x.
+int build_window_tables(const std::vector<int32_t>& soff, const std::vector<int32_t>& srows, int32_t n_time, int n_groups,
+                        WinTables& win) {
+  std::vector<int32_t> stamp(n_time, -1), local(n_time, 0);
+  std::vector<int32_t> chunk_g{0}, urow_off{0}, urows;
+  std::vector<uint16_t> lseg(srows.size(), 0xFFFF);
+  std::vector<int32_t> cur;  // rows of the open chunk
+  int chunk_id = 0, groups_in = 0, max_union = 0, max_groups = 0;
+  auto close_chunk = [&](int next_g) {
+    std::sort(cur.begin(), cur.end());
+    for (size_t i = 0; i < cur.size(); ++i) local[cur[i]] = (int32_t)i;
+    for (int g = chunk_g.back(); g < next_g; ++g)
+      for (int s_ = soff[g]; s_ < soff[g + 1]; ++s_)
+        if (srows[s_] >= 0) lseg[s_] = (uint16_t)local[srows[s_]];
+    urows.insert(urows.end(), cur.begin(), cur.end());
+    urow_off.push_back((int32_t)urows.size());
+    chunk_g.push_back(next_g);
+    max_union = std::max<int>(max_union, (int)cur.size());
+    max_groups = std::max(max_groups, groups_in);
+    cur.clear(); groups_in = 0; ++chunk_id;
+  };
+  std::vector<int32_t> seen(n_time, -1);
+  for (int g = 0; g < n_groups; ++g) {
+    int fresh = 0;
+    for (int s_ = soff[g]; s_ < soff[g + 1]; ++s_) {
+      const int32_t t = srows[s_];
+      if (t < 0) continue;
+      if (seen[t] == g) return XSDBA_OK;  // a row twice in one window: not a case for the bitmap selection
+      seen[t] = g;
+      if (stamp[t] != chunk_id) ++fresh;
+    }
+    int own = 0;
+    for (int s_ = soff[g]; s_ < soff[g + 1]; ++s_) own += srows[s_] >= 0 ? 1 : 0;
+    if (own > kWinMaxRows) return XSDBA_OK;
+    if (groups_in > 0 && ((int)cur.size() + fresh > kWinMaxRows || groups_in >= kWinMaxGroups)) close_chunk(g);
+    for (int s_ = soff[g]; s_ < soff[g + 1]; ++s_) {
+      const int32_t t = srows[s_];
+      if (t >= 0 && stamp[t] != chunk_id) { stamp[t] = chunk_id; cur.push_back(t); }
+    }
+    ++groups_in;
+  }
+  if (groups_in > 0) close_chunk(n_groups);
+  if (urows.size() * 2 > srows.size()) return XSDBA_OK;  // less than 2x sharing: the per-group kernels are as good
+  cudaError_t e = cudaMalloc(&win.chunk_g, chunk_g.size() * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&win.urow_off, urow_off.size() * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&win.urows, std::max<size_t>(urows.size(), 1) * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&win.lseg, std::max<size_t>(lseg.size(), 1) * sizeof(uint16_t));
+  if (e == cudaSuccess) e = cudaMemcpy(win.chunk_g, chunk_g.data(), chunk_g.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(win.urow_off, urow_off.data(), urow_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(win.urows, urows.data(), urows.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(win.lseg, lseg.data(), lseg.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return (int)e;
+  win.n_chunks = (int32_t)chunk_g.size() - 1;
+  win.max_union = max_union;
+  win.max_groups = max_groups;
+  return XSDBA_OK;
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -3286,6 +3382,7 @@ int xsdba_grouping_create(xsdba_grouping_t** out, const int32_t* grp_idx_host, i
         }
         soff[n_groups] = (int32_t)srows.size();
         rc = upload_table(soff, srows, g->segments);
+        if (rc == XSDBA_OK) rc = build_window_tables(soff, srows, (int32_t)n_time, n_groups, g->win);
       }
     }
   }
@@ -3301,6 +3398,7 @@ int xsdba_grouping_destroy(xsdba_grouping_t* g) {
   cudaFree(g->members.off);
   cudaFree(g->members.rows);
   cudaFree(g->gidx);
+  cudaFree(g->win.chunk_g); cudaFree(g->win.urow_off); cudaFree(g->win.urows); cudaFree(g->win.lseg);
   delete g;
   return XSDBA_OK;
 }
