@@ -43,7 +43,7 @@ struct WinTables {
   int32_t* chunk_g = nullptr;   // [n_chunks + 1] first group of every chunk
   int32_t* urow_off = nullptr;  // [n_chunks + 1] offsets into urows
   int32_t* urows = nullptr;     // union of the chunk's window rows (time indices, ascending)
-  uint16_t* lseg = nullptr;     // [segments.total] position of every segment slot in its chunk's union, 0xFFFF: missing
+  unsigned long long* gmask = nullptr;  // [union rows] bit j: group chunk_g + j has the row in its window
   int32_t max_union = 0, max_groups = 0;
 };
 
@@ -2476,8 +2476,8 @@ bool launch_train_window(const float* ref, const float* hist, int64_t n_pts, int
   *rc = set_smem(train_window_kernel, WinSmem::total);
   if (*rc) return true;
   dim3 grid((unsigned)((n_pts + kWinCols - 1) / kWinCols), (unsigned)grp->win.n_chunks);
-  train_window_kernel<<<grid, kWinThreads, WinSmem::total, s>>>(ref, hist, n_pts, st, grp->segments.off, grp->win.lseg,
-                                                                grp->win.chunk_g, grp->win.urow_off, grp->win.urows,
+  train_window_kernel<<<grid, kWinThreads, WinSmem::total, s>>>(ref, hist, n_pts, st, grp->segments.off, grp->win.chunk_g,
+                                                                grp->win.urow_off, grp->win.urows, grp->win.gmask,
                                                                 grp->n_groups, q, nq, kind, mode, af, hq);
   ++g_launches;
   *rc = cuda_status(cudaGetLastError());
@@ -3260,15 +3260,17 @@ int build_window_tables(const std::vector<int32_t>& soff, const std::vector<int3
                         WinTables& win) {
   std::vector<int32_t> stamp(n_time, -1), local(n_time, 0);
   std::vector<int32_t> chunk_g{0}, urow_off{0}, urows;
-  std::vector<uint16_t> lseg(srows.size(), 0xFFFF);
+  std::vector<unsigned long long> gmask;
   std::vector<int32_t> cur;  // rows of the open chunk
   int chunk_id = 0, groups_in = 0, max_union = 0, max_groups = 0;
   auto close_chunk = [&](int next_g) {
     std::sort(cur.begin(), cur.end());
     for (size_t i = 0; i < cur.size(); ++i) local[cur[i]] = (int32_t)i;
+    const size_t base = gmask.size();
+    gmask.resize(base + cur.size(), 0ull);
     for (int g = chunk_g.back(); g < next_g; ++g)
       for (int s_ = soff[g]; s_ < soff[g + 1]; ++s_)
-        if (srows[s_] >= 0) lseg[s_] = (uint16_t)local[srows[s_]];
+        if (srows[s_] >= 0) gmask[base + local[srows[s_]]] |= 1ull << (g - chunk_g.back());
     urows.insert(urows.end(), cur.begin(), cur.end());
     urow_off.push_back((int32_t)urows.size());
     chunk_g.push_back(next_g);
@@ -3301,11 +3303,11 @@ int build_window_tables(const std::vector<int32_t>& soff, const std::vector<int3
   cudaError_t e = cudaMalloc(&win.chunk_g, chunk_g.size() * sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMalloc(&win.urow_off, urow_off.size() * sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMalloc(&win.urows, std::max<size_t>(urows.size(), 1) * sizeof(int32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&win.lseg, std::max<size_t>(lseg.size(), 1) * sizeof(uint16_t));
+  if (e == cudaSuccess) e = cudaMalloc(&win.gmask, std::max<size_t>(gmask.size(), 1) * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemcpy(win.chunk_g, chunk_g.data(), chunk_g.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(win.urow_off, urow_off.data(), urow_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(win.urows, urows.data(), urows.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(win.lseg, lseg.data(), lseg.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(win.gmask, gmask.data(), gmask.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return (int)e;
   win.n_chunks = (int32_t)chunk_g.size() - 1;
   win.max_union = max_union;
@@ -3398,7 +3400,7 @@ int xsdba_grouping_destroy(xsdba_grouping_t* g) {
   cudaFree(g->members.off);
   cudaFree(g->members.rows);
   cudaFree(g->gidx);
-  cudaFree(g->win.chunk_g); cudaFree(g->win.urow_off); cudaFree(g->win.urows); cudaFree(g->win.lseg);
+  cudaFree(g->win.chunk_g); cudaFree(g->win.urow_off); cudaFree(g->win.urows); cudaFree(g->win.gmask);
   delete g;
   return XSDBA_OK;
 }
