@@ -753,7 +753,7 @@ def time_ordinal(time: TimeAxis) -> np.ndarray:
     return (o - o[0]).astype(np.float64)
 
 
-def group_trend_poly(x, gidx, n_groups, window, tcoord, degree):
+def group_trend_poly(x, gidx, n_groups, window, tcoord, degree, preserve_mean=False, kind="+"):
     """``PolyDetrend(degree, group).fit(x).ds.trend`` (detrending.py:189-208 through map_groups /
     Grouper.apply, base.py:410-420): per group, window dims are averaged first (NaN-skipping), then a
     polynomial is fitted on the group's time steps and evaluated there.  Returns float64 [N, T]."""
@@ -772,6 +772,11 @@ def group_trend_poly(x, gidx, n_groups, window, tcoord, degree):
             series = x[:, sel].astype(np.float64)
         for i in range(N):
             trend[i, sel] = poly_trend(series[i], tcoord[sel], degree)
+        if preserve_mean:   # detrending.py:205: trend (+|*) invert(mean of the group's trend)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                m = np.nanmean(trend[:, sel], axis=1, keepdims=True)
+            trend[:, sel] = apply_correction(trend[:, sel], invert(m, kind), kind)
     return trend
 
 
@@ -916,6 +921,30 @@ def mbcn_adjust(ref, hist, sim, af_q, rots, quantiles, blocks, kinds, method="ne
             for v in range(V):
                 scen[v, i, g] = reordering_1d(scen_block[v], npdft_block[v])[keep]
     return scen
+
+
+def npdf_transform(ref, hist, sim, rots, quantiles, *, group, time, sim_time, window=1, interp="nearest",
+                   extrap="constant"):
+    """``npdf_transform`` (_adjustment.py:977-1057) with base = QuantileDeltaMapping: ref, hist [V, N, T], sim
+    [V, N, Ts] -> (scenh, scens).  ``x @ R`` of xarray is a dot product over the variable dimension -- restated with
+    numpy's einsum (xarray is absent from this image, its dot calls einsum too; parity unpinned beyond that)."""
+    V, N, T = ref.shape
+    dt = ref.dtype
+    q = np.asarray(quantiles, dt)
+    gidx, G, _ = group_index(time, group)
+    hist, sim = hist.copy(), sim.copy()
+    for R in rots:
+        refp, histp, simp = (np.einsum("xnt,xy->ynt", a, R).astype(dt) for a in (ref, hist, sim))
+        sh, ss = np.empty_like(histp), np.empty_like(simp)
+        for v in range(V):
+            af, _ = eqm_train(refp[v], histp[v], gidx, G, window, q, "+")
+            sh[v], _ = qdm_adjust(histp[v], af, q, group=group, time=time, window=window, interp=interp,
+                                  extrapolation=extrap, kind="+")
+            ss[v], _ = qdm_adjust(simp[v], af, q, group=group, time=sim_time, window=window, interp=interp,
+                                  extrapolation=extrap, kind="+")
+        hist = np.einsum("ynt,xy->xnt", sh, R).astype(dt)
+        sim = np.einsum("ynt,xy->xnt", ss, R).astype(dt)
+    return hist, sim
 
 
 # ----------------------------------------------------------------------------------------------

@@ -942,3 +942,23 @@ def test_generic_train_kernel_jitter_and_signed_zeros():
     gidx1, G1, _ = o.group_index(to, "time")
     _, hq_o = o.eqm_train(ref.T.copy(), z.T.copy(), gidx1, G1, 1, q, "+")
     np.testing.assert_allclose(_np(ds.hist_q), hq_o, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("kind", ["+", "*"])
+def test_poly_trend_preserve_mean(kind):
+    """PolyDetrend(preserve_mean=True) (detrending.py:205): the group's trend loses its own mean."""
+    xs = _xs()
+    rng = np.random.default_rng(8)
+    tx, to = _time("noleap", 6)
+    x = synth.tas(rng, to, 7, "sim", np.float64)
+    gidx, G, _ = o.group_index(to, "time.month")
+    want = o.group_trend_poly(x.T.copy(), gidx, G, 1, o.time_ordinal(to), 1, preserve_mean=True, kind=kind)
+    got = _np(xs.poly_trend(x, time=tx, group="time.month", degree=1, kind=kind, preserve_mean=True)).T
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9, equal_nan=True)
+    sim = synth.tas(rng, to, 7, "sim", np.float32)
+    out = xs.dqm_adjust(xs.Dataset({"sim": sim, "af": np.zeros((7, G, 4), np.float32),
+                                    "hist_q": np.tile(np.linspace(-20, 20, 4, dtype=np.float32), (7, G, 1)),
+                                    "scaling": np.zeros((7, G), np.float32)}, time=tx), group="time.month",
+                        interp="nearest", extrapolation="constant", kind="+",
+                        detrend=xs.PolyDetrend(degree=1, kind="+", group="time.month", preserve_mean=True))
+    np.testing.assert_allclose(_np(out.scen), sim, rtol=2e-6, equal_nan=True)   # zero factors: detrend + retrend = identity

@@ -12,5 +12,5 @@ from .detrending import LoessDetrend, PolyDetrend  # noqa: F401
 
 __version__ = "0.1.0"
 from .processing import escore, jitter, jitter_over_thresh, jitter_under_thresh  # noqa: F401
-from .mbcn import MBCn, mbcn_adjust, mbcn_train, rand_rot_matrix  # noqa: F401
+from .mbcn import MBCn, NpdfTransform, mbcn_adjust, mbcn_train, npdf_transform, rand_rot_matrix  # noqa: F401
 from .periods import Periods, adjust_periods, stack_periods, unstack_periods  # noqa: F401

@@ -382,13 +382,14 @@ def group_rank(x, *, time, group, rank_window=False, time_axis=0):
     return out
 
 
-def poly_trend(x, *, time, group, degree, kind="+", scaling=None, time_axis=0):
+def poly_trend(x, *, time, group, degree, kind="+", scaling=None, time_axis=0, preserve_mean=False):
     """Trend of ``x`` (optionally of ``x (+|*) scaling``) as ``PolyDetrend(degree, group).fit`` computes it
     (detrending.py:189-208): float64 tensor shaped like ``x``."""
     group = parse_group(group)
     lib = _lib.load()
     dt = _widest(x)
-    xs, n_pts, sp, st, _ = _series(x, time_axis, len(time), dt)
+    xs_ = _series(x, time_axis, len(time), dt)
+    xs, n_pts, sp, st, _ = xs_
     h = group.handle(time)
     sc = None
     if scaling is not None:
@@ -400,6 +401,17 @@ def poly_trend(x, *, time, group, degree, kind="+", scaling=None, time_axis=0):
     fn = getattr(lib, f"xsdba_poly_trend_{_sfx(dt)}")
     _lib.check(fn(xs.data_ptr(), n_pts, sp, st, h.ptr, sc.data_ptr() if sc is not None else None, _lib.KIND[kind],
                   int(degree), tc.data_ptr(), trend.data_ptr(), _stream()), "poly_trend")
+    if preserve_mean:
+        # detrending.py:205: trend (+|*) invert(trend.mean(time)) inside every group -- a reduction over 30-10 950
+        # values per (point, group) on a tensor that is already on the device (torch ops, no kernel of its own)
+        tm = trend if xs_.axis == 0 else trend.movedim(-1, 0)
+        tm2 = tm.reshape(tm.shape[0], -1)
+        gi = torch.as_tensor(group.zero_based_index(time), device=trend.device, dtype=torch.long)
+        ok = ~torch.isnan(tm2)
+        sums = torch.zeros((h.n_groups, tm2.shape[1]), dtype=trend.dtype, device=trend.device).index_add_(0, gi, torch.nan_to_num(tm2))
+        cnts = torch.zeros_like(sums).index_add_(0, gi, ok.to(trend.dtype))
+        mean = (sums / cnts)[gi]
+        tm2.copy_(tm2 - mean if kind == "+" else tm2 * (1.0 / mean))
     return trend
 
 
@@ -461,6 +473,7 @@ def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_
         detrend = PolyDetrend(degree=int(detrend), kind=kind, group=group)   # _adjustment.py:759-762
     if isinstance(detrend, PolyDetrend):
         trend = poly_trend(sim, time=time, group=detrend.group, degree=detrend.degree, kind=kind,
+                           preserve_mean=getattr(detrend, "preserve_mean", False),
                            scaling=scaling if detrend.group.name == group.name and detrend.group.window == group.window else None,
                            time_axis=ta)
         if not (detrend.group.name == group.name and detrend.group.window == group.window):

@@ -13,15 +13,16 @@ class BaseDetrend:
 
 
 class PolyDetrend(BaseDetrend):
-    """``PolyDetrend(group, kind, degree)`` (detrending.py:165-193); ``preserve_mean`` is not built."""
+    """``PolyDetrend(group, kind, degree, preserve_mean)`` (detrending.py:165-208)."""
 
     def __init__(self, group="time", kind="+", degree=4, preserve_mean=False, mult_skip_zeros=False):
-        if preserve_mean or mult_skip_zeros:
-            raise NotImplementedError("preserve_mean / mult_skip_zeros are not built in xsdba_b200 yet")
+        if mult_skip_zeros:
+            raise NotImplementedError("mult_skip_zeros is not built in xsdba_b200 yet")
         if not 0 <= int(degree) <= 4:
             raise NotImplementedError("xsdba_b200 fits polynomial trends of degree 0..4")
-        super().__init__(group=group, kind=kind, degree=int(degree))
+        super().__init__(group=group, kind=kind, degree=int(degree), preserve_mean=bool(preserve_mean))
         self.degree = int(degree)
+        self.preserve_mean = bool(preserve_mean)
 
 
 class LoessDetrend(BaseDetrend):

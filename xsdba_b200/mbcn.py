@@ -280,3 +280,73 @@ class MBCn:
         return mbcn_adjust(ref, hist, sim, time=time, af_q=self.ds["af_q"], rot_matrices=self.ds["rot_matrices"],
                            quantiles=self.ds["quantiles"], group=self.group, kinds=kinds, interp=self.interp,
                            extrapolation=self.extrapolation)
+
+
+def npdf_transform(ref, hist, sim, *, time, sim_time, rot_matrices, base_kws=None, adj_kws=None, n_escore=-1, base="qdm"):
+    """``xsdba._adjustment.npdf_transform`` (_adjustment.py:977-1057): iterative univariate adjustment in randomly
+    rotated spaces.  ref / hist (V, time, *points), sim (V, sim_time, *points) -> dict(scenh, scen, escores).
+
+    Every iteration rotates the three clouds (``x @ R`` along the variable dimension, i.e. ``R.T`` applied: xarray's
+    dot / einsum arithmetic, products and sums rounded separately), trains the univariate ``base`` adjustment
+    (QuantileDeltaMapping, kind "+", any grouping -- this is the route by which monthly grouping has a meaning for the
+    multivariate path, SURVEY.md section 8 note) on every rotated variable, adjusts hist and sim with it and rotates
+    back (``x' @ R``: ``R`` applied).  ``n_escore >= 0`` also returns the energy score of (ref, hist) after every
+    iteration (scale=True; 0 = all time steps)."""
+    if base not in ("qdm", "eqm"):
+        raise NotImplementedError("npdf_transform is built for base = QuantileDeltaMapping / EmpiricalQuantileMapping")
+    base_kws = dict(base_kws or {})
+    adj_kws = dict(adj_kws or {})
+    if "kind" in base_kws and base_kws["kind"] != "+":
+        import warnings
+        warnings.warn('The adjustment kind cannot be controlled when using NpdfTransform, it defaults to "+".', stacklevel=2)
+    base_kws["kind"] = "+"   # adjustment.py:1331-1337
+    group = parse_group(base_kws.pop("group", "time"), base_kws.pop("window", 1))
+    nquantiles = base_kws.pop("nquantiles", 20)
+    adj_kws.setdefault("interp", "nearest")
+    adj_kws.setdefault("extrapolation", "constant")
+    ref, pshape = _prep(ref)
+    hist, _ = _prep(hist, ref.dtype)
+    sim, _ = _prep(sim, ref.dtype)
+    dt = ref.dtype
+    V, T, N = ref.shape
+    Ts = sim.shape[1]
+    rots = np.asarray(rot_matrices, np.float32)
+    npdt = np.float32 if dt == torch.float32 else np.float64
+    q = equally_spaced_nodes(int(nquantiles)).astype(npdt) if np.isscalar(nquantiles) else np.asarray(nquantiles, npdt)
+    blk_t, blk_s = _Block(T, N, dt), _Block(Ts, N, dt)
+    flat = lambda a: a.permute(1, 0, 2).reshape(a.shape[1], V * N).contiguous()            # (V, t, N) -> (t, V*N)
+    unflat = lambda a, t: a.reshape(t, V, N).permute(1, 0, 2).contiguous()                   # noqa: E731
+    escores = []
+    for R in rots:
+        refp, histp, simp = blk_t.rotate(ref, R.T, fused=False), blk_t.rotate(hist, R.T, fused=False), blk_s.rotate(sim, R.T, fused=False)
+        tr = L4.eqm_train(L4.Dataset({"ref": flat(refp), "hist": flat(histp)}, time=time), group=group, kind="+",
+                          quantiles=q, **base_kws)
+        outs = []
+        for x, tx in ((histp, time), (simp, sim_time)):
+            if base == "qdm":
+                o = L4.qdm_adjust(L4.Dataset({"sim": flat(x), "af": tr["af"], "quantiles": tr["quantiles"]}, time=tx),
+                                  group=group, kind="+", **adj_kws)
+            else:
+                o = L4.qm_adjust(L4.Dataset({"sim": flat(x), "af": tr["af"], "hist_q": tr["hist_q"]}, time=tx),
+                                 group=group, kind="+", **adj_kws)
+            outs.append(unflat(o["scen"], len(tx)))
+        hist = blk_t.rotate(outs[0], R, fused=False)
+        sim = blk_s.rotate(outs[1], R, fused=False)
+        if n_escore >= 0:
+            from .processing import escore
+            escores.append(escore(ref, hist, N=n_escore, scale=True))
+    esc = torch.stack(escores) if escores else torch.full((len(rots), N), float("nan"), dtype=dt, device=ref.device)
+    return {"scenh": hist.reshape(V, T, *pshape), "scen": sim.reshape(V, Ts, *pshape),
+            "escores": esc.reshape(len(rots), *pshape), "rotation_matrices": rots}
+
+
+class NpdfTransform:
+    """``xsdba.adjustment.NpdfTransform`` (adjustment.py:1239-1391): ``NpdfTransform.adjust(ref, hist, sim, ...)``
+    trains and adjusts in one call; arrays are (multivar, time, *points)."""
+
+    @classmethod
+    def adjust(cls, ref, hist, sim, *, time, sim_time=None, base="qdm", base_kws=None, n_escore=0, n_iter=20,
+               adj_kws=None, rot_matrices=None, seed=None):
+        rots = rand_rot_matrix(ref.shape[0], n_iter, seed) if rot_matrices is None else np.asarray(rot_matrices, np.float32)
+        return npdf_transform(ref, hist, sim, time=time, sim_time=time if sim_time is None else sim_time, rot_matrices=rots,
+                              base_kws=base_kws, adj_kws=adj_kws, n_escore=n_escore, base=base)
