@@ -352,7 +352,18 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to the C stdout when the first communicator is created: keep stdout for the
+        # ONE JSON line and send whatever the libraries say during initialisation to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     lib = _lib.load()
 
     t_train = xs.TimeAxis.daily(1981, NYEARS, "noleap")
