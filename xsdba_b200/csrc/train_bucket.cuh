@@ -19,24 +19,28 @@
 //      slot and scatters it: the column is now sorted by bucket, buckets hold 1-3 samples for continuous data;
 //   5. order statistics i, i+1: the bucket of position i is a function of the VALUE stored there (no search); its
 //      range comes from the prefix table; up to 8 samples are selected in registers through a 19-exchange
-//      network, up to 64 by counting, otherwise (heavy ties, multi-scale data, infinite ranges) the CTA runs K1f's
-//      sorter on the scattered column -- same results.
+//      network.  A node that meets a bucket of 9..24 samples (~1e-4 of the nodes of smooth data, but one of them
+//      used to hold the other 31 warps at the barrier for a whole serial selection) is put on a shared-memory work
+//      list and served afterwards by a whole warp: one sample per lane, ranks by shuffles.  Columns with heavier
+//      buckets (ties, multi-scale data) or an infinite range send the tile to K1f's sorter right after the
+//      histogram -- same results.
 // Semantics: nbutils._nan_quantile_1d / _get_indexes / _linear_interpolation (nbutils.py:24-148), NaNs excluded,
 // utils.get_correction (utils.py:130-143), dqm_train's normalisation (_adjustment.py:163-179) -- as K1f.
 // =============================================================================================
 constexpr int kBktN = 1024;       // buckets per column
 constexpr int kBktW = kBktN / 2;  // counter words per column: bucket b lives in half b / 512 of word b % 512
-constexpr int kBktLoopMax = 64;   // largest bucket selected by counting; larger ones -> sorter fallback
 constexpr int kBktAbort = 24;     // a bucket with more keys than this (seen in the histogram) sends the tile to the sorter
+constexpr int kBktPitch = 33;     // row pitch of the [warp][column] partial tables (transposed reads are conflict free)
 
 struct BktSmem {
-  static constexpr size_t buf = 0;                                   // float    [1024][32] scattered / sorted column
-  static constexpr size_t hist = buf + 1024 * 32 * 4;                // unsigned [512][32] packed counters (aliases: psum)
-  static constexpr size_t part = hist + (size_t)kBktW * 32 * 4;      // [3][32][32]: pmin, pmax (float), pcnt (int); tot aliases pmin
-  static constexpr size_t col = part + 3 * 1024 * 4;                 // [8][32]: cmin, cmax (float), cnt (int), mu[2] (float), nlow
+  static constexpr size_t buf = 0;                                   // float    [1024 + 8][32] scattered / sorted column, 8 rows of +inf
+  static constexpr size_t hist = buf + (1024 + 8) * 32 * 4;          // unsigned [512][32] packed counters (aliases: psum)
+  static constexpr size_t part = hist + (size_t)kBktW * 32 * 4;      // [3][32][33]: pmin, pmax (float), pcnt (int); aliases: tot, work list
+  static constexpr size_t col = part + 3 * 32 * kBktPitch * 4;       // [8][32]: cmin, cmax (float), cnt (int), mu[2], scale (float), work-list length
   static constexpr size_t rows = col + 8 * 32 * 4;                   // int [1024] member rows of the group (-1 past S)
   static constexpr size_t q = rows + 1024 * 4;                       // double [kFastMaxNq]
-  static constexpr size_t refq = q + kFastMaxNq * 8;                 // float [nq][33]
+  static constexpr size_t pos = q + kFastMaxNq * 8;                  // int [kFastMaxNq], float [kFastMaxNq]: node positions of a full column
+  static constexpr size_t refq = pos + kFastMaxNq * 8;               // float [nq][33]
   static __host__ __device__ constexpr size_t total(int nq) { return refq + (size_t)nq * 33 * 4; }
 };
 
@@ -58,6 +62,18 @@ __device__ __forceinline__ int bucket_end(const unsigned* __restrict__ endp, uns
   return (int)((b & kBktW) ? (w >> 16) : (w & 0xffffu));
 }
 
+// Bucket width of one column.  degenerate: infinite / NaN range -- the bucket map says nothing about such a column.
+__device__ __forceinline__ float bucket_scale(float cmin, float cmax, bool& degenerate) {
+  const float finf = __int_as_float(0x7f800000);
+  const bool nonempty = !(cmin == finf && cmax == -finf);  // (min / max of no samples)
+  const float range = __fsub_rn(cmax, cmin);
+  const float sc = __fdiv_rn((float)kBktN - 2.5f, range);  // ceil((v - min) * scale) <= 1022 for finite v <= max
+  const bool fin = range == range && fabsf(range) != finf;
+  const bool ok = fin && range > 0.0f && fabsf(sc) != finf;
+  degenerate = nonempty && !(ok || (fin && range == 0.0f));
+  return ok ? sc : 0.0f;
+}
+
 __device__ __forceinline__ void ce8(float& a, float& b) { const float lo = fminf(a, b); b = fmaxf(a, b); a = lo; }
 __device__ __forceinline__ float pick8(const float (&x)[8], int r) {  // x[r], 0 <= r < 8: a 3-level select tree
   const bool b0 = r & 1, b1 = r & 2, b2 = r & 4;
@@ -66,26 +82,10 @@ __device__ __forceinline__ float pick8(const float (&x)[8], int r) {  // x[r], 0
   return b2 ? z1 : z0;
 }
 
-// slow path of bucket_select_pair: a bucket with 8 < m <= kBktLoopMax samples, r-th and (r+1)-th by counting
-__device__ __noinline__ void bucket_count_select(const float* __restrict__ col, int s, int e, int r, float& left,
-                                                 float& right) {
-  for (int a = s; a < e; ++a) {
-    const float xa = col[a * 32];
-    int c = 0;
-    for (int j = s; j < e; ++j) {
-      const float y = col[j * 32];
-      c += (y < xa || (y == xa && j < a)) ? 1 : 0;
-    }
-    if (c == r) left = xa;
-    if (c == r + 1) right = xa;
-  }
-}
-
 // Order statistics i and i + 1 of one bucket-sorted, non-degenerate column (0 <= i, i + 1 < n).  Returns false when a
-// bucket is too large for the in-place selection (the caller falls back to the sorter).
+// bucket holds more than 8 samples: the node goes to the warp-cooperative path (bucket_select_pair_warp).
 __device__ __forceinline__ bool bucket_select_pair(const unsigned* __restrict__ endp, const float* __restrict__ col,
                                                    float cmin, float scale, int i, float& left, float& right) {
-  const float inf = __int_as_float(0x7f800000);
   const float xi = col[i * 32], xj = col[(i + 1) * 32];
   const unsigned b0 = bucket_key(xi, cmin, scale) & (kBktN - 1), b1 = bucket_key(xj, cmin, scale) & (kBktN - 1);
   bool ok = true;
@@ -94,75 +94,117 @@ __device__ __forceinline__ bool bucket_select_pair(const unsigned* __restrict__ 
     const int e0 = bucket_end(endp, b0);
     const int s0 = bucket_end(endp, b0 - 1);
     const int m = e0 - s0, r = i - s0;
-    if (m <= 8) {
-      float x[8];
-      const float* p = col + s0 * 32;
+    ok = m <= 8;
+    // the 8 slots from s0 on: the m samples of the bucket, then samples of later buckets (all larger: the bucket map
+    // is monotone) or the +inf rows behind the column -- the first m of the sorted window are the sorted bucket
+    float x[8];
+    const float* p = col + s0 * 32;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = j < m ? p[j * 32] : inf;
-      ce8(x[0], x[1]); ce8(x[2], x[3]); ce8(x[4], x[5]); ce8(x[6], x[7]);
-      ce8(x[0], x[2]); ce8(x[1], x[3]); ce8(x[4], x[6]); ce8(x[5], x[7]);
-      ce8(x[1], x[2]); ce8(x[5], x[6]); ce8(x[0], x[4]); ce8(x[3], x[7]);
-      ce8(x[1], x[5]); ce8(x[2], x[6]);
-      ce8(x[1], x[4]); ce8(x[3], x[6]);
-      ce8(x[2], x[4]); ce8(x[3], x[5]);
-      ce8(x[3], x[4]);
-      left = pick8(x, r);
-      right = pick8(x, (r + 1) & 7);
-    } else if (m <= kBktLoopMax) {
-      bucket_count_select(col, s0, e0, r, left, right);
-    } else {
-      ok = false;
-    }
+    for (int j = 0; j < 8; ++j) x[j] = p[j * 32];
+    ce8(x[0], x[1]); ce8(x[2], x[3]); ce8(x[4], x[5]); ce8(x[6], x[7]);
+    ce8(x[0], x[2]); ce8(x[1], x[3]); ce8(x[4], x[6]); ce8(x[5], x[7]);
+    ce8(x[1], x[2]); ce8(x[5], x[6]); ce8(x[0], x[4]); ce8(x[3], x[7]);
+    ce8(x[1], x[5]); ce8(x[2], x[6]);
+    ce8(x[1], x[4]); ce8(x[3], x[6]);
+    ce8(x[2], x[4]); ce8(x[3], x[5]);
+    ce8(x[3], x[4]);
+    left = pick8(x, r);
+    right = pick8(x, (r + 1) & 7);
   }
   if (b1 != b0) {  // position i + 1 opens the next non-empty bucket: its smallest sample
     float mn = xj;
     if (b1 != kBktN - 1) {
       const int m1 = bucket_end(endp, b1) - (i + 1);
-      const float* p = col + (i + 1) * 32;
-      if (m1 <= 8) {
-        float y[8];
+      ok = ok && m1 <= 8;
+      const float* p = col + (i + 1) * 32;  // (slots past the bucket hold larger samples: the minimum is unchanged)
+      float y[8];
 #pragma unroll
-        for (int j = 1; j < 8; ++j) y[j] = j < m1 ? p[j * 32] : inf;
-        mn = min3f(mn, y[1], y[2]); mn = min3f(mn, y[3], y[4]); mn = min3f(mn, y[5], y[6]); mn = fminf(mn, y[7]);
-      } else {
-        for (int a = 1; a < m1; ++a) mn = fminf(mn, p[a * 32]);
-      }
+      for (int j = 1; j < 8; ++j) y[j] = p[j * 32];
+      mn = min3f(mn, y[1], y[2]); mn = min3f(mn, y[3], y[4]); mn = min3f(mn, y[5], y[6]); mn = fminf(mn, y[7]);
     }
     right = mn;
   }
   return ok;
 }
 
-// One quantile node of one column from the bucket-sorted column (fast = true) or from the two sorted runs the
-// sorter leaves (fast = false).  Returns the node value; sets fb when the bucket path has to give up.
-template <bool FAST>
-__device__ __forceinline__ float bucket_quantile_node(const unsigned* __restrict__ endp, const float* __restrict__ colp,
-                                                      double qk, int n, int S, float cmin, float cmax, float scale,
-                                                      bool degenerate, int& fb) {
-  const double vi = (double)(n - 1) * qk;  // nbutils.py:131
-  float left, right, gamma;
-  if (vi >= (double)(n - 1)) {  // nbutils.py:47-51: position -1 of the full-length sorted row
-    left = right = (n < S) ? Num<float>::nan() : cmax;
-    gamma = (float)(vi + 1.0);
-  } else if (vi < 0.0) {
-    left = right = cmin;
-    gamma = (float)vi;
-  } else {
-    const int i = (int)vi;
-    left = right = cmin;
-    if (FAST) {
-      if (degenerate || !bucket_select_pair(endp, colp, cmin, scale, i, left, right)) fb = 1;
-    } else {
-      // both runs in full: the 1024 keys are the valid values plus +inf padding, and in a degenerate column
-      // (infinite range: every key in one bucket) the scatter order says nothing about which is which
-      two_run_pair(colp, 512, colp + 512 * 32, 512, i, left, right);
+// The same pair by a whole warp (all 32 lanes call it with the same column): buckets of up to 32 samples, one sample
+// per lane, rank = number of samples that sort before it (value, then slot), by shuffles.
+__device__ __forceinline__ void bucket_select_pair_warp(const unsigned* __restrict__ endp, const float* __restrict__ col,
+                                                        float cmin, float scale, int i, float& left, float& right) {
+  const float inf = __int_as_float(0x7f800000);
+  const int lane = threadIdx.x & 31;
+  const float xi = col[i * 32], xj = col[(i + 1) * 32];
+  const unsigned b0 = bucket_key(xi, cmin, scale) & (kBktN - 1), b1 = bucket_key(xj, cmin, scale) & (kBktN - 1);
+  left = right = xi;
+  if (b0 != 0 && b0 != kBktN - 1) {
+    const int e0 = bucket_end(endp, b0);
+    const int s0 = bucket_end(endp, b0 - 1);
+    const int m = e0 - s0, r = i - s0;  // (m <= kBktAbort < 32)
+    const float x = lane < m ? col[(s0 + lane) * 32] : inf;
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const float y = __shfl_sync(0xffffffffu, x, j);
+      rank += (y < x || (y == x && j < lane)) ? 1 : 0;
     }
-    gamma = (float)(vi - (double)i);  // nbutils.py:142
+    if (lane >= m) rank = 64;
+    left = __shfl_sync(0xffffffffu, x, __ffs(__ballot_sync(0xffffffffu, rank == r)) - 1);
+    const unsigned nxt = __ballot_sync(0xffffffffu, rank == r + 1);
+    if (nxt) right = __shfl_sync(0xffffffffu, x, __ffs(nxt) - 1);
   }
+  if (b1 != b0) {
+    float mn = xj;
+    if (b1 != kBktN - 1) {
+      const int m1 = bucket_end(endp, b1) - (i + 1);
+      mn = lane < m1 ? col[(i + 1 + lane) * 32] : inf;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+    }
+    right = mn;
+  }
+}
+
+// nbutils._linear_interpolation (nbutils.py:101-104, 146) on the pair
+__device__ __forceinline__ float bucket_interpolate(float left, float right, float gamma, float cmax) {
   const float diff = right - left;
   float r = gamma >= 0.5f ? __fmaf_rn(-diff, 1.0f - gamma, right) : __fmaf_rn(diff, gamma, left);
   if (r != r) r = cmax;  // nbutils.py:146
   return r;
+}
+
+// Position of quantile q in a column of n valid samples (nbutils.py:131, 47-56, 142): the index i of the left order
+// statistic and the interpolation weight; i = -1: beyond the last sample, i = -2: before the first.
+__device__ __forceinline__ void bucket_node_position(int n, double qk, int& i, float& gamma) {
+  const double vi = (double)(n - 1) * qk;
+  if (vi >= (double)(n - 1)) { i = -1; gamma = (float)(vi + 1.0); }
+  else if (vi < 0.0) { i = -2; gamma = (float)vi; }
+  else { i = (int)vi; gamma = (float)(vi - (double)i); }
+}
+
+// One quantile node of one column.  MODE 0: from the bucket-sorted column, one thread (sets heavy and returns
+// garbage when a bucket is too large for it); MODE 1: the same by a whole warp; MODE 2: from the two sorted runs
+// the sorter leaves.
+template <int MODE>
+__device__ __forceinline__ float bucket_quantile_node(const unsigned* __restrict__ endp, const float* __restrict__ colp,
+                                                      int i, float gamma, int n, int S, float cmin, float cmax,
+                                                      float scale, bool& heavy) {
+  float left, right;
+  if (i == -1) {  // nbutils.py:47-51: position -1 of the full-length sorted row
+    left = right = (n < S) ? Num<float>::nan() : cmax;
+  } else if (i == -2) {
+    left = right = cmin;
+  } else {
+    left = right = cmin;
+    if (MODE == 0) {
+      if (!bucket_select_pair(endp, colp, cmin, scale, i, left, right)) heavy = true;
+    } else if (MODE == 1) {
+      bucket_select_pair_warp(endp, colp, cmin, scale, i, left, right);
+    } else {
+      // both runs in full: the 1024 keys are the valid values plus +inf padding, and in a degenerate column
+      // (infinite range: every key in one bucket) the slot order says nothing about which is which
+      two_run_pair(colp, 512, colp + 512 * 32, 512, i, left, right);
+    }
+  }
+  return bucket_interpolate(left, right, gamma, cmax);
 }
 
 // The sorter path of one pass (heavy buckets / degenerate columns): K1f's sorting network on the 1024 keys of every
@@ -176,12 +218,16 @@ __device__ __noinline__ void bucket_sorter_select(float* buf, const BktOut& o, i
   sort_halves_512(buf, 0);
   const int lane = threadIdx.x & 31;
   const float* colp = buf + lane;
-  int fb_unused = 0;
+  bool heavy_unused = false;
 #pragma unroll 1
   for (int item = threadIdx.x; item < o.n_items; item += kFastThreads) {
     const int k = item >> 5;
     float r = Num<float>::nan();
-    if (n > 0) r = bucket_quantile_node<false>(nullptr, colp, o.qs[k], n, o.S, cmin, cmax, 0.0f, false, fb_unused);
+    if (n > 0) {
+      int i; float gamma;
+      bucket_node_position(n, o.qs[k], i, gamma);
+      r = bucket_quantile_node<2>(nullptr, colp, i, gamma, n, o.S, cmin, cmax, 0.0f, heavy_unused);
+    }
     if (o.mode == 1) {
       if (o.col_ok) o.af[o.o_col + k] = r;
     } else if (o.pass == 0) {
@@ -208,15 +254,20 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
   unsigned* hist = reinterpret_cast<unsigned*>(smem_raw + BktSmem::hist);
   double* psum = reinterpret_cast<double*>(smem_raw + BktSmem::hist);  // alias (NORM reduction, before the histogram)
   float* pmin = reinterpret_cast<float*>(smem_raw + BktSmem::part);
-  float* pmax = pmin + 1024;
-  int* pcnt = reinterpret_cast<int*>(pmax + 1024);
+  float* pmax = pmin + 32 * kBktPitch;
+  int* pcnt = reinterpret_cast<int*>(pmax + 32 * kBktPitch);
   unsigned* tot = reinterpret_cast<unsigned*>(pmin);                   // alias (prefix, after the min / max reduction)
+  unsigned short* work = reinterpret_cast<unsigned short*>(pmin);      // alias (selection, after the prefix)
   float* cminv = reinterpret_cast<float*>(smem_raw + BktSmem::col);
   float* cmaxv = cminv + 32;
   int* cnt = reinterpret_cast<int*>(cmaxv + 32);
   float* mu = reinterpret_cast<float*>(cnt + 32);                      // [2][32]
+  float* scalev = cminv + 5 * 32;
+  int* n_work = reinterpret_cast<int*>(cminv + 7 * 32);
   int* rows_tab = reinterpret_cast<int*>(smem_raw + BktSmem::rows);
   double* qs = reinterpret_cast<double*>(smem_raw + BktSmem::q);
+  int* pos_i = reinterpret_cast<int*>(smem_raw + BktSmem::pos);        // node positions of a column without NaNs (n == S)
+  float* pos_g = reinterpret_cast<float*>(pos_i + kFastMaxNq);
   float* refq = reinterpret_cast<float*>(smem_raw + BktSmem::refq);
 
   const int g = blockIdx.y;
@@ -238,26 +289,42 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
     if (mode == 0 && scaling && tid < 32 && n0 + tid < n_pts) scaling[(n0 + tid) * n_groups + g] = fnan;
     return;
   }
-  if (tid < nq) qs[tid] = q64 ? q64[tid] : (double)q[tid];
+  if (tid < nq) {
+    const double qk = q64 ? q64[tid] : (double)q[tid];
+    qs[tid] = qk;
+    bucket_node_position(S, qk, pos_i[tid], pos_g[tid]);
+  }
   rows_tab[tid] = tid < S ? seg_rows[seg_off[g] + tid] : -1;
+  if (tid < 32) reinterpret_cast<int*>(cminv + 6 * 32)[tid] = (int)st * 4;
+  if (tid < 8 * 32) buf[1024 * 32 + tid] = finf;  // the rows behind the column (bucket_select_pair reads 8-slot windows)
   __syncthreads();
   const bool col_ok = n0 + lane < n_pts;
   const int n_pass = mode == 0 ? 2 : 1;
   const int n_items = nq * 32;
-  const int st4 = (int)st * 4;
+  // the row stride, read back from shared memory: a value ptxas cannot prove uniform stays in a vector register, and
+  // row x stride + base is then ONE IMAD.WIDE per load instead of IMAD.WIDE (uniform operand) + a 64-bit add
+  const int st4 = reinterpret_cast<volatile int*>(cminv + 6 * 32)[lane];  // (32 equal copies, one per lane)
   const long long n_tiles = gridDim.x;
 
   for (int pass = 0; pass < n_pass; ++pass) {
-    // ---- load: warp w takes slots w, w + 32, ...; columns past n_pts read column n0 (always valid memory) ----
+    // ---- load: warp w takes slots 32 w .. 32 w + 31 (one 128-byte row per instruction); columns past n_pts read
+    //      column n0 (always valid memory).  Warps whose 32 slots all hold a row (warp-uniform) load without predicates ----
     float v[32];
+    const int slot0 = warp * 32;
     {
       const char* __restrict__ srcb = reinterpret_cast<const char*>((pass == 0 ? ref : hist_in) + n0 + (col_ok ? lane : 0));
+      if (__all_sync(0xffffffffu, rows_tab[slot0 + lane] >= 0)) {  // (-1: past the segment, or a missing window slot)
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int t = rows_tab[warp + 32 * i];
-        const char* pa = row_address(srcb, t, st4);
-        asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, 0;\n\tmov.f32 %0, %3;\n\t@p ld.global.nc.f32 %0, [%2];\n\t}"
-            : "=f"(v[i]) : "r"(t), "l"(pa), "f"(fnan));
+        for (int i = 0; i < 32; ++i)
+          asm("ld.global.nc.f32 %0, [%1];" : "=f"(v[i]) : "l"(row_address(srcb, rows_tab[slot0 + i], st4)));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int t = rows_tab[slot0 + i];
+          const char* pa = row_address(srcb, t, st4);
+          asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, 0;\n\tmov.f32 %0, %3;\n\t@p ld.global.nc.f32 %0, [%2];\n\t}"
+              : "=f"(v[i]) : "r"(t), "l"(pa), "f"(fnan));
+        }
       }
     }
     // ---- L2 prefetch of what this SM loads next, so that the next load phase (during which nothing else runs on
@@ -276,7 +343,7 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
         if (gn < n_groups) nxt = ref + x2 * 32;
       }
       if (nxt) {
-        const int slot = warp + 32 * lane;
+        const int slot = slot0 + lane;
         int t = -1;
         if (gn == g) t = rows_tab[slot];
         else if (slot < seg_off[gn + 1] - seg_off[gn]) t = seg_rows[seg_off[gn] + slot];
@@ -284,18 +351,16 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
       }
     }
     float my_mn = finf, my_mx = -finf;
-    int my_cnt = 0;
     if (JITTER && use_jitter && pass == 1) {  // hist only, per window slot (_adjustment.py:58-67); see K1f
       const long long seg_base = seg_off[g];
-      float* own = buf + warp * 32 + lane;
+      float* own = buf + slot0 * 32 + lane;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) own[(size_t)i * 1024] = v[i];
+      for (int i = 0; i < 32; ++i) own[i * 32] = v[i];
 #pragma unroll 1
       for (int i = 0; i < 32; ++i)
-        own[(size_t)i * 1024] = jitter_value<float>(
-            own[(size_t)i * 1024], jp, (unsigned long long)((seg_base + warp + 32 * i) * n_pts + n0 + lane));
+        own[i * 32] = jitter_value<float>(own[i * 32], jp, (unsigned long long)((seg_base + slot0 + i) * n_pts + n0 + lane));
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = own[(size_t)i * 1024];
+      for (int i = 0; i < 32; ++i) v[i] = own[i * 32];
     }
     if (normalize) {  // dqm_train: x + (-mean) or x * (1/mean)   (_adjustment.py:167-168)
       double my_sum = 0.0;
@@ -319,51 +384,35 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
         v[i] = (v[i] == v[i] && w != w) ? finf : w;  // (a valid value stays a valid sort key, as in K1f)
       }
     }
-    // ---- column max / count on the raw values (max skips NaN operands), NaN -> +inf keys, column min ----
+    // ---- column min / max of the raw values (min / max skip NaN operands).  NaN values and missing slots need no
+    //      treatment here: their bucket key is 1023 like +inf's (bucket_key), the scatter stores them as +inf, and the
+    //      number of valid samples is 1024 minus the population of bucket 1023 (a real +inf makes the column
+    //      degenerate, and that path counts for itself) ----
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
       my_mx = max3f(my_mx, v[i], v[i + 1]);
-      asm("{\n\t.reg .pred p;\n\tsetp.num.f32 p, %1, %1;\n\t@p add.s32 %0, %0, 1;\n\t@!p mov.f32 %1, %2;\n\t}"
-          : "+r"(my_cnt), "+f"(v[i]) : "f"(finf));
-      asm("{\n\t.reg .pred p;\n\tsetp.num.f32 p, %1, %1;\n\t@p add.s32 %0, %0, 1;\n\t@!p mov.f32 %1, %2;\n\t}"
-          : "+r"(my_cnt), "+f"(v[i + 1]) : "f"(finf));
       my_mn = min3f(my_mn, v[i], v[i + 1]);
     }
-    pmin[warp * 32 + lane] = my_mn;
-    pmax[warp * 32 + lane] = my_mx;
-    pcnt[warp * 32 + lane] = my_cnt;
+    pmin[warp * kBktPitch + lane] = my_mn;
+    pmax[warp * kBktPitch + lane] = my_mx;
 #pragma unroll
     for (int j = 0; j < kBktW * 32 / kFastThreads; ++j) hist[tid + j * kFastThreads] = 0u;
+    if (tid == 0) *n_work = 0;
     __syncthreads();
-    if (warp == 0) {
-      float mn = finf;
-#pragma unroll 8
-      for (int w = 0; w < 32; ++w) mn = fminf(mn, pmin[w * 32 + lane]);
-      cminv[lane] = mn;
-    } else if (warp == 1) {
-      float mx = -finf;
-#pragma unroll 8
-      for (int w = 0; w < 32; ++w) mx = fmaxf(mx, pmax[w * 32 + lane]);
-      cmaxv[lane] = mx;
-    } else if (warp == 2) {
-      int n = 0;
-#pragma unroll 8
-      for (int w = 0; w < 32; ++w) n += pcnt[w * 32 + lane];
-      cnt[lane] = n;
+    {  // warp c reduces column c: lane r holds the partial of warp r (pitch 33: conflict free both ways)
+      float mn = pmin[lane * kBktPitch + warp], mx = pmax[lane * kBktPitch + warp];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      }
+      if (lane == 0) { cminv[warp] = mn; cmaxv[warp] = mx; }
     }
     __syncthreads();
     const float cmin = cminv[lane], cmax = cmaxv[lane];
-    const int n = cnt[lane];
-    float scale;
     bool degenerate;  // infinite / NaN range: the bucket map says nothing, the column goes through the sorter
-    {
-      const float range = __fsub_rn(cmax, cmin);
-      const float sc = __fdiv_rn((float)kBktN - 2.5f, range);  // ceil((v - min) * scale) <= 1022 for finite v <= max
-      const bool fin = range == range && fabsf(range) != finf;
-      const bool ok = fin && range > 0.0f && fabsf(sc) != finf;
-      scale = ok ? sc : 0.0f;
-      degenerate = n > 0 && !(ok || (fin && range == 0.0f));
-    }
+    const float scale = bucket_scale(cmin, cmax, degenerate);
+    if (warp == 0) scalev[lane] = scale;  // (read back by the scatter and by the work-list pass, both behind barriers)
     // ---- histogram: every slot has a key (valid value or +inf), no predicates --------------------------
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
@@ -371,6 +420,8 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
       atomicAdd(hist + (u & (kBktW - 1)) * 32 + lane, (u & kBktW) ? 65536u : 1u);
     }
     __syncthreads();
+    int n = 1024 - (int)(hist[(kBktW - 1) * 32 + lane] >> 16);  // valid samples: all keys but those of bucket 1023
+    if (warp == 0) cnt[lane] = n;
     // ---- exclusive prefix over the buckets of every column: thread (w, lane) owns words 16w .. 16w+15.  The two
     //      halves of a word are prefixed independently by the packed adds (no carry: totals <= 1024); the upper
     //      halves (buckets 512..1023) then start at the number of keys in buckets 0..511 ----------------------
@@ -385,29 +436,41 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
         const unsigned hi = (warp == 31 && j == kBktW / 32 - 1) ? 0u : (w >> 16);
         mxc = max(mxc, max(lo, hi));
       }
-      tot[warp * 32 + lane] = sum;
+      tot[warp * kBktPitch + lane] = sum;
       // Heavy buckets (ties away from the minimum, multi-scale data such as jittered precipitation) or a degenerate
       // column: selecting inside such buckets would cost more than sorting, so the whole tile goes to K1f's sorter
       // now -- keys stored in slot order, no prefix, no scatter.  (The barrier is the one the prefix needs anyway.)
       if (__syncthreads_or((mxc > (unsigned)kBktAbort || degenerate) ? 1 : 0)) {
+        int my_cnt = 0;  // exact count here: a real +inf is a valid sample, its key is not told from a NaN's
 #pragma unroll
-        for (int i = 0; i < 32; ++i) buf[(warp + 32 * i) * 32 + lane] = v[i];
+        for (int i = 0; i < 32; ++i) {
+          my_cnt += v[i] == v[i] ? 1 : 0;
+          buf[(slot0 + i) * 32 + lane] = fminf(v[i], finf);  // NaN -> +inf
+        }
+        pcnt[warp * kBktPitch + lane] = my_cnt;
         __syncthreads();
+        n = 0;
+#pragma unroll 8
+        for (int w = 0; w < 32; ++w) n += pcnt[w * kBktPitch + lane];
         const BktOut bo{af, hist_q, refq, qs, (n0 + lane) * out_stride + (long long)g * nq, n_items, nq, S, mode, pass, kind,
                         col_ok};
         bucket_sorter_select(buf, bo, n, cmin, cmax);
         continue;
       }
-      if (warp == 0) {  // one warp scans the 32 chunk totals of every column
-        unsigned all = 0;  // (two sweeps over shared memory: 32 more registers next to v[] would spill)
-#pragma unroll 8
-        for (int w = 0; w < 32; ++w) all += tot[w * 32 + lane];
-        unsigned run = all << 16;
-#pragma unroll 4
-        for (int w = 0; w < 32; ++w) { const unsigned t = tot[w * 32 + lane]; tot[w * 32 + lane] = run; run += t; }
+      {  // warp c scans the 32 chunk totals of column c (lane r = chunk r) with packed adds; the upper halves start
+         // at the number of keys in buckets 0..511, i.e. the lower half of the grand total
+        const unsigned t = tot[lane * kBktPitch + warp];
+        unsigned inc = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned y = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += y;
+        }
+        const unsigned all = __shfl_sync(0xffffffffu, inc, 31);
+        tot[lane * kBktPitch + warp] = inc - t + (all << 16);
       }
       __syncthreads();
-      unsigned run = tot[warp * 32 + lane];
+      unsigned run = tot[warp * kBktPitch + lane];
 #pragma unroll
       for (int j = 0; j < kBktW / 32; ++j) {
         unsigned* p = hist + (warp * (kBktW / 32) + j) * 32 + lane;
@@ -418,49 +481,69 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
     }
     __syncthreads();
     // ---- scatter: the atomic hands out the slot, start[b] becomes end[b].  (The keys are recomputed -- 3
-    //      instructions -- from opaque copies of cmin / scale: otherwise the compiler keeps the 64 addresses and
-    //      increments of the histogram pass alive across the prefix, i.e. spills them to local memory.) --------
+    //      instructions -- from cmin / scale re-read from shared memory (volatile: opaque to nvvm AND ptxas): otherwise
+    //      the compiler keeps the 64 addresses and increments of the histogram pass alive across the prefix, i.e.
+    //      spills them to local memory.) --------
     {
-      float cmin_b = cmin, scale_b = scale;
-      asm volatile("" : "+f"(cmin_b), "+f"(scale_b));
+      const float cmin_b = *reinterpret_cast<volatile float*>(cminv + lane);
+      const float scale_b = *reinterpret_cast<volatile float*>(scalev + lane);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const unsigned u = bucket_key(v[i], cmin_b, scale_b);
         const bool hi = (u & kBktW) != 0;
         const unsigned old = atomicAdd(hist + (u & (kBktW - 1)) * 32 + lane, hi ? 65536u : 1u);
         const unsigned pos = hi ? (old >> 16) : (old & 0xffffu);
-        buf[pos * 32 + lane] = v[i];
+        buf[pos * 32 + lane] = fminf(v[i], finf);  // (NaN -> +inf: the selection windows may reach into bucket 1023)
       }
     }
     __syncthreads();
     // ---- quantiles: node k = item / 32 is warp-uniform, lane = column.  Results go straight to global memory
     //      (4-byte stores 2400 bytes apart; the 8 nodes of a 32-byte sector are written by 8 warps within the same
     //      round, the L2 write-back merges them) -- no staging buffer, no result registers across the barrier ----
-    const unsigned* endp = hist + lane;
-    const float* colp = buf + lane;
-    const long long o_col = (n0 + lane) * out_stride + (long long)g * nq;
-    int fb = 0;
+    auto emit = [&](int k, int c, float r) {
+      const long long o = (n0 + c) * out_stride + (long long)g * nq + k;
+      const bool okc = n0 + c < n_pts;
+      if (mode == 1) {
+        if (okc) af[o] = r;
+      } else if (pass == 0) {
+        refq[k * 33 + c] = r;
+      } else if (okc) {
+        const float rq = refq[k * 33 + c];
+        hist_q[o] = r;
+        af[o] = kind == XSDBA_KIND_ADD ? __fsub_rn(rq, r) : __fdiv_rn(rq, r);
+      }
+    };
 #pragma unroll 1
     for (int item = tid; item < n_items; item += kFastThreads) {
       const int k = item >> 5;
       float r = fnan;
-      if (n > 0) r = bucket_quantile_node<true>(endp, colp, qs[k], n, S, cmin, cmax, scale, degenerate, fb);
-      if (mode == 1) {
-        if (col_ok) af[o_col + k] = r;
-      } else if (pass == 0) {
-        refq[k * 33 + lane] = r;
-      } else if (col_ok) {
-        const float rq = refq[k * 33 + lane];
-        hist_q[o_col + k] = r;
-        af[o_col + k] = kind == XSDBA_KIND_ADD ? __fsub_rn(rq, r) : __fdiv_rn(rq, r);
+      bool heavy = false;
+      if (n > 0) {
+        int i = pos_i[k];
+        float gamma = pos_g[k];
+        if (n != S) bucket_node_position(n, qs[k], i, gamma);  // a column with NaNs: its own positions
+        r = bucket_quantile_node<0>(hist + lane, buf + lane, i, gamma, n, S, cmin, cmax, scale, heavy);
+      }
+      if (heavy) work[atomicAdd(n_work, 1)] = (unsigned short)item;  // a bucket of 9..24 samples: a warp's job
+      else emit(k, lane, r);
+    }
+    __syncthreads();
+    {
+      const int n_heavy = *n_work;
+#pragma unroll 1
+      for (int e = warp; e < n_heavy; e += 32) {
+        const int item = work[e], k = item >> 5, c = item & 31;
+        const float cmin_c = cminv[c], cmax_c = cmaxv[c];
+        const int n_c = cnt[c];
+        bool unused = false;
+        const float scale_c = scalev[c];
+        int i; float gamma;
+        bucket_node_position(n_c, qs[k], i, gamma);
+        const float r = bucket_quantile_node<1>(hist + c, buf + c, i, gamma, n_c, S, cmin_c, cmax_c, scale_c, unused);
+        if (lane == 0) emit(k, c, r);
       }
     }
-    if (__syncthreads_or(fb)) {
-      // a bucket too large to select from (heavy ties, multi-scale data) or a degenerate column: the scattered
-      // column holds all 1024 keys (valid values, then +inf) -- run K1f's sorter on it, select from the two runs
-      const BktOut bo{af, hist_q, refq, qs, o_col, n_items, nq, S, mode, pass, kind, col_ok};
-      bucket_sorter_select(buf, bo, n, cmin, cmax);
-      }
+    __syncthreads();  // refq complete; hist / buf / the partial tables are free for the next pass
   }
   if (normalize && mode == 0 && scaling && tid < 32 && n0 + tid < n_pts) {
     const float mr = mu[tid], mh = mu[32 + tid];  // scaling = get_correction(mu_hist, mu_ref)

@@ -795,48 +795,124 @@ adjust_fast_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
 }
 
 // =============================================================================================
-// K2p + K2t: packed tables and the tile-persistent adjust kernel (float32, grouped nearest).
+// K2p + K2t: packed decision tables and the tile-persistent adjust kernel (float32, grouped nearest).
 //
-// K2p `pack_tables_kernel` turns the caller's point-major af / hist_q [N][G][nq] into per-(tile, group)
-// slots in the exact shared-memory image the lookup wants: xs[LD][32], ys[LD][32] (column = point, NaN
-// nodes dropped, +inf padding), bounds / constants and node counts.  One slot is one contiguous,
-// 16-byte aligned block, so K2t fetches it with a single bulk async copy (cp.async.bulk -> SASS UBLKCP,
-// completion on an mbarrier) -- no transposition, no per-element staging work in the hot kernel.
+// The 2-D nearest rule restricted to one table row is a step function of the sample: node k answers for the
+// samples between the midpoints towards nodes k-1 and k+1.  Float32 arithmetic on the sample cannot be trusted near
+// a midpoint (tie) or when the nearest in-row node is >= 1 away (a node of a neighbouring row, one unit of group
+// coordinate away, may be nearer), so K2p `pack_tables_kernel` turns every (point, group) row of the caller's
+// point-major af / hist_q [N][G][nq] into nq + 2 INTERVALS with float32 bounds (directed rounding, towards the node):
+//     interval 0        : (-inf, blo)                             -> first factor (constant extrapolation) or NaN
+//     interval k + 1    : [lo_k, hi_k] around node k, inside its midpoints (shrunk by 1e-5 of the node gap),
+//                          inside node +- 0.99 and inside [blo, bhi]                      -> af[k]
+//     interval nq' + 1  : (bhi, +inf]                             -> last factor or NaN
+// hi is ascending.  A sample x belongs to interval i = #{hi < x} and is DECIDED iff x >= lo_i; the undecided ones
+// (gaps between intervals: ~1e-4 of the samples) go to the exact float64 / cross-row second pass as before.
+// Rows are stored column-major per tile of 32 points -- hi[R][32], lo[R][32], y[R][32], R = nq + 2, then nv[32]
+// (number of NaN-free nodes, for the second pass) -- the exact shared-memory image of the lookup, so K2t fetches a
+// row with three bulk async copies (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier).
 //
-// K2t `adjust_tile_kernel`: one CTA per tile of 32 points walks ALL groups; a ring of four slots holds
-// rows g-1, g, g+1 while row g+2 is in flight, so table traffic is (G+2) slots per tile instead of 3G
-// and the staging latency is hidden behind the previous group's streaming.
+// K2t `adjust_tile_kernel`: one CTA per tile of 32 points walks ALL groups; a ring of two slots holds the current
+// group's intervals while the next one streams in.  Per sample: a 6-step branch-free search on hi, one compare
+// against lo, one load of y -- about half the instructions of a search on the nodes followed by the distance logic.
 // =============================================================================================
-template <int LD>
-struct PackedSlot {
-  float xs[LD * 32];
-  float ys[LD * 32];
-  float blo[32], bhi[32], clo[32], chi[32];
-  int nv[32];
-};
+__host__ __device__ constexpr size_t packed_slot_floats(int nq) { return (size_t)(3 * (nq + 2) + 1) * 32; }
 
-template <int TOP>
 __global__ void __launch_bounds__(kThreads)
 pack_tables_kernel(const float* __restrict__ af, const float* __restrict__ hist_q, long long n_pts, int n_groups,
-                   int nq, PackedSlot<2 * TOP>* __restrict__ packed) {
-  constexpr int C = 32, LD = 2 * TOP;
+                   int nq, int extrap, float* __restrict__ packed) {
+  constexpr int C = 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  PackedSlot<LD>* slot = reinterpret_cast<PackedSlot<LD>*>(smem_raw);
-  float* stage = reinterpret_cast<float*>(smem_raw + sizeof(PackedSlot<LD>));
-  Tables<float, C> tb;
-  tb.nq = nq; tb.top = TOP; tb.ld = LD;
-  // one-slot view: stage_tables(grouped = false) fills slot index 1
-  for (int sl = 0; sl < 3; ++sl) { tb.xsl[sl] = slot->xs; tb.ysl[sl] = slot->ys; tb.nvl[sl] = slot->nv; }
-  tb.blo = slot->blo; tb.bhi = slot->bhi; tb.clo = slot->clo; tb.chi = slot->chi;
+  // the row of every point as it lies in memory (nq contiguous nodes), pitch odd: column-wise reads are conflict free
+  const int pitch = nq | 1;
+  float* sx = reinterpret_cast<float*>(smem_raw);  // [C][pitch] hist_q, compacted in place when a row has NaNs
+  float* sy = sx + C * pitch;                      // [C][pitch] af
+  __shared__ int nv[C], bad[C];
+  __shared__ float s_blo[C], s_bhi[C], s_clo[C], s_chi[C];
   const int g = blockIdx.y;
   const long long n0 = (long long)blockIdx.x * C;
-  // present group g as the only group of a one-group table
-  tb.gx = hist_q + (long long)g * nq; tb.gy = af + (long long)g * nq; tb.x_shared = false; tb.G = 1;
-  tb.pt_stride = (long long)n_groups * nq;
-  stage_tables<float, C>(tb, stage, n0, n_pts, 0, false);
-  const float4* src = reinterpret_cast<const float4*>(slot);
-  float4* dst = reinterpret_cast<float4*>(packed + ((size_t)blockIdx.x * n_groups + g));
-  for (int i = threadIdx.x; i < (int)(sizeof(PackedSlot<LD>) / 16); i += blockDim.x) dst[i] = src[i];
+  const long long pt_stride = (long long)n_groups * nq;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const float finf = Num<float>::inf(), fnan = Num<float>::nan();
+  if (threadIdx.x < C) bad[threadIdx.x] = 0;
+  __syncthreads();
+  int has_nan = 0;
+  for (int c = warp; c < C; c += n_warps) {  // one point per warp and round: contiguous reads, no index division
+    const bool ok = n0 + c < n_pts;
+    const long long o = (n0 + c) * pt_stride + (long long)g * nq;
+    int flag = 0;
+    for (int k = lane; k < nq; k += 32) {
+      const float xv = ok ? hist_q[o + k] : fnan, yv = ok ? af[o + k] : fnan;
+      sx[c * pitch + k] = xv;
+      sy[c * pitch + k] = yv;
+      flag |= (xv != xv || yv != yv) ? 1 : 0;
+      flag |= (fabsf(xv) == finf) ? 2 : 0;
+    }
+    flag = __reduce_or_sync(0xffffffffu, flag);
+    if (lane == 0 && flag) bad[c] = flag;
+    has_nan |= flag & 1;
+  }
+  has_nan = __syncthreads_or(has_nan);
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
+    float* x = sx + c * pitch;
+    float* y = sy + c * pitch;
+    if (!(bad[c] & 1)) {
+      nv[c] = nq; s_blo[c] = x[0]; s_bhi[c] = x[nq - 1]; s_clo[c] = y[0]; s_chi[c] = y[nq - 1];
+    } else {  // NaN nodes are dropped (utils.py:381-382); bounds / constants from the first / last non-NaN of each table
+      float blo = fnan, bhi = fnan, clo = fnan, chi = fnan;
+      bool have_b = false, have_c = false;
+      int w = 0;
+      for (int k = 0; k < nq; ++k) {
+        const float xv = x[k], yv = y[k];
+        if (xv == xv) { if (!have_b) { blo = xv; have_b = true; } bhi = xv; }
+        if (yv == yv) { if (!have_c) { clo = yv; have_c = true; } chi = yv; }
+        if (xv == xv && yv == yv) { x[w] = xv; y[w] = yv; ++w; }
+      }
+      nv[c] = w; s_blo[c] = blo; s_bhi[c] = bhi; s_clo[c] = clo; s_chi[c] = chi;
+    }
+  }
+  __syncthreads();
+  const float* xs = sx + lane * pitch;
+  const float* ys = sy + lane * pitch;
+  const int n = nv[lane];
+  const bool usable = n > 0 && !(bad[lane] & 2);  // otherwise every (non-NaN) sample goes to the exact pass
+  const float blo = s_blo[lane], bhi = s_bhi[lane];
+  const float clo = extrap == 0 ? s_clo[lane] : fnan, chi = extrap == 0 ? s_chi[lane] : fnan;
+  const int R = nq + 2;
+  float* out = packed + ((size_t)blockIdx.x * n_groups + g) * packed_slot_floats(nq);
+  // float32 arithmetic with directed rounding, every bound moved TOWARDS its node: the decided intervals can only be
+  // narrower than the exact ones (midpoint +- 1e-5 gap, node +- 0.99), never wider
+  const float tiny = __int_as_float(1);  // smallest subnormal: x -+ tiny rounds to the neighbour of x
+  for (int j = warp; j < R; j += n_warps) {
+    float hi = finf, lo = finf, y = fnan;
+    if (usable) {
+      if (j == 0) {
+        hi = __fadd_rd(blo, -tiny); lo = -finf; y = clo;
+      } else if (j <= n) {
+        const int k = j - 1;
+        const float xk = xs[k];
+        float L = blo, H = bhi;
+        if (k > 0) {
+          const float xl = xs[k - 1];
+          L = __fadd_ru(__fmul_ru(0.5f, __fadd_ru(xl, xk)), __fmul_ru(1e-5f, __fsub_ru(xk, xl)));
+        }
+        if (k < n - 1) {
+          const float xh = xs[k + 1];
+          H = __fsub_rd(__fmul_rd(0.5f, __fadd_rd(xk, xh)), __fmul_ru(1e-5f, __fsub_ru(xh, xk)));
+        }
+        lo = fmaxf(L, __fadd_ru(xk, -0.99f));
+        hi = fminf(H, __fadd_rd(xk, 0.99f));
+        y = ys[k];
+      } else if (j == n + 1) {
+        lo = __fadd_ru(bhi, tiny); y = chi;
+      }
+    }
+    out[(size_t)j * C + lane] = hi;
+    out[(size_t)(R + j) * C + lane] = lo;
+    out[(size_t)(2 * R + j) * C + lane] = y;
+  }
+  if (warp == 0) reinterpret_cast<int*>(out + (size_t)3 * R * C)[lane] = n;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -857,126 +933,97 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                    smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-
-// Exact 2-D nearest rule straight from the raw global tables (no staging): used for the few samples the
-// float32 fast path of K2t cannot decide (near-ties, far nodes, empty rows).  Same candidate order as
-// lookup_2d_nearest_n: centre row first, then rows at distance 1, 2, ... (-, +), nodes ascending, strict <.
-__device__ float exact_lookup_global(const float* __restrict__ hist_q, const float* __restrict__ af, long long pt, int G,
-                                     int nq, int g, float x, int extrap) {
-  if (x != x) return Num<float>::nan();
-  const long long base = pt * (long long)G * nq;
-  const float* xr = hist_q + base + (long long)g * nq;
-  const float* yr = af + base + (long long)g * nq;
-  float blo = Num<float>::nan(), bhi = blo, clo = blo, chi = blo;
-  bool hb = false, hc = false;
-  for (int k = 0; k < nq; ++k) {
-    const float xv = xr[k], yv = yr[k];
-    if (xv == xv) { if (!hb) { blo = xv; hb = true; } bhi = xv; }
-    if (yv == yv) { if (!hc) { clo = yv; hc = true; } chi = yv; }
-  }
-  const double xd = (double)x;
-  if (xd < (double)blo) return extrap == 0 ? clo : Num<float>::nan();
-  if (xd > (double)bhi) return extrap == 0 ? chi : Num<float>::nan();
-  double best_d2 = __longlong_as_double(0x7ff0000000000000LL);
-  float best_y = Num<float>::nan();
-  for (int dist = 0; dist <= G + 1; ++dist) {
-    const double dg2 = (double)dist * (double)dist;
-    if (dg2 >= best_d2) break;
-    for (int sgn = -1; sgn <= 1; sgn += 2) {
-      if (dist == 0 && sgn > 0) break;
-      const int pr = g + 1 + sgn * dist;  // padded row index in [0, G+1]
-      if (pr < 0 || pr > G + 1) continue;
-      const int gg = (pr - 1 + G) % G;
-      const float* gx = hist_q + base + (long long)gg * nq;
-      const float* gy = af + base + (long long)gg * nq;
-      for (int k = 0; k < nq; ++k) {
-        const float xv = gx[k], yv = gy[k];
-        if (xv != xv || yv != yv) continue;
-        const double d = fabs(xd - (double)xv);
-        const double d2 = __dadd_rn(__dmul_rn(d, d), dg2);
-        if (d2 < best_d2) { best_d2 = d2; best_y = yv; }
-      }
+// Best candidate of one table row for the exact 2-D nearest rule (second pass).  `sorted`: the row is NaN free
+// (hence ascending): the nearest node is one of the two neighbours of a binary search; otherwise all nq nodes are
+// scanned.  Tie rule of the scan in both cases: the first (lowest-index) node among equally near ones, i.e. the left
+// neighbour on a distance tie and the first element of a run of duplicated nodes; strict < between rows.
+__device__ __forceinline__ void nearest_in_raw_row(const float* __restrict__ gx, const float* __restrict__ gy, int nq,
+                                                   bool sorted, double xd, double dg2, double& best_d2, float& best_y) {
+  if (!sorted) {
+    for (int k = 0; k < nq; ++k) {
+      const float xv = gx[k], yv = gy[k];
+      if (xv != xv || yv != yv) continue;
+      const double d = fabs(xd - (double)xv);
+      const double d2 = __dadd_rn(__dmul_rn(d, d), dg2);
+      if (d2 < best_d2) { best_d2 = d2; best_y = yv; }
     }
+    return;
   }
-  return best_y;
-}
-
-struct FixEntry { long long off; long long pt; float x; int g; };
-
-// second pass of K2t: the deferred samples (typically ~1e-4 of all) get the exact rule
-__global__ void adjust_fix_kernel(const FixEntry* __restrict__ fix, const unsigned* __restrict__ count, unsigned cap,
-                                  const float* __restrict__ af, const float* __restrict__ hist_q, int G, int nq, int extrap,
-                                  int kind, float* __restrict__ scen) {
-  const unsigned n = min(*count, cap);
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const FixEntry e = fix[i];
-    const float f = exact_lookup_global(hist_q, af, e.pt, G, nq, e.g, e.x, extrap);
-    scen[e.off] = kind == XSDBA_KIND_ADD ? __fadd_rn(e.x, f) : __fmul_rn(e.x, f);
-  }
-}
-
-// The same second pass on the PACKED tables (K2p's output, still alive): every row there is compacted (NaN nodes
-// dropped), ascending and +inf padded, so the nearest node of a row is one of the two neighbours of a binary search
-// instead of a scan of all nq nodes -- about 20 scattered 32-byte sectors per sample instead of 56, and a tenth of the
-// instructions.  Tie rule of the scan kept: the first (lowest-index) node among equally near ones, i.e. the left
-// neighbour on a distance tie and the first element of a run of duplicated nodes.
-template <int LD>
-__device__ __forceinline__ void nearest_in_sorted_row(const float* __restrict__ xs, const float* __restrict__ ys, int n,
-                                                      double xd, double dg2, double& best_d2, float& best_y) {
-  if (n <= 0) return;
   const float xf = (float)xd;  // (x is a float32 sample: exact)
-  int lo = 0, hi = n;          // lower bound: first node >= x
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (xs[mid * 32] < xf) lo = mid + 1; else hi = mid; }
+  int lo = 0, hi = nq;         // lower bound: first node >= x
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (gx[mid] < xf) lo = mid + 1; else hi = mid; }
   const int i = lo;
   double d = __longlong_as_double(0x7ff0000000000000LL);
   int idx = -1;
   if (i > 0) {
-    const float xl = xs[(i - 1) * 32];
+    const float xl = gx[i - 1];
     d = fabs(xd - (double)xl);
     idx = i - 1;
-    if (i > 1 && xs[(i - 2) * 32] == xl) {  // duplicated node: the scan keeps its first occurrence
+    if (i > 1 && gx[i - 2] == xl) {  // duplicated node: the scan keeps its first occurrence
       int a = 0, b = i - 1;
-      while (a < b) { const int mid = (a + b) >> 1; if (xs[mid * 32] < xl) a = mid + 1; else b = mid; }
+      while (a < b) { const int mid = (a + b) >> 1; if (gx[mid] < xl) a = mid + 1; else b = mid; }
       idx = a;
     }
   }
-  if (i < n) {
-    const double dr = fabs((double)xs[i * 32] - xd);
+  if (i < nq) {
+    const double dr = fabs((double)gx[i] - xd);
     if (idx < 0 || dr < d) { d = dr; idx = i; }
   }
   const double d2 = __dadd_rn(__dmul_rn(d, d), dg2);
-  if (d2 < best_d2) { best_d2 = d2; best_y = ys[idx * 32]; }
+  if (d2 < best_d2) { best_d2 = d2; best_y = gy[idx]; }
 }
 
-template <int TOP>
-__global__ void adjust_fix_packed_kernel(const FixEntry* __restrict__ fix, const unsigned* __restrict__ count, unsigned cap,
-                                         const PackedSlot<2 * TOP>* __restrict__ packed, int G, int extrap, int kind,
-                                         float* __restrict__ scen) {
-  constexpr int LD = 2 * TOP;
+struct FixEntry { long long off; long long pt; float x; int g; };
+
+// Second pass of K2t: the deferred samples (typically ~1e-4 of all) get the exact rule -- float64 distances over the
+// cyclically padded rows, centre row first, then rows at distance 1, 2, ... (-, +), as lookup_2d_nearest_n -- from
+// the caller's raw point-major tables: a point's row is nq contiguous floats (7 sectors), and K2p's nv says whether
+// it is NaN free, i.e. searchable.  nv == nullptr: scan everything (debug / no packed image).
+__global__ void adjust_fix_kernel(const FixEntry* __restrict__ fix, const unsigned* __restrict__ count, unsigned cap,
+                                  const float* __restrict__ af, const float* __restrict__ hist_q, int G, int nq, int extrap,
+                                  int kind, const float* __restrict__ packed, float* __restrict__ scen) {
   const unsigned n_fix = min(*count, cap);
+  const size_t slot_f = packed_slot_floats(nq);
   for (unsigned e_i = blockIdx.x * blockDim.x + threadIdx.x; e_i < n_fix; e_i += gridDim.x * blockDim.x) {
     const FixEntry e = fix[e_i];
-    const int lane = (int)(e.pt & 31);
-    const PackedSlot<LD>* tile = packed + (size_t)(e.pt >> 5) * G;
-    const PackedSlot<LD>& c = tile[e.g];
-    const double xd = (double)e.x;
     const float fnan = Num<float>::nan();
-    float f;
-    if (e.x != e.x) f = fnan;
-    else if (xd < (double)c.blo[lane]) f = extrap == 0 ? c.clo[lane] : fnan;
-    else if (xd > (double)c.bhi[lane]) f = extrap == 0 ? c.chi[lane] : fnan;
-    else {
-      double best_d2 = __longlong_as_double(0x7ff0000000000000LL);
-      f = fnan;
-      for (int dist = 0; dist <= G + 1; ++dist) {
-        const double dg2 = (double)dist * (double)dist;
-        if (dg2 >= best_d2) break;
-        for (int sgn = -1; sgn <= 1; sgn += 2) {
-          if (dist == 0 && sgn > 0) break;
-          const int pr = e.g + 1 + sgn * dist;  // padded row index in [0, G+1]
-          if (pr < 0 || pr > G + 1) continue;
-          const PackedSlot<LD>& r = tile[(pr - 1 + G) % G];
-          nearest_in_sorted_row<LD>(r.xs + lane, r.ys + lane, r.nv[lane], xd, dg2, best_d2, f);
+    float f = fnan;
+    if (e.x == e.x) {
+      const long long base = e.pt * (long long)G * nq;
+      const int lane = (int)(e.pt & 31);
+      const float* tile = packed ? packed + (size_t)(e.pt >> 5) * G * slot_f + (size_t)3 * (nq + 2) * 32 : nullptr;
+      auto row_sorted = [&](int gg) {
+        return tile && reinterpret_cast<const int*>(tile + (size_t)gg * slot_f)[lane] == nq;
+      };
+      const float* xr = hist_q + base + (long long)e.g * nq;
+      const float* yr = af + base + (long long)e.g * nq;
+      float blo = fnan, bhi = fnan, clo = fnan, chi = fnan;
+      if (row_sorted(e.g)) {
+        blo = xr[0]; bhi = xr[nq - 1]; clo = yr[0]; chi = yr[nq - 1];
+      } else {
+        bool hb = false, hc = false;
+        for (int k = 0; k < nq; ++k) {
+          const float xv = xr[k], yv = yr[k];
+          if (xv == xv) { if (!hb) { blo = xv; hb = true; } bhi = xv; }
+          if (yv == yv) { if (!hc) { clo = yv; hc = true; } chi = yv; }
+        }
+      }
+      const double xd = (double)e.x;
+      if (xd < (double)blo) f = extrap == 0 ? clo : fnan;
+      else if (xd > (double)bhi) f = extrap == 0 ? chi : fnan;
+      else {
+        double best_d2 = __longlong_as_double(0x7ff0000000000000LL);
+        for (int dist = 0; dist <= G + 1; ++dist) {
+          const double dg2 = (double)dist * (double)dist;
+          if (dg2 >= best_d2) break;
+          for (int sgn = -1; sgn <= 1; sgn += 2) {
+            if (dist == 0 && sgn > 0) break;
+            const int pr = e.g + 1 + sgn * dist;  // padded row index in [0, G+1]
+            if (pr < 0 || pr > G + 1) continue;
+            const int gg = (pr - 1 + G) % G;
+            nearest_in_raw_row(hist_q + base + (long long)gg * nq, af + base + (long long)gg * nq, nq, row_sorted(gg), xd,
+                               dg2, best_d2, f);
+          }
         }
       }
     }
@@ -991,49 +1038,61 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   return v;
 }
 
-constexpr int kFixStage = 192;     // deferred samples staged per CTA between two flushes (K2t)
+constexpr int kFixStage = 64;       // deferred samples staged per CTA between two flushes (K2t)
 constexpr int kTileMaxRows = 1024;  // member rows of one group kept in shared memory by K2t (x2 buffers)
 
+// shared memory of K2t: ring of 2 slots {hi[2 TOP][32], lo[R][32], y[R][32]}, 2 row lists, mbarriers, fix staging
+__host__ __device__ constexpr size_t tile_slot_floats(int top, int nq) { return (size_t)(2 * top + 2 * (nq + 2)) * 32; }
+
 template <int TOP>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp, int st,
-                   const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows, int n_groups,
-                   const float* __restrict__ af, const float* __restrict__ hist_q, int nq,
-                   const PackedSlot<2 * TOP>* __restrict__ packed, int extrap, int kind, float* __restrict__ scen,
+                   const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows, int n_groups, int nq,
+                   const float* __restrict__ packed, int kind, float* __restrict__ scen,
                    FixEntry* __restrict__ fix, unsigned* __restrict__ fix_count, unsigned fix_cap) {
-  constexpr int C = 32, U = 8, LD = 2 * TOP, RING = 2;  // centre rows only: current group + the next one in flight
-  typedef PackedSlot<LD> Slot;
+  constexpr int C = 32, U = 8, LD = 2 * TOP, RING = 2;  // current group + the next one in flight
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Slot* ring = reinterpret_cast<Slot*>(smem_raw);
-  int* rows_sm = reinterpret_cast<int*>(smem_raw + RING * sizeof(Slot));     // [2][kTileMaxRows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rows_sm + 2 * kTileMaxRows);  // [RING]
+  const int R = nq + 2;  // rows per array in the packed image; hi rows [R, LD) of the ring keep their initial +inf
+  const int slot_fl = (int)tile_slot_floats(TOP, nq);
+  const uint32_t off_lo = LD * C * 4, off_y = (LD + R) * C * 4;               // byte offsets inside a ring slot (CTA-uniform)
+  float* ring = reinterpret_cast<float*>(smem_raw);                            // [RING]{hi[LD][C], lo[R][C], y[R][C]}
+  int* rows_sm = reinterpret_cast<int*>(ring + RING * slot_fl);                // [2][kTileMaxRows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rows_sm + 2 * kTileMaxRows);    // [RING]
   // deferred samples are collected per CTA and appended to the global list once per group: one global atomic per
   // flush instead of one per sample (a warp otherwise waits a global round trip for its slot number)
-  FixEntry* stage_fix = reinterpret_cast<FixEntry*>(bars + 4);               // [kFixStage]
-  unsigned* stage_n = reinterpret_cast<unsigned*>(stage_fix + kFixStage);    // [1] (+ [1] flush base)
+  FixEntry* stage_fix = reinterpret_cast<FixEntry*>(bars + 4);                 // [kFixStage]
+  unsigned* stage_n = reinterpret_cast<unsigned*>(stage_fix + kFixStage);      // [1] (+ [1] flush base)
 
   const int tile = blockIdx.x;
   const long long n0 = (long long)tile * C;
   const int G = n_groups;
-  const Slot* my = packed + (size_t)tile * G;
+  const size_t slot_f = packed_slot_floats(nq);
+  const float* my = packed + (size_t)tile * G * slot_f;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const long long pt = n0 + lane;
   const bool pt_ok = pt < n_pts;
   const float* __restrict__ src = sim + (pt_ok ? pt : n0) * sp;
   float* __restrict__ dst = scen + (pt_ok ? pt : n0) * sp;
-  const float fnan = Num<float>::nan(), finf = Num<float>::inf();
+  const float finf = Num<float>::inf();
 
+  for (int i = threadIdx.x; i < RING * slot_fl; i += blockDim.x) ring[i] = finf;
   if (threadIdx.x == 0) {
     for (int i = 0; i < RING; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     stage_n[0] = 0;
   }
+  // (generic-proxy writes above vs. the async-proxy bulk copies below)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
-  // the row of group e lives in ring slot e % RING (use number e / RING of that slot's mbarrier)
+  // the intervals of group e live in ring slot e % RING (use number e / RING of that slot's mbarrier)
   auto fetch = [&](int e) {
     const int s = e % RING;
-    mbar_expect_tx(&bars[s], (uint32_t)sizeof(Slot));
-    bulk_g2s(&ring[s], &my[e], (uint32_t)sizeof(Slot), &bars[s]);
+    const uint32_t bytes = (uint32_t)R * C * 4;
+    mbar_expect_tx(&bars[s], 3 * bytes);
+    const float* g0 = my + (size_t)e * slot_f;
+    float* s0 = ring + (size_t)s * slot_fl;
+    bulk_g2s(s0, g0, bytes, &bars[s]);
+    bulk_g2s(s0 + LD * C, g0 + (size_t)R * C, 2 * bytes, &bars[s]);  // lo and y are adjacent on both sides
   };
   if (threadIdx.x == 0) fetch(0);
   {
@@ -1059,28 +1118,27 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
     if (threadIdx.x == 0 && g + 1 < G) fetch(g + 1);  // streams in while this group is processed
     mbar_wait(&bars[g % RING], (uint32_t)((g / RING) & 1));
 
-    const Slot& sc = ring[g % RING];
-    const float* xs = sc.xs + lane;
-    const float* ys = sc.ys + lane;
-    const int n = sc.nv[lane];
-    const float blo = sc.blo[lane], bhi = sc.bhi[lane];
-    const float clo = extrap == 0 ? sc.clo[lane] : fnan, chi = extrap == 0 ? sc.chi[lane] : fnan;
-
     // two register sets (A, B) alternate between "being loaded" and "being processed": the next batch of U rows is
     // always in flight while the current one is searched, and no register-to-register copies are needed
-    const uint32_t xb = (uint32_t)__cvta_generic_to_shared(xs);
+    const uint32_t xb = smem_u32(ring + (size_t)(g % RING) * slot_fl + lane);  // hi[0] of this lane's column
     const char* __restrict__ srcb = reinterpret_cast<const char*>(src);  // byte addressing: one IMAD.WIDE per sample
     char* __restrict__ dstb = reinterpret_cast<char*>(dst);
     const int st4 = st * 4;
-    auto load_batch = [&](int mb, float (&xv)[U], int (&ov)[U]) {
+    // (the row numbers are read from shared memory again at store time: keeping them next to the two value sets
+    //  costs 16 registers, i.e. the fourth resident CTA)
+    auto batch_rows = [&](int mb, int (&ov)[U]) {
       const int4 r0 = *reinterpret_cast<const int4*>(rows + mb), r1 = *reinterpret_cast<const int4*>(rows + mb + 4);
       ov[0] = r0.x; ov[1] = r0.y; ov[2] = r0.z; ov[3] = r0.w;
       ov[4] = r1.x; ov[5] = r1.y; ov[6] = r1.z; ov[7] = r1.w;
+    };
+    auto load_batch = [&](int mb, float (&xv)[U]) {
+      int ov[U];
+      batch_rows(mb, ov);
 #pragma unroll
       for (int j = 0; j < U; ++j) xv[j] = *reinterpret_cast<const float*>(srcb + (long long)ov[j] * st4);
     };
-    auto process_batch = [&](int mb, const float (&x)[U], const int (&ov)[U]) {
-      uint32_t po[U];  // shared-memory address of xs[pos]: the search advances it by step rows (128 B each)
+    auto process_batch = [&](int mb, const float (&x)[U]) {
+      uint32_t po[U];  // shared-memory address of hi[i]: the search advances it by step rows (128 B each)
 #pragma unroll
       for (int j = 0; j < U; ++j) po[j] = xb;
 #pragma unroll
@@ -1091,29 +1149,18 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
           po[j] = v < x[j] ? po[j] + step * (C * 4) : po[j];
         }
       }
+      int ov[U];
+      batch_rows(mb, ov);
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        // po = address of xs[i], i = #nodes < x (<= n); xs[n] = +inf.  ys sits LD rows after xs.
-        const bool first = po[j] == xb;
-        const uint32_t pl = first ? xb : po[j] - C * 4;
-        const float xl = lds_f32(pl), xh = lds_f32(po[j]);
-        const float yl = lds_f32(pl + LD * C * 4);
-        const bool last = xh == finf;  // i == n (or a genuine +inf node: same treatment, dh = inf)
-        const float yh = lds_f32((last ? pl : po[j]) + LD * C * 4);
-        const float dl = first ? finf : x[j] - xl;
-        const float dh = xh - x[j];
-        const float dmin = fminf(dl, dh);
-        float f = dh < dl ? yh : yl;
-        const bool below = x[j] < blo, above = x[j] > bhi;
-        // NaN samples need no lookup at all: x (+|*) anything = NaN
-        const bool sure = ((fabsf(dl - dh) > 1e-5f * dmin) && (dmin < 0.99f)) || (x[j] != x[j]);
-        f = below ? clo : f;
-        f = above ? chi : f;
+        // po = address of hi[i], i = #{hi < x}: the interval of x; decided iff x >= lo[i] (a NaN sample is "decided":
+        // NaN (+|*) anything = NaN)
+        const float lo = lds_f32(po[j] + off_lo), f = lds_f32(po[j] + off_y);
         if (mb + j < n_rows && pt_ok) {
           *reinterpret_cast<float*>(dstb + (long long)ov[j] * st4) =
               kind == XSDBA_KIND_ADD ? __fadd_rn(x[j], f) : __fmul_rn(x[j], f);
-          if (!(sure || below || above)) {
-            // float32 cannot decide (near-tie / far node / empty row): defer to the exact second pass
+          if (x[j] < lo) {
+            // between two intervals (near-tie / far node / empty row): defer to the exact second pass
             const FixEntry en{(long long)(dst - scen) + (long long)ov[j] * st, pt, x[j], g};
             const unsigned sl = atomicAdd(stage_n, 1u);
             if (sl < kFixStage) {
@@ -1128,17 +1175,16 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
     };
     {
       float xa[U], xbv[U];
-      int oa[U], ob[U];
       const int stride = n_warps * U;
       int m = warp * U;
-      if (m < n_rows) load_batch(m, xa, oa);
+      if (m < n_rows) load_batch(m, xa);
       while (m < n_rows) {
-        if (m + stride < n_rows) load_batch(m + stride, xbv, ob);
-        process_batch(m, xa, oa);
+        if (m + stride < n_rows) load_batch(m + stride, xbv);
+        process_batch(m, xa);
         m += stride;
         if (m >= n_rows) break;
-        if (m + stride < n_rows) load_batch(m + stride, xa, oa);
-        process_batch(m, xbv, ob);
+        if (m + stride < n_rows) load_batch(m + stride, xa);
+        process_batch(m, xbv);
         m += stride;
       }
     }
@@ -2421,7 +2467,8 @@ bool launch_train_fast(const float* ref, const float* hist, int64_t n_pts, int64
   dim3 grid((unsigned)((n_pts + 31) / 32), (unsigned)grp->n_groups);
   // K1b (bucket select) is the default; XSDBA_B200_TRAIN_ALGO=sort keeps K1f's sorting network for A/B runs
   const char* algo = getenv("XSDBA_B200_TRAIN_ALGO");
-  if (!(algo && strcmp(algo, "sort") == 0)) {
+  // (its shared-memory image fits the 227 KB of an SM up to nq ~ 110; finer grids keep the sorter)
+  if (!(algo && strcmp(algo, "sort") == 0) && BktSmem::total(nq) <= 227 * 1024) {
     const size_t smem_b = BktSmem::total(nq);
 #define XS_TRAIN_BKT(J, N)                                                                                            \
   do {                                                                                                               \
@@ -2528,19 +2575,18 @@ int launch_train(const T* ref, const T* hist, int64_t n_pts, int64_t sp, int64_t
 template <int TOP>
 bool launch_adjust_tile_t(const float* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp,
                           const float* af, const float* hq, int nq, int extrap, int kind, float* scen, cudaStream_t s) {
-  typedef PackedSlot<2 * TOP> Slot;
-  const size_t smem_t = 2 * sizeof(Slot) + 2 * kTileMaxRows * sizeof(int) + 4 * sizeof(uint64_t) +
-                        kFixStage * sizeof(FixEntry) + 2 * sizeof(unsigned) + 128;
-  const size_t smem_p = sizeof(Slot) + stage_bytes<float, 32>(nq);
+  const size_t smem_t = 2 * tile_slot_floats(TOP, nq) * sizeof(float) + 2 * kTileMaxRows * sizeof(int) +
+                        4 * sizeof(uint64_t) + kFixStage * sizeof(FixEntry) + 2 * sizeof(unsigned) + 128;
+  const size_t smem_p = stage_bytes<float, 32>(nq);
   if (smem_t > 220 * 1024 || smem_p > 220 * 1024 || st < 0 || st > INT32_MAX / 4) return false;
   const int64_t tiles = (n_pts + 31) / 32;
-  Slot* packed = nullptr;
+  float* packed = nullptr;
   keep_pool_memory();
-  if (cudaMallocAsync(&packed, (size_t)tiles * grp->n_groups * sizeof(Slot), s) != cudaSuccess) {
+  if (cudaMallocAsync(&packed, (size_t)tiles * grp->n_groups * packed_slot_floats(nq) * sizeof(float), s) != cudaSuccess) {
     cudaGetLastError();
     return false;  // not enough memory for the packed image: the caller falls back to the staging kernel
   }
-  if (set_smem(pack_tables_kernel<TOP>, smem_p) || set_smem(adjust_tile_kernel<TOP>, smem_t)) {
+  if (set_smem(pack_tables_kernel, smem_p) || set_smem(adjust_tile_kernel<TOP>, smem_t)) {
     cudaFreeAsync(packed, s);
     return false;
   }
@@ -2562,14 +2608,14 @@ bool launch_adjust_tile_t(const float* sim, int64_t n_pts, int64_t sp, int64_t s
     cudaFreeAsync(packed, s); cudaFreeAsync(fix, s); cudaFreeAsync(fix_count, s);
     return false;
   }
-  pack_tables_kernel<TOP><<<dim3((unsigned)tiles, (unsigned)grp->n_groups), kThreads, smem_p, s>>>(af, hq, n_pts,
-                                                                                                   grp->n_groups, nq, packed);
+  pack_tables_kernel<<<dim3((unsigned)tiles, (unsigned)grp->n_groups), kThreads, smem_p, s>>>(
+      af, hq, n_pts, grp->n_groups, nq, extrap, packed);
   adjust_tile_kernel<TOP><<<(unsigned)tiles, kThreads, smem_t, s>>>(sim, n_pts, sp, (int)st, grp->members.off,
-                                                                    grp->members.rows, grp->n_groups, af, hq, nq, packed,
-                                                                    extrap, kind, scen, fix, fix_count, fix_cap);
-  static const bool fix_scan = getenv("XSDBA_B200_FIX_SCAN") != nullptr;  // (debug: the table-scanning second pass)
-  if (fix_scan) adjust_fix_kernel<<<sm_count() * 4, 256, 0, s>>>(fix, fix_count, fix_cap, af, hq, grp->n_groups, nq, extrap, kind, scen);
-  else adjust_fix_packed_kernel<TOP><<<sm_count() * 6, 256, 0, s>>>(fix, fix_count, fix_cap, packed, grp->n_groups, extrap, kind, scen);
+                                                                    grp->members.rows, grp->n_groups, nq, packed, kind,
+                                                                    scen, fix, fix_count, fix_cap);
+  static const bool fix_scan = getenv("XSDBA_B200_FIX_SCAN") != nullptr;  // (debug: scan every row in the second pass)
+  adjust_fix_kernel<<<sm_count() * 6, 256, 0, s>>>(fix, fix_count, fix_cap, af, hq, grp->n_groups, nq, extrap, kind,
+                                                   fix_scan ? nullptr : packed, scen);
   {
     const size_t smem_g = ((tables_bytes<float, 32>(nq) + 15) & ~(size_t)15) + stage_bytes<float, 32>(nq);
     auto kern = adjust_kernel<float, 32>;
@@ -2602,9 +2648,13 @@ bool launch_adjust_fast(const float* sim, int64_t n_pts, int64_t sp, int64_t st,
   if (grp->members.max_len > kAdjMaxRows) return false;
   int top = 1;
   while (top * 2 <= nq) top *= 2;
-  if (grp->members.max_len <= kTileMaxRows - 8 && !getenv("XSDBA_B200_NO_TILE") &&
-      launch_adjust_tile(sim, n_pts, sp, st, grp, af, hq, nq, top, extrap, kind, scen, s))
-    return true;
+  {
+    int top_t = 8;  // K2t searches nq + 2 intervals: 2 * top_t - 1 >= nq + 1
+    while (2 * top_t < nq + 2) top_t *= 2;
+    if (grp->members.max_len <= kTileMaxRows - 8 && !getenv("XSDBA_B200_NO_TILE") &&
+        launch_adjust_tile(sim, n_pts, sp, st, grp, af, hq, nq, top_t, extrap, kind, scen, s))
+      return true;
+  }
   smem += (size_t)grp->members.max_len * sizeof(int);
 #define XS_LAUNCH(TOP)                                                                                          \
   case TOP:                                                                                                     \

@@ -299,7 +299,7 @@ def npdf_transform(ref, hist, sim, *, time, sim_time, rot_matrices, base_kws=Non
     if "kind" in base_kws and base_kws["kind"] != "+":
         import warnings
         warnings.warn('The adjustment kind cannot be controlled when using NpdfTransform, it defaults to "+".', stacklevel=2)
-    base_kws["kind"] = "+"   # adjustment.py:1331-1337
+    base_kws.pop("kind", None)   # always "+" (adjustment.py:1331-1337)
     group = parse_group(base_kws.pop("group", "time"), base_kws.pop("window", 1))
     nquantiles = base_kws.pop("nquantiles", 20)
     adj_kws.setdefault("interp", "nearest")
