@@ -2470,6 +2470,7 @@ bool launch_train_fast(const float* ref, const float* hist, int64_t n_pts, int64
   // (its shared-memory image fits the 227 KB of an SM up to nq ~ 110; finer grids keep the sorter)
   if (!(algo && strcmp(algo, "sort") == 0) && BktSmem::total(nq) <= 227 * 1024) {
     const size_t smem_b = BktSmem::total(nq);
+    static const int vec_enable = getenv("XSDBA_B200_NO_VEC_LOAD") ? 0 : 1;  // (A/B switch of the 16-byte load path)
 #define XS_TRAIN_BKT(J, N)                                                                                            \
   do {                                                                                                               \
     *rc = set_smem(train_bucket_kernel<J, N>, smem_b);                                                               \
@@ -2477,7 +2478,7 @@ bool launch_train_fast(const float* ref, const float* hist, int64_t n_pts, int64
     train_bucket_kernel<J, N><<<grid, kFastThreads, smem_b, s>>>(ref, hist, n_pts, st, grp->segments.off,            \
                                                                  grp->segments.rows, grp->n_groups, q, nq, kind,    \
                                                                  normalize, mode, af, hq, scaling, jp, use_jitter,  \
-                                                                 q64);                                              \
+                                                                 q64, vec_enable);                                  \
   } while (0)
     if (use_jitter && normalize) XS_TRAIN_BKT(true, true);
     else if (use_jitter) XS_TRAIN_BKT(true, false);
