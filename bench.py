@@ -460,6 +460,7 @@ def run_b200(args):
                 "what": "every rank processes its own full 721-row grid (one step)"}
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------
+    NCU_TRAFFIC_RATIO = (6.145772e9 + 0.600114e9) / (69120 * (2 * 10950 * 4 + 2 * 12 * 50 * 4))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -479,9 +480,11 @@ def run_b200(args):
         "bound": "hbm", "kernel": train_kernel if dom == "train" else "pack_tables_kernel + adjust_tile_kernel",
         "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
-        # not measured in this run: see the ncu --set full capture of the same kernel under profiles/
-        # (dram__bytes_read.sum + dram__bytes_write.sum per launch)
-        "traffic": None, "traffic_source": "profiles/r02_ncu_train_bucket.txt",
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full` capture of this kernel on a 69 120-point
+        # slab (profiles/r02_ncu_train_bucket.txt: 6.146 + 0.600 GB against 6.387 GB algorithmic), scaled to the mean
+        # launch of this run; bench.py itself never runs under a profiler
+        "traffic": (NCU_TRAFFIC_RATIO * dom_bytes * args.steps / n_launch) if dom == "train" and "bucket" in train_kernel else None,
+        "traffic_source": "profiles/r02_ncu_train_bucket.txt (dram bytes per launch = 1.056 x algorithmic)",
         "launches": n_launch, "avg_launch_ms": dom_ms / n_launch,
         "algorithmic_bytes_per_launch": dom_bytes * args.steps / n_launch,
         "step": {"train_ms": tr_ms / args.steps, "adjust_ms": ad_ms / args.steps,

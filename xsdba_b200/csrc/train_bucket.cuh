@@ -74,6 +74,13 @@ __device__ __forceinline__ float bucket_scale(float cmin, float cmax, bool& dege
   return ok ? sc : 0.0f;
 }
 
+// base + 128 * row as one IMAD (the C expression becomes shift + mask + add)
+__device__ __forceinline__ uint32_t row128(uint32_t base, unsigned row) {
+  uint32_t a;
+  asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(a) : "r"(row), "r"(base));
+  return a;
+}
+
 __device__ __forceinline__ void ce8(float& a, float& b) { const float lo = fminf(a, b); b = fmaxf(a, b); a = lo; }
 __device__ __forceinline__ float pick8(const float (&x)[8], int r) {  // x[r], 0 <= r < 8: a 3-level select tree
   const bool b0 = r & 1, b1 = r & 2, b2 = r & 4;
@@ -440,10 +447,13 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
     const float scale = bucket_scale(cmin, cmax, degenerate);
     if (warp == 0) scalev[lane] = scale;  // (read back by the scatter and by the work-list pass, both behind barriers)
     // ---- histogram: every slot has a key (valid value or +inf), no predicates --------------------------
+    // (32-bit shared addresses: counter word = this lane's base + 128 bytes x (bucket mod 512) -- LOP3 + LEA)
+    const uint32_t hist_lane = (uint32_t)__cvta_generic_to_shared(hist + lane);
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const unsigned u = bucket_key(v[i], cmin, scale);
-      atomicAdd(hist + (u & (kBktW - 1)) * 32 + lane, (u & kBktW) ? 65536u : 1u);
+      asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(row128(hist_lane, u & (kBktW - 1))),
+                   "r"((u & kBktW) ? 65536u : 1u) : "memory");
     }
     __syncthreads();
     int n = 1024 - (int)(hist[(kBktW - 1) * 32 + lane] >> 16);  // valid samples: all keys but those of bucket 1023
@@ -511,15 +521,19 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
     //      the compiler keeps the 64 addresses and increments of the histogram pass alive across the prefix, i.e.
     //      spills them to local memory.) --------
     {
+      const uint32_t buf_lane = (uint32_t)__cvta_generic_to_shared(buf + lane);
       const float cmin_b = *reinterpret_cast<volatile float*>(cminv + lane);
       const float scale_b = *reinterpret_cast<volatile float*>(scalev + lane);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const unsigned u = bucket_key(v[i], cmin_b, scale_b);
         const bool hi = (u & kBktW) != 0;
-        const unsigned old = atomicAdd(hist + (u & (kBktW - 1)) * 32 + lane, hi ? 65536u : 1u);
+        unsigned old;
+        asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(row128(hist_lane, u & (kBktW - 1))),
+                     "r"(hi ? 65536u : 1u) : "memory");
         const unsigned pos = hi ? (old >> 16) : (old & 0xffffu);
-        buf[pos * 32 + lane] = fminf(v[i], finf);  // (NaN -> +inf: the selection windows may reach into bucket 1023)
+        // (NaN -> +inf: the selection windows may reach into bucket 1023)
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(row128(buf_lane, pos)), "f"(fminf(v[i], finf)) : "memory");
       }
     }
     __syncthreads();
