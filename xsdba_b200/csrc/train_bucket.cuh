@@ -33,8 +33,8 @@ constexpr int kBktAbort = 24;     // a bucket with more keys than this (seen in 
 constexpr int kBktPitch = 33;     // row pitch of the [warp][column] partial tables (transposed reads are conflict free)
 
 struct BktSmem {
-  static constexpr size_t buf = 0;                                   // float    [1024 + 8][32] scattered / sorted column, 8 rows of +inf
-  static constexpr size_t hist = buf + (1024 + 8) * 32 * 4;          // unsigned [512][32] packed counters (aliases: psum)
+  static constexpr size_t buf = 0;                                   // float    [1024 + 16][32] scattered / sorted column, 16 rows of +inf
+  static constexpr size_t hist = buf + (1024 + 16) * 32 * 4;          // unsigned [512][32] packed counters (aliases: psum)
   static constexpr size_t part = hist + (size_t)kBktW * 32 * 4;      // [3][32][33]: pmin, pmax (float), pcnt (int); aliases: tot, work list
   static constexpr size_t col = part + 3 * 32 * kBktPitch * 4;       // [8][32]: cmin, cmax (float), cnt (int), mu[2], scale (float), work-list length
   static constexpr size_t rows = col + 8 * 32 * 4;                   // int [1024] member rows of the group (-1 past S)
@@ -90,48 +90,100 @@ __device__ __forceinline__ float pick8(const float (&x)[8], int r) {  // x[r], 0
 }
 
 // Order statistics i and i + 1 of one bucket-sorted, non-degenerate column (0 <= i, i + 1 < n).  Returns false when a
-// bucket holds more than 8 samples: the node goes to the warp-cooperative path (bucket_select_pair_warp).
+// bucket holds more than 8 samples (the caller retries with bucket_select_pair16).  Straight-line code (selects, no
+// branches), so that the two nodes a thread may own are interleaved by the instruction scheduler.
 __device__ __forceinline__ bool bucket_select_pair(const unsigned* __restrict__ endp, const float* __restrict__ col,
                                                    float cmin, float scale, int i, float& left, float& right) {
   const float xi = col[i * 32], xj = col[(i + 1) * 32];
   const unsigned b0 = bucket_key(xi, cmin, scale) & (kBktN - 1), b1 = bucket_key(xj, cmin, scale) & (kBktN - 1);
-  bool ok = true;
-  left = right = xi;  // buckets 0 (== column minimum) and 1023 (== +inf) hold one value each
+  // buckets 0 (== column minimum) and 1023 (== +inf) hold one value each: nothing to select (the loads below then
+  // look at bucket 1, in range and unused)
+  const bool single = b0 == 0 || b0 == kBktN - 1;
+  const unsigned bq = single ? 1u : b0;
+  const int s0 = bucket_end(endp, bq - 1);
+  const int m = bucket_end(endp, bq) - s0;
+  const int r = single ? 0 : i - s0;
+  // the 8 slots from s0 on: the m samples of the bucket, then samples of later buckets (all larger: the bucket map
+  // is monotone) or the +inf rows behind the column -- the first m of the sorted window are the sorted bucket
+  float x[8];
+  const float* p = col + s0 * 32;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = p[j * 32];
+  ce8(x[0], x[1]); ce8(x[2], x[3]); ce8(x[4], x[5]); ce8(x[6], x[7]);
+  ce8(x[0], x[2]); ce8(x[1], x[3]); ce8(x[4], x[6]); ce8(x[5], x[7]);
+  ce8(x[1], x[2]); ce8(x[5], x[6]); ce8(x[0], x[4]); ce8(x[3], x[7]);
+  ce8(x[1], x[5]); ce8(x[2], x[6]);
+  ce8(x[1], x[4]); ce8(x[3], x[6]);
+  ce8(x[2], x[4]); ce8(x[3], x[5]);
+  ce8(x[3], x[4]);
+  const float l8 = pick8(x, r & 7), r8 = pick8(x, (r + 1) & 7);
+  left = single ? xi : l8;
+  right = single ? xi : r8;
+  // position i + 1 in another bucket: that bucket's smallest sample (slots past the bucket hold larger samples: the
+  // minimum of the 8-slot window is the minimum of the bucket).  Bucket 1023 holds +inf only.
+  const bool next = b1 != b0, next_inf = b1 == kBktN - 1;
+  const int m1 = bucket_end(endp, b1) - (i + 1);
+  const float* pn = col + (i + 1) * 32;
+  float y[8];
+#pragma unroll
+  for (int j = 1; j < 8; ++j) y[j] = pn[j * 32];
+  float mn = min3f(xj, y[1], y[2]);
+  mn = min3f(mn, y[3], y[4]); mn = min3f(mn, y[5], y[6]); mn = fminf(mn, y[7]);
+  right = next ? (next_inf ? xj : mn) : right;
+  return (single || m <= 8) && (!next || next_inf || m1 <= 8);
+}
+
+__device__ __forceinline__ float pick16(const float (&x)[16], int r) {  // x[r], 0 <= r < 16
+  const bool b0 = r & 1, b1 = r & 2, b2 = r & 4, b3 = r & 8;
+  float y[8], z[4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) y[j] = b0 ? x[2 * j + 1] : x[2 * j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) z[j] = b1 ? y[2 * j + 1] : y[2 * j];
+  const float w0 = b2 ? z[1] : z[0], w1 = b2 ? z[3] : z[2];
+  return b3 ? w1 : w0;
+}
+
+// The same for buckets of up to 16 samples (Batcher's 63-exchange network on a 16-slot window) and a next bucket of
+// any size: the out-of-line second try of the few threads (~1e-3) that meet such a bucket.  Returns false for
+// m > 16: that node goes to the warp-cooperative path.
+__device__ __noinline__ bool bucket_select_pair16(const unsigned* __restrict__ endp, const float* __restrict__ col,
+                                                  float cmin, float scale, int i, float& left, float& right) {
+  const float xi = col[i * 32], xj = col[(i + 1) * 32];
+  const unsigned b0 = bucket_key(xi, cmin, scale) & (kBktN - 1), b1 = bucket_key(xj, cmin, scale) & (kBktN - 1);
+  left = right = xi;
   if (b0 != 0 && b0 != kBktN - 1) {
-    const int e0 = bucket_end(endp, b0);
     const int s0 = bucket_end(endp, b0 - 1);
-    const int m = e0 - s0, r = i - s0;
-    ok = m <= 8;
-    // the 8 slots from s0 on: the m samples of the bucket, then samples of later buckets (all larger: the bucket map
-    // is monotone) or the +inf rows behind the column -- the first m of the sorted window are the sorted bucket
-    float x[8];
+    const int m = bucket_end(endp, b0) - s0, r = i - s0;
+    if (m > 16) return false;
+    float x[16];
     const float* p = col + s0 * 32;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = p[j * 32];
-    ce8(x[0], x[1]); ce8(x[2], x[3]); ce8(x[4], x[5]); ce8(x[6], x[7]);
-    ce8(x[0], x[2]); ce8(x[1], x[3]); ce8(x[4], x[6]); ce8(x[5], x[7]);
-    ce8(x[1], x[2]); ce8(x[5], x[6]); ce8(x[0], x[4]); ce8(x[3], x[7]);
-    ce8(x[1], x[5]); ce8(x[2], x[6]);
-    ce8(x[1], x[4]); ce8(x[3], x[6]);
-    ce8(x[2], x[4]); ce8(x[3], x[5]);
-    ce8(x[3], x[4]);
-    left = pick8(x, r);
-    right = pick8(x, (r + 1) & 7);
+    for (int j = 0; j < 16; ++j) x[j] = p[j * 32];
+    ce8(x[0], x[1]); ce8(x[2], x[3]); ce8(x[0], x[2]); ce8(x[1], x[3]); ce8(x[1], x[2]); ce8(x[4], x[5]);
+    ce8(x[6], x[7]); ce8(x[4], x[6]); ce8(x[5], x[7]); ce8(x[5], x[6]); ce8(x[0], x[4]); ce8(x[2], x[6]);
+    ce8(x[2], x[4]); ce8(x[1], x[5]); ce8(x[3], x[7]); ce8(x[3], x[5]); ce8(x[1], x[2]); ce8(x[3], x[4]);
+    ce8(x[5], x[6]); ce8(x[8], x[9]); ce8(x[10], x[11]); ce8(x[8], x[10]); ce8(x[9], x[11]); ce8(x[9], x[10]);
+    ce8(x[12], x[13]); ce8(x[14], x[15]); ce8(x[12], x[14]); ce8(x[13], x[15]); ce8(x[13], x[14]); ce8(x[8], x[12]);
+    ce8(x[10], x[14]); ce8(x[10], x[12]); ce8(x[9], x[13]); ce8(x[11], x[15]); ce8(x[11], x[13]); ce8(x[9], x[10]);
+    ce8(x[11], x[12]); ce8(x[13], x[14]); ce8(x[0], x[8]); ce8(x[4], x[12]); ce8(x[4], x[8]); ce8(x[2], x[10]);
+    ce8(x[6], x[14]); ce8(x[6], x[10]); ce8(x[2], x[4]); ce8(x[6], x[8]); ce8(x[10], x[12]); ce8(x[1], x[9]);
+    ce8(x[5], x[13]); ce8(x[5], x[9]); ce8(x[3], x[11]); ce8(x[7], x[15]); ce8(x[7], x[11]); ce8(x[3], x[5]);
+    ce8(x[7], x[9]); ce8(x[11], x[13]); ce8(x[1], x[2]); ce8(x[3], x[4]); ce8(x[5], x[6]); ce8(x[7], x[8]);
+    ce8(x[9], x[10]); ce8(x[11], x[12]); ce8(x[13], x[14]);
+    left = pick16(x, r);
+    right = pick16(x, (r + 1) & 15);
   }
-  if (b1 != b0) {  // position i + 1 opens the next non-empty bucket: its smallest sample
+  if (b1 != b0) {
     float mn = xj;
     if (b1 != kBktN - 1) {
       const int m1 = bucket_end(endp, b1) - (i + 1);
-      ok = ok && m1 <= 8;
-      const float* p = col + (i + 1) * 32;  // (slots past the bucket hold larger samples: the minimum is unchanged)
-      float y[8];
-#pragma unroll
-      for (int j = 1; j < 8; ++j) y[j] = p[j * 32];
-      mn = min3f(mn, y[1], y[2]); mn = min3f(mn, y[3], y[4]); mn = min3f(mn, y[5], y[6]); mn = fminf(mn, y[7]);
+      const float* pn = col + (i + 1) * 32;
+      for (int a = 1; a < m1; ++a) mn = fminf(mn, pn[a * 32]);
     }
     right = mn;
   }
-  return ok;
+  return true;
 }
 
 // The same pair by a whole warp (all 32 lanes call it with the same column): buckets of up to 32 samples, one sample
@@ -187,8 +239,24 @@ __device__ __forceinline__ void bucket_node_position(int n, double qk, int& i, f
   else { i = (int)vi; gamma = (float)(vi - (double)i); }
 }
 
-// One quantile node of one column.  MODE 0: from the bucket-sorted column, one thread (sets heavy and returns
-// garbage when a bucket is too large for it); MODE 1: the same by a whole warp; MODE 2: from the two sorted runs
+// One quantile node of one column from the bucket-sorted column, buckets of up to 8 samples: straight-line code.
+// heavy: a larger bucket was met (the result is then garbage and the caller retries with bucket_quantile_node<0>).
+__device__ __forceinline__ float bucket_quantile_node_fast(const unsigned* __restrict__ endp, const float* __restrict__ colp,
+                                                           int i, float gamma, int n, int S, float cmin, float cmax,
+                                                           float scale, bool& heavy) {
+  const bool edge_hi = i == -1, edge_lo = i == -2;  // (a non-edge node implies n >= 2 and i + 1 <= n - 1)
+  float l, r;
+  const bool ok = bucket_select_pair(endp, colp, cmin, scale, (edge_hi || edge_lo) ? 0 : i, l, r);
+  const float hi_val = (n < S) ? Num<float>::nan() : cmax;  // nbutils.py:47-51: position -1 of the full-length sorted row
+  const float left = edge_hi ? hi_val : edge_lo ? cmin : l;
+  const float right = edge_hi ? hi_val : edge_lo ? cmin : r;
+  heavy = !(ok || edge_hi || edge_lo) && n > 0;
+  const float res = bucket_interpolate(left, right, gamma, cmax);
+  return n > 0 ? res : Num<float>::nan();
+}
+
+// One quantile node of one column.  MODE 0: second try of a thread after bucket_quantile_node_fast (buckets of up to 16
+// samples; sets heavy beyond that); MODE 1: the same by a whole warp (up to 32); MODE 2: from the two sorted runs
 // the sorter leaves.
 template <int MODE>
 __device__ __forceinline__ float bucket_quantile_node(const unsigned* __restrict__ endp, const float* __restrict__ colp,
@@ -202,7 +270,7 @@ __device__ __forceinline__ float bucket_quantile_node(const unsigned* __restrict
   } else {
     left = right = cmin;
     if (MODE == 0) {
-      if (!bucket_select_pair(endp, colp, cmin, scale, i, left, right)) heavy = true;
+      heavy = !bucket_select_pair16(endp, colp, cmin, scale, i, left, right);
     } else if (MODE == 1) {
       bucket_select_pair_warp(endp, colp, cmin, scale, i, left, right);
     } else {
@@ -303,7 +371,7 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
   }
   rows_tab[tid] = tid < S ? seg_rows[seg_off[g] + tid] : -1;
   if (tid < 32) reinterpret_cast<int*>(cminv + 6 * 32)[tid] = (int)st * 4;
-  if (tid < 8 * 32) buf[1024 * 32 + tid] = finf;  // the rows behind the column (bucket_select_pair reads 8-slot windows)
+  if (tid < 16 * 32) buf[1024 * 32 + tid] = finf;  // the rows behind the column (the selection reads 8 / 16-slot windows)
   __syncthreads();
   const bool col_ok = n0 + lane < n_pts;
   // whole tile inside the grid, rows 16-byte aligned: the vector load path
@@ -540,9 +608,10 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
     // ---- quantiles: node k = item / 32 is warp-uniform, lane = column.  Results go straight to global memory
     //      (4-byte stores 2400 bytes apart; the 8 nodes of a 32-byte sector are written by 8 warps within the same
     //      round, the L2 write-back merges them) -- no staging buffer, no result registers across the barrier ----
-    auto emit = [&](int k, int c, float r) {
-      const long long o = (n0 + c) * out_stride + (long long)g * nq + k;
-      const bool okc = n0 + c < n_pts;
+    // (o = offset of node 0 of the column in the trained tables: hoisted out of the node loop for the thread's own
+    //  column, recomputed only for the few work-list nodes)
+    auto emit = [&](long long o_col0, bool okc, int k, int c, float r) {
+      const long long o = o_col0 + k;
       if (mode == 1) {
         if (okc) af[o] = r;
       } else if (pass == 0) {
@@ -553,19 +622,36 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
         af[o] = kind == XSDBA_KIND_ADD ? __fsub_rn(rq, r) : __fdiv_rn(rq, r);
       }
     };
-#pragma unroll 1
-    for (int item = tid; item < n_items; item += kFastThreads) {
-      const int k = item >> 5;
-      float r = fnan;
+    const long long o_own = (n0 + lane) * out_stride + (long long)g * nq;
+    // a thread owns nodes tid / 32 and tid / 32 + 32 (nq = 50: two nodes for 18 warps, one for 14): both go through the
+    // same straight-line code in one basic block, so the scheduler overlaps their shared-memory latencies
+    auto node_retry = [&](int item, int k, int i, float gamma) {  // a bucket of 9..24 samples (rare, divergent)
       bool heavy = false;
-      if (n > 0) {
-        int i = pos_i[k];
-        float gamma = pos_g[k];
-        if (n != S) bucket_node_position(n, qs[k], i, gamma);  // a column with NaNs: its own positions
-        r = bucket_quantile_node<0>(hist + lane, buf + lane, i, gamma, n, S, cmin, cmax, scale, heavy);
+      const float r = bucket_quantile_node<0>(hist + lane, buf + lane, i, gamma, n, S, cmin, cmax, scale, heavy);
+      if (heavy) work[atomicAdd(n_work, 1)] = (unsigned short)item;  // more than 16: a warp's job
+      else emit(o_own, col_ok, k, lane, r);
+    };
+#pragma unroll 1
+    for (int item0 = tid; item0 < n_items; item0 += 2 * kFastThreads) {
+      const int item1 = item0 + kFastThreads;
+      const int k0 = item0 >> 5, k1 = item1 >> 5;
+      int i0 = pos_i[k0];
+      float g0 = pos_g[k0];
+      if (n != S) bucket_node_position(n, qs[k0], i0, g0);  // a column with NaNs: its own positions
+      if (item1 < n_items) {  // (warp-uniform)
+        int i1 = pos_i[k1];
+        float g1 = pos_g[k1];
+        if (n != S) bucket_node_position(n, qs[k1], i1, g1);
+        bool h0, h1;
+        const float r0 = bucket_quantile_node_fast(hist + lane, buf + lane, i0, g0, n, S, cmin, cmax, scale, h0);
+        const float r1 = bucket_quantile_node_fast(hist + lane, buf + lane, i1, g1, n, S, cmin, cmax, scale, h1);
+        if (h0) node_retry(item0, k0, i0, g0); else emit(o_own, col_ok, k0, lane, r0);
+        if (h1) node_retry(item1, k1, i1, g1); else emit(o_own, col_ok, k1, lane, r1);
+      } else {
+        bool h0;
+        const float r0 = bucket_quantile_node_fast(hist + lane, buf + lane, i0, g0, n, S, cmin, cmax, scale, h0);
+        if (h0) node_retry(item0, k0, i0, g0); else emit(o_own, col_ok, k0, lane, r0);
       }
-      if (heavy) work[atomicAdd(n_work, 1)] = (unsigned short)item;  // a bucket of 9..24 samples: a warp's job
-      else emit(k, lane, r);
     }
     __syncthreads();
     {
@@ -580,7 +666,7 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
         int i; float gamma;
         bucket_node_position(n_c, qs[k], i, gamma);
         const float r = bucket_quantile_node<1>(hist + c, buf + c, i, gamma, n_c, S, cmin_c, cmax_c, scale_c, unused);
-        if (lane == 0) emit(k, c, r);
+        if (lane == 0) emit((n0 + c) * out_stride + (long long)g * nq, n0 + c < n_pts, k, c, r);
       }
     }
     __syncthreads();  // refq complete; hist / buf / the partial tables are free for the next pass
