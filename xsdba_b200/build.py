@@ -15,8 +15,13 @@ OUT = os.path.join(HERE, "libxsdba_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
-    "--split-compile=0",  # ptxas of the ~100 kernel instantiations in parallel on all host cores (2.5 min -> 1 min)
 ]
+# `--split-compile=0` (parallel back end, 2.5 min -> 1 min) is opt-in for development only: it partitions the module
+# before optimisation, and the code generated for one kernel then depends on unrelated edits elsewhere -- the train
+# kernel sits at the 64-register cap of a 1024-thread CTA, where such a perturbation flipped it between 0 and 100
+# spill instructions (4.0 vs 4.9 ms per slab on the same box, profiles/README.md).
+if os.environ.get("XSDBA_B200_SPLIT_COMPILE"):
+    NVCC_FLAGS.append("--split-compile=0")
 
 
 def nvcc_path() -> str:

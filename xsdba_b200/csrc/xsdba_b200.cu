@@ -1045,7 +1045,7 @@ constexpr int kTileMaxRows = 1024;  // member rows of one group kept in shared m
 __host__ __device__ constexpr size_t tile_slot_floats(int top, int nq) { return (size_t)(2 * top + 2 * (nq + 2)) * 32; }
 
 template <int TOP>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 3)
 adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp, int st,
                    const int32_t* __restrict__ mem_off, const int32_t* __restrict__ mem_rows, int n_groups, int nq,
                    const float* __restrict__ packed, int kind, float* __restrict__ scen,
@@ -1124,8 +1124,9 @@ adjust_tile_kernel(const float* __restrict__ sim, long long n_pts, long long sp,
     const char* __restrict__ srcb = reinterpret_cast<const char*>(src);  // byte addressing: one IMAD.WIDE per sample
     char* __restrict__ dstb = reinterpret_cast<char*>(dst);
     const int st4 = st * 4;
-    // (the row numbers are read from shared memory again at store time: keeping them next to the two value sets
-    //  costs 16 registers, i.e. the fourth resident CTA)
+    // (the row numbers are read from shared memory again at store time: measured faster than keeping them in 16
+    //  registers next to the two value sets -- 1.72 vs 1.83 ms per slab for the whole adjust, same box.  Three CTAs per
+    //  SM at 80 registers beat four at 64: 1.72 vs 1.87 ms)
     auto batch_rows = [&](int mb, int (&ov)[U]) {
       const int4 r0 = *reinterpret_cast<const int4*>(rows + mb), r1 = *reinterpret_cast<const int4*>(rows + mb + 4);
       ov[0] = r0.x; ov[1] = r0.y; ov[2] = r0.z; ov[3] = r0.w;
