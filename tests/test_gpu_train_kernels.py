@@ -226,3 +226,48 @@ def test_window_kernel_matches_oracle_sampled_groups():
             hist_q = o.nan_quantile(o.group_segment(hist.T.copy(), gidx, g, 31), q)
             assert bits_equal(hq[:, g], hist_q), g
             assert bits_equal(af[:, g], o.get_correction(hist_q, ref_q, "*").astype(np.float32)), g
+
+
+def _qdm_adjust_window(xs, sim, af, q, tx, group, kind, window_kernel):
+    old = os.environ.pop("XSDBA_B200_NO_WINDOW_KERNEL", None)
+    if not window_kernel:
+        os.environ["XSDBA_B200_NO_WINDOW_KERNEL"] = "1"
+    try:
+        out = xs.qdm_adjust(xs.Dataset({"sim": sim, "af": af, "quantiles": q}, time=tx), group=group, interp="nearest",
+                            extrapolation="constant", kind=kind, rank_window=True)
+        torch.cuda.synchronize()
+        return _np(out.sim_q), _np(out.scen)
+    finally:
+        os.environ.pop("XSDBA_B200_NO_WINDOW_KERNEL", None)
+        if old is not None:
+            os.environ["XSDBA_B200_NO_WINDOW_KERNEL"] = old
+
+
+@pytest.mark.parametrize("cal,years,window,nq,var,kind", [
+    ("noleap", 30, 31, 100, "pr", "*"),
+    ("noleap", 30, 31, 50, "tas", "+"),
+    ("standard", 12, 31, 50, "tas", "+"),      # day 366: a sparse group, windows shifted after Feb 29
+    ("360_day", 5, 7, 20, "pr", "*"),
+    ("noleap", 3, 5, 200, "tas", "+"),          # more nodes than the kernel's quantile axis holds: per-group fallback
+])
+def test_rank_window_kernel_equals_per_group_kernel(cal, years, window, nq, var, kind):
+    """K3w (rank_window=True from one ordering per chunk of day-of-year groups) against K3 (one sort per group): ranks and
+    adjusted values of every time step, bit for bit -- ties, signed zeros, +-inf, NaN samples, NaN factors at the ends
+    and in the middle of a factor row, an all-NaN factor row."""
+    xs = _xs()
+    rng = np.random.default_rng(79)
+    to = o.daily_time_axis(1981, years, cal); tx = xs.TimeAxis.daily(1981, years, cal)
+    P = 21
+    ref, hist = _stress_inputs(rng, to, P, var)
+    sim = hist.copy()
+    sim[:, 0] = ref[:, 0]
+    q = o.equally_spaced_nodes(nq).astype(np.float32)
+    grp = xs.Grouper("time.dayofyear", window)
+    af = _np(xs.eqm_train(xs.Dataset({"ref": ref, "hist": hist}, time=tx), group=grp, kind=kind, quantiles=q).af).copy()
+    af[3, :, 5:9] = np.nan            # NaN factors inside the rows of one point ...
+    af[4, :, :3] = np.nan; af[4, :, -2:] = np.nan   # ... at both ends of another ...
+    af[5, 10:20, :] = np.nan          # ... and whole rows (the neighbouring groups answer)
+    sq_a, sc_a = _qdm_adjust_window(xs, sim, af, q, tx, grp, kind, True)
+    sq_b, sc_b = _qdm_adjust_window(xs, sim, af, q, tx, grp, kind, False)
+    assert bits_equal(sq_a, sq_b)
+    assert bits_equal(sc_a, sc_b)

@@ -44,6 +44,7 @@ struct WinTables {
   int32_t* urow_off = nullptr;  // [n_chunks + 1] offsets into urows
   int32_t* urows = nullptr;     // union of the chunk's window rows (time indices, ascending)
   unsigned long long* gmask = nullptr;  // [union rows] bit j: group chunk_g + j has the row in its window
+  int32_t* mem_u = nullptr;     // [members] index of every exact group member inside the union rows of its chunk (K3w)
   int32_t max_union = 0, max_groups = 0;
 };
 
@@ -549,6 +550,7 @@ train_fast_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
 
 #include "train_bucket.cuh"
 #include "train_window.cuh"
+#include "rank_window.cuh"
 
 // =============================================================================================
 // Table staging shared by the adjust kernels: rows r-1, r, r+1 (cyclic) of the tile's tables into
@@ -2742,6 +2744,28 @@ int launch_rank_c(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsd
   return cuda_status(cudaGetLastError());
 }
 
+// rank_window = True on groupings with heavily overlapping windows: one ordering per chunk of groups (K3w)
+bool launch_rank_window(const float* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const float* af,
+                        const float* q, int nq, int extrap, int kind, int do_adjust, float* scen, double* sim_q,
+                        cudaStream_t s, int* rc) {
+  if (sp != 1 || st < 0 || grp->win.n_chunks <= 0 || !grp->win.mem_u || (do_adjust && nq > RankWinSmem::kWinMaxNq) ||
+      getenv("XSDBA_B200_NO_WINDOW_KERNEL") || getenv("XSDBA_B200_NO_FAST"))
+    return false;
+  *rc = set_smem(rank_window_kernel, RankWinSmem::total);
+  if (*rc) return true;
+  dim3 grid((unsigned)((n_pts + kWinCols - 1) / kWinCols), (unsigned)grp->win.n_chunks);
+  rank_window_kernel<<<grid, kWinThreads, RankWinSmem::total, s>>>(
+      sim, n_pts, st, grp->members.off, grp->members.rows, grp->win.mem_u, grp->win.chunk_g, grp->win.urow_off,
+      grp->win.urows, grp->win.gmask, grp->n_groups, af, q, nq, extrap, kind, do_adjust, scen, sim_q);
+  ++g_launches;
+  *rc = cuda_status(cudaGetLastError());
+  return true;
+}
+bool launch_rank_window(const double*, int64_t, int64_t, int64_t, const xsdba_grouping*, const double*, const double*, int,
+                        int, int, int, double*, double*, cudaStream_t, int*) {
+  return false;
+}
+
 template <typename T>
 int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* af,
                 const T* q, int nq, int interp, int extrap, int kind, int rank_window, int do_adjust, T* scen,
@@ -2760,6 +2784,12 @@ int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba
   }
   if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
   if (n_pts == 0) return XSDBA_OK;
+  {
+    int wrc = 0;
+    if (rank_window && rank_mode == 0 && grp->n_groups > 1 && (!do_adjust || interp == XSDBA_INTERP_NEAREST) &&
+        launch_rank_window(sim, n_pts, sp, st, grp, af, q, nq, extrap, kind, do_adjust, scen, sim_q, (cudaStream_t)stream, &wrc))
+      return wrc;
+  }
   const DevTable& seg = rank_window ? grp->segments : grp->members;
   const int n_pad = std::max(2, next_pow2(seg.max_len));
   int C = pick_cols<T>(n_pad);
@@ -3309,8 +3339,10 @@ int upload_table(const std::vector<int32_t>& off, const std::vector<int32_t>& ro
 // Greedy chunking of consecutive groups for K1w.  Leaves win.n_chunks == 0 (kernel not used) when a group repeats a
 // row, a single group exceeds the row budget, or the sharing is below 2x.
 int build_window_tables(const std::vector<int32_t>& soff, const std::vector<int32_t>& srows, int32_t n_time, int n_groups,
-                        WinTables& win) {
+                        const std::vector<int32_t>& moff, const std::vector<int32_t>& mrows, WinTables& win) {
   std::vector<int32_t> stamp(n_time, -1), local(n_time, 0);
+  std::vector<int32_t> mem_u(mrows.size(), -1);
+  bool members_inside = true;  // every exact member is a row of its own window (the centre slot)
   std::vector<int32_t> chunk_g{0}, urow_off{0}, urows;
   std::vector<unsigned long long> gmask;
   std::vector<int32_t> cur;  // rows of the open chunk
@@ -3323,6 +3355,11 @@ int build_window_tables(const std::vector<int32_t>& soff, const std::vector<int3
     for (int g = chunk_g.back(); g < next_g; ++g)
       for (int s_ = soff[g]; s_ < soff[g + 1]; ++s_)
         if (srows[s_] >= 0) gmask[base + local[srows[s_]]] |= 1ull << (g - chunk_g.back());
+    for (int g = chunk_g.back(); g < next_g; ++g)
+      for (int m = moff[g]; m < moff[g + 1]; ++m) {
+        if (stamp[mrows[m]] == chunk_id) mem_u[m] = local[mrows[m]];
+        else members_inside = false;
+      }
     urows.insert(urows.end(), cur.begin(), cur.end());
     urow_off.push_back((int32_t)urows.size());
     chunk_g.push_back(next_g);
@@ -3360,6 +3397,10 @@ int build_window_tables(const std::vector<int32_t>& soff, const std::vector<int3
   if (e == cudaSuccess) e = cudaMemcpy(win.urow_off, urow_off.data(), urow_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(win.urows, urows.data(), urows.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(win.gmask, gmask.data(), gmask.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && members_inside && !mem_u.empty()) {
+    e = cudaMalloc(&win.mem_u, mem_u.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(win.mem_u, mem_u.data(), mem_u.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) return (int)e;
   win.n_chunks = (int32_t)chunk_g.size() - 1;
   win.max_union = max_union;
@@ -3436,7 +3477,7 @@ int xsdba_grouping_create(xsdba_grouping_t** out, const int32_t* grp_idx_host, i
         }
         soff[n_groups] = (int32_t)srows.size();
         rc = upload_table(soff, srows, g->segments);
-        if (rc == XSDBA_OK) rc = build_window_tables(soff, srows, (int32_t)n_time, n_groups, g->win);
+        if (rc == XSDBA_OK) rc = build_window_tables(soff, srows, (int32_t)n_time, n_groups, off, rows, g->win);
       }
     }
   }
@@ -3452,7 +3493,7 @@ int xsdba_grouping_destroy(xsdba_grouping_t* g) {
   cudaFree(g->members.off);
   cudaFree(g->members.rows);
   cudaFree(g->gidx);
-  cudaFree(g->win.chunk_g); cudaFree(g->win.urow_off); cudaFree(g->win.urows); cudaFree(g->win.gmask);
+  cudaFree(g->win.chunk_g); cudaFree(g->win.urow_off); cudaFree(g->win.urows); cudaFree(g->win.gmask); cudaFree(g->win.mem_u);
   delete g;
   return XSDBA_OK;
 }
