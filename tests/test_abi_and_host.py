@@ -39,6 +39,21 @@ def test_library_is_sm100a_only():
     assert archs == {"100a"}, archs
 
 
+def test_headline_train_kernel_is_not_spilling():
+    """train_bucket_kernel<false,false> sits at the 64-register cap of a 1024-thread CTA: a code-generation accident
+    (nvcc --split-compile, an edit that lengthens a live range) costs 20 %.  The good build keeps
+    its stack frame at 80 bytes (the out-of-line sorter's call frame); spilling builds showed 144-330."""
+    import shutil
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-res-usage", os.path.join(ROOT, "xsdba_b200", "libxsdba_b200.so")],
+                         capture_output=True, text=True).stdout
+    m = re.search(r"train_bucket_kernelILb0ELb0[^\n]*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert m, "train_bucket_kernel<false,false> not found in the library"
+    assert int(m.group(1)) <= 64 and int(m.group(2)) <= 96, m.group(0)
+
+
 def test_version_and_status_strings(lib):
     assert lib.xsdba_version() >= 100
     assert b"invalid" in lib.xsdba_status_string(-1)
