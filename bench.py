@@ -178,6 +178,24 @@ def synth_pr(torch, gen, T, n, which, device):
     return x
 
 
+def ncu_traffic_ratio(path, kernel):
+    """dram bytes (read + write) of the captured launch of `kernel` in a profiles/ncu_summary.py text file, divided by
+    the algorithmic bytes of that launch (grid.x tiles of 32 points x grid.y month groups); None if not found."""
+    try:
+        txt = open(path).read()
+    except OSError:
+        return None
+    import re
+    m = re.search(r"Kernel Name\s+[^\n]*" + kernel + r"[^\n]*\nGrid Size\s+\((\d+), (\d+), 1\)[^\n]*\n(?:[^\n]*\n){1,3}?"
+                  r"dram__bytes_read\.sum\s+([\d.]+) (\w+)\ndram__bytes_write\.sum\s+([\d.]+) (\w+)", txt)
+    if not m:
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = float(m.group(3)) * unit[m.group(4)] + float(m.group(5)) * unit[m.group(6)]
+    pts, groups = int(m.group(1)) * 32, int(m.group(2))
+    return total / (pts * (2 * NYEARS * 365 * 4 + 2 * groups * NQ * 4))
+
+
 def time_device(torch, fn, steps, warmup=2):  # (two: the second call still grows torch's caching allocator)
     for _ in range(warmup):
         fn()
@@ -460,7 +478,7 @@ def run_b200(args):
                 "what": "every rank processes its own full 721-row grid (one step)"}
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------
-    NCU_TRAFFIC_RATIO = (6.145772e9 + 0.600114e9) / (69120 * (2 * 10950 * 4 + 2 * 12 * 50 * 4))
+    ncu_ratio = ncu_traffic_ratio(os.path.join(ROOT, "profiles", "r02_ncu_train_bucket.txt"), "train_bucket_kernel")
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -480,11 +498,12 @@ def run_b200(args):
         "bound": "hbm", "kernel": train_kernel if dom == "train" else "pack_tables_kernel + adjust_tile_kernel",
         "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full` capture of this kernel on a 69 120-point
-        # slab (profiles/r02_ncu_train_bucket.txt: 6.146 + 0.600 GB against 6.387 GB algorithmic), scaled to the mean
-        # launch of this run; bench.py itself never runs under a profiler
-        "traffic": (NCU_TRAFFIC_RATIO * dom_bytes * args.steps / n_launch) if dom == "train" and "bucket" in train_kernel else None,
-        "traffic_source": "profiles/r02_ncu_train_bucket.txt (dram bytes per launch = 1.056 x algorithmic)",
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full` capture of this kernel (the committed
+        # summary is parsed at run time, so the figure follows the capture and is null without it), scaled from the
+        # captured launch to the mean launch of this run; bench.py itself never runs under a profiler
+        "traffic": (ncu_ratio * dom_bytes * args.steps / n_launch) if ncu_ratio and dom == "train" and "bucket" in train_kernel else None,
+        "traffic_source": "profiles/r02_ncu_train_bucket.txt, parsed at run time: dram bytes per launch = "
+                          + (f"{ncu_ratio:.3f}" if ncu_ratio else "n/a") + " x algorithmic on the captured 69 120-point launch",
         "launches": n_launch, "avg_launch_ms": dom_ms / n_launch,
         "algorithmic_bytes_per_launch": dom_bytes * args.steps / n_launch,
         "step": {"train_ms": tr_ms / args.steps, "adjust_ms": ad_ms / args.steps,
