@@ -401,6 +401,16 @@ int xsdba_loess_trend_f64(const double* x_dev, int64_t n_pts, int64_t stride_pt,
                           const xsdba_grouping_t* grp, const double* scaling_dev, int32_t kind, double f,
                           int32_t niter, int32_t degree, const double* xn_dev, double* trend_dev,
                           void* cuda_stream);
+/* The same with the weight function selectable: weights 0 = tricube (loess.py:29-35), 1 = gaussian (loess.py:16-26,
+ * `LoessDetrend(weights="gaussian")`, loess.py:247). */
+int xsdba_loess_trend_w_f32(const float* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                            const xsdba_grouping_t* grp, const float* scaling_dev, int32_t kind, double f,
+                            int32_t niter, int32_t degree, int32_t weights, const double* xn_dev, double* trend_dev,
+                            void* cuda_stream);
+int xsdba_loess_trend_w_f64(const double* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
+                            const xsdba_grouping_t* grp, const double* scaling_dev, int32_t kind, double f,
+                            int32_t niter, int32_t degree, int32_t weights, const double* xn_dev, double* trend_dev,
+                            void* cuda_stream);
 
 /*
  * Adjust (DQM): replaces _adjustment.dqm_adjust.func (_adjustment.py:748-780) once the trend of the

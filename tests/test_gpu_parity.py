@@ -1030,3 +1030,36 @@ def test_train_row_stride_beyond_int32_bytes_takes_the_generic_kernel():
     assert bits_equal(outs[0][0], outs[1][0]) and bits_equal(outs[0][1], outs[1][1])
     del big
     torch.cuda.empty_cache()
+
+
+def test_loess_gaussian_weights_reference_golden():
+    """CUDA LOESS with `weights="gaussian"` against the reference's numba kernel (golden) on the per-point path, and
+    against the restatement on complete series (shared-table paths) and with robustness iterations."""
+    import os
+    xs = _xs()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loess_gaussian.npz"))
+    x, y = g["loess_x"], g["loess_y"]
+    n = x.size
+    t = xs.TimeAxis.daily(2001, 1, "noleap")[:n]
+    series = np.stack([y, y[::-1].copy()], axis=1)
+    for k in range(3):
+        d, f, niter, dx = g[f"case{k}_params"]
+        got = _np(xs.loess_trend(series, time=t, f=float(f), niter=int(niter), d=int(d), weights="gaussian"))
+        np.testing.assert_allclose(got[:, 0], g[f"case{k}_out"], rtol=1e-9, atol=1e-10, equal_nan=True)
+        want = o.loess_nb(x, series[:, 1], f=float(f), niter=int(niter), weights="gaussian", d=int(d), dx=float(dx))
+        np.testing.assert_allclose(got[:, 1], want, rtol=1e-9, atol=1e-10, equal_nan=True)
+    rng = np.random.default_rng(9)
+    t3 = xs.TimeAxis.daily(2001, 3, "noleap")
+    m = len(t3)
+    xx = np.arange(m, dtype=np.float64)
+    yy = (280 + 5 * np.sin(2 * np.pi * xx / 365)[:, None] + rng.standard_normal((m, 40))).astype(np.float32)
+    yy[100:130, 35] = np.nan
+    got = _np(xs.loess_trend(yy, time=t3, f=0.2, niter=1, d=0, weights="gaussian"))
+    # (the abscissa exactly as loess_smoothing and the library build it, loess.py:244-245: the gaussian kernel is
+    #  discontinuous at the window edge, so the last bit of |x_j - x_i| / h decides whether the edge sample counts)
+    xx = (xx - xx[0]) / (xx[-1] - xx[0])
+    for j in (0, 31, 32, 35, 39):
+        want = o.loess_nb(xx, yy[:, j].astype(np.float64), f=0.2, niter=1, weights="gaussian", d=0, dx=float(xx[1] - xx[0]))
+        np.testing.assert_allclose(got[:, j], want, rtol=1e-11, atol=1e-12, equal_nan=True)
+    tas = xs.LoessDetrend(group="time", kind="+", f=0.2, niter=1, d=0, weights="gaussian")
+    assert tas.weights == "gaussian"

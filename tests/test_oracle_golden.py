@@ -146,3 +146,15 @@ def test_vecquantiles_and_map_cdf_vs_reference(golden):
         assert bits_equal(got, golden[f"vecq_{tag}_out"])
     got = o.map_cdf_1d(golden["mapcdf_x"], golden["mapcdf_y"], golden["mapcdf_v"])
     assert bits_equal(got, golden["mapcdf_out"])
+
+
+def test_loess_gaussian_weights_reference_golden():
+    """`weights="gaussian"` (loess.py:16-26): the restatement against the reference's numba _loess_nb with
+    _gaussian_weighting (tests/golden/loess_gaussian.npz, oracle/gen_golden_loess_gaussian.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loess_gaussian.npz"))
+    x, y = g["loess_x"], g["loess_y"]
+    for k in range(3):
+        d, f, niter, dx = g[f"case{k}_params"]
+        got = o.loess_nb(x, y, f=float(f), niter=int(niter), weights="gaussian", d=int(d), dx=float(dx))
+        np.testing.assert_allclose(got, g[f"case{k}_out"], rtol=1e-12, atol=1e-13, equal_nan=True)

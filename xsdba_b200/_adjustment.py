@@ -416,7 +416,7 @@ def poly_trend(x, *, time, group, degree, kind="+", scaling=None, time_axis=0, p
 
 
 def loess_trend(x, *, time, f=0.2, niter=1, d=0, kind="+", scaling=None, scaling_group=None, loess_group="time",
-                time_axis=0):
+                time_axis=0, weights="tricube"):
     """``LoessDetrend(group="time", f, niter, d).fit(x (+|*) scaling).ds.trend`` (detrending.py:274-296 ->
     loess.loess_smoothing, loess.py:182-279): float64 tensor shaped like ``x``."""
     loess_group = parse_group(loess_group)
@@ -437,9 +437,12 @@ def loess_trend(x, *, time, f=0.2, niter=1, d=0, kind="+", scaling=None, scaling
         if sc.numel() != n_pts * h.n_groups:
             raise ValueError("scaling must be (*points, n_groups)")
     trend = torch.empty(xs.shape, dtype=torch.float64, device=xs.device)
-    fn = getattr(lib, f"xsdba_loess_trend_{_sfx(dt)}")
+    if weights not in ("tricube", "gaussian"):
+        raise NotImplementedError("LOESS weights: 'tricube' or 'gaussian' (loess.py:247)")
+    fn = getattr(lib, f"xsdba_loess_trend_w_{_sfx(dt)}")
     _lib.check(fn(xs.data_ptr(), n_pts, sp, st, h.ptr, sc.data_ptr() if sc is not None else None, _lib.KIND[kind],
-                  float(f), int(niter), int(d), xn.data_ptr(), trend.data_ptr(), _stream()), "loess_trend")
+                  float(f), int(niter), int(d), 1 if weights == "gaussian" else 0, xn.data_ptr(), trend.data_ptr(),
+                  _stream()), "loess_trend")
     return trend
 
 
@@ -480,7 +483,8 @@ def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_
             raise NotImplementedError("a PolyDetrend with a group different from the adjustment group is not built yet")
     elif isinstance(detrend, LoessDetrend):
         trend = loess_trend(sim, time=time, f=detrend.f, niter=detrend.niter, d=detrend.d, kind=kind, scaling=scaling,
-                            scaling_group=group, loess_group=detrend.group, time_axis=ta)
+                            scaling_group=group, loess_group=detrend.group, time_axis=ta,
+                            weights=getattr(detrend, "weights", "tricube"))
     else:
         raise TypeError("detrend must be an int, a PolyDetrend or a LoessDetrend")
     nq = af.shape[-1]

@@ -1396,11 +1396,18 @@ __device__ __forceinline__ double tricube_w(double u) {  // loess.py:31-35
   const double c = 1.0 - u * u * u;
   return u >= 1.0 ? 0.0 : c * c * c;
 }
+__device__ __forceinline__ double gaussian_w(double u) {  // loess.py:16-26: the span covers 95 % of the gaussian
+  return u >= 1.0 ? 0.0 : exp(-(u * u) / (2.0 * ((1.0 / 1.96) * (1.0 / 1.96))));
+}
 
 // LOESS window geometry of one compacted series of n samples (loess.py:104-119)
+// (the weight function travels in the sign of f inside the library: f < 0 = gaussian weights on the span |f|)
 struct LoessGeom {
   int r, hw, R, HW;
-  __device__ LoessGeom(int n, double f) {
+  bool gauss;
+  __device__ LoessGeom(int n, double f_signed) {
+    gauss = f_signed < 0.0;
+    const double f = fabs(f_signed);
     r = (int)(2.0 * floor(f * (double)n / 2.0) + 1.0);
     hw = (r - 1) / 2;
     R = r + 4 < n ? r + 4 : n;
@@ -1408,6 +1415,7 @@ struct LoessGeom {
   }
   // true when output i uses the weights computed at i = HW on the window [i-HW, i+HW] (loess.py:131-150)
   __device__ bool interior(int i, int n) const { return i > HW && i < n - HW - 1; }
+  __device__ double w(double u) const { return gauss ? gaussian_w(u) : tricube_w(u); }
 };
 
 // K6c: the "interior" weights of every point: w[k] = tricube(|x[k] - x[HW]| / ((hw+1) dx)), k in [0, 2HW],
@@ -1425,7 +1433,7 @@ loess_weights_kernel(const int32_t* __restrict__ tc, const int32_t* __restrict__
   const double xc = xn[tc[(long long)gm.HW * n_pts + pt]];
   for (int k = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); k < w_rows; k += gridDim.y * (blockDim.x >> 5))
     wtab[(long long)k * n_pts + pt] =
-        k <= 2 * gm.HW ? tricube_w(fabs(xn[tc[(long long)k * n_pts + pt]] - xc) / h) : 0.0;  // zero tail: K6 reads past K
+        k <= 2 * gm.HW ? gm.w(fabs(xn[tc[(long long)k * n_pts + pt]] - xc) / h) : 0.0;  // zero tail: K6 reads past K
 }
 
 // total interior weight of every point, summed in tap order like the reference's w.sum() (loess.py:38-39): all
@@ -1456,7 +1464,7 @@ __global__ void loess_shared_weights_kernel(const double* __restrict__ xn, int n
   const double h = (double)(gm.hw + 1) * dx;
   const double xc = xn[gm.HW];
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < w_rows; k += gridDim.x * blockDim.x)
-    wsh[k] = (k <= 2 * gm.HW && n >= 2 * gm.HW + 3) ? tricube_w(fabs(xn[k] - xc) / h) : 0.0;
+    wsh[k] = (k <= 2 * gm.HW && n >= 2 * gm.HW + 3) ? gm.w(fabs(xn[k] - xc) / h) : 0.0;
 }
 
 // one output by the literal rule (edges, short series)
@@ -1482,7 +1490,7 @@ __device__ double loess_one(const T* __restrict__ y, const int32_t* __restrict__
   double sw = 0, swy = 0, swx = 0, swxx = 0, swxy = 0;
   for (int j = lo; j < hi; ++j) {
     const int k = wlo + (j - lo);
-    double w = k < n ? tricube_w(fabs(xn[tcp[(long long)k * n_pts]] - xc) / h) : 0.0;
+    double w = k < n ? gm.w(fabs(xn[tcp[(long long)k * n_pts]] - xc) / h) : 0.0;
     if (delta) w = delta[(long long)j * n_pts] * w;            // robustness weights: w = di * wi (loess.py:150)
     const double yj = (double)y[(long long)j * n_pts];
     sw += w; swy += w * yj;
@@ -1525,7 +1533,8 @@ loess_edge_table_kernel(const double* __restrict__ xn, int n, double f, double* 
     if (i < gm.hw) h = (double)(gm.r - i) * dx;
     else if (i >= n - gm.hw) h = (double)(i - (n - gm.r) + 1) * dx;
     else h = (double)(gm.hw + 1) * dx;
-    etab[idx] = tricube_w(fabs(xn[lo + j] - xn[i]) * (1.0 / h));
+    // (the gaussian weight jumps from 0.146 to 0 at u = 1: u must be the reference's quotient there, loess.py:153)
+    etab[idx] = gm.gauss ? gm.w(fabs(xn[lo + j] - xn[i]) / h) : gm.w(fabs(xn[lo + j] - xn[i]) * (1.0 / h));
   }
 }
 __global__ void loess_edge_sum_kernel(int n, double f, const double* __restrict__ etab, double* __restrict__ esum) {
@@ -1635,7 +1644,7 @@ loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, co
         if (i < gm.hw) h = (double)(gm.r - i) * dx;
         else if (i >= n - gm.hw) h = (double)(i - (n - gm.r) + 1) * dx;
         else h = (double)(gm.hw + 1) * dx;
-        ih[r] = 1.0 / h;
+        ih[r] = gm.gauss ? h : 1.0 / h;  // (gaussian weights jump at u = 1: u must be the reference's quotient, loess.py:153)
         xi[r] = xn[tcp[(long long)i * n_pts]];
         sw[r] = 0; swy[r] = 0;
       }
@@ -1644,7 +1653,7 @@ loess_smooth_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, co
         const double yj = (double)y[(long long)j * n_pts];
 #pragma unroll
         for (int r = 0; r < RO; ++r) {
-          const double wgt = tricube_w(fabs(xj - xi[r]) * ih[r]);
+          const double wgt = gm.gauss ? gm.w(fabs(xj - xi[r]) / ih[r]) : gm.w(fabs(xj - xi[r]) * ih[r]);
           sw[r] += wgt; swy[r] = fma(wgt, yj, swy[r]);
         }
       }
@@ -3004,7 +3013,7 @@ template <typename T>
 int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* scaling,
                        int kind, double f, int niter, int degree, const double* xn, double* trend, void* stream) {
   if (wrong_device(grp)) return XSDBA_ERR_INVALID_ARGUMENT;  // the handle's tables live on another device
-  if ((n_pts > 0 && !x) || !grp || (n_pts > 0 && !xn) || (n_pts > 0 && !trend) || n_pts < 0 || !(f > 0.0) || degree < 0 || degree > 1) return XSDBA_ERR_INVALID_ARGUMENT;
+  if ((n_pts > 0 && !x) || !grp || (n_pts > 0 && !xn) || (n_pts > 0 && !trend) || n_pts < 0 || !(f != 0.0) || degree < 0 || degree > 1) return XSDBA_ERR_INVALID_ARGUMENT;
   if (niter < 1) return XSDBA_ERR_INVALID_ARGUMENT;
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
   if (n_pts == 0) return XSDBA_OK;
@@ -3023,7 +3032,8 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
   loess_compact_kernel<T><<<(unsigned)((n_pts + kThreads - 1) / kThreads), kThreads, 0, s>>>(
       x, n_pts, sp, st, n_time, grp->gidx, grp->n_groups, scaling, kind, yc, tc, nv, trend);
   // interior weight table: at most 2*HW+1 <= f*n_time + 6 rows per point
-  const int w_rows = (int)std::min<double>((double)n_time, f * (double)n_time + 8.0);
+  const double fa = std::fabs(f);  // (f < 0: gaussian weights, see LoessGeom)
+  const int w_rows = (int)std::min<double>((double)n_time, fa * (double)n_time + 8.0);
   double* wtab = nullptr;
   if (cudaMallocAsync(&wtab, sizeof(double) * n_pts * (w_rows + 1), s) != cudaSuccess) {
     cudaGetLastError();
@@ -3045,7 +3055,7 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
   double* etab = nullptr;
   double* esum = nullptr;
   if (degree == 0 && n_time >= 8) {
-    const int r_ = (int)(2.0 * std::floor(f * (double)n_time / 2.0) + 1.0);   // LoessGeom on the host
+    const int r_ = (int)(2.0 * std::floor(fa * (double)n_time / 2.0) + 1.0);   // LoessGeom on the host
     const int HW_ = (r_ - 1) / 2 + 2, R_ = std::min(r_ + 4, n_time), NI_ = 2 * HW_ + 1;
     if (n_time >= R_ && n_time > 2 * HW_ + 2 &&
         cudaMallocAsync(&etab, sizeof(double) * (size_t)R_ * NI_ + sizeof(double) * NI_, s) == cudaSuccess) {
@@ -3085,7 +3095,7 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
                                       kThreads, smem_t, s>>>(yc, nv, n_pts, sp, st, n_time, f, wsh, w_rows, trend);
       ++g_launches;
       {
-        const int r_ = (int)(2.0 * std::floor(f * (double)n_time / 2.0) + 1.0);
+        const int r_ = (int)(2.0 * std::floor(fa * (double)n_time / 2.0) + 1.0);
         const int HW_ = (r_ - 1) / 2 + 2;
         const int cps = (HW_ + 1 + per_cta - 1) / per_cta;
         loess_edge_tile_kernel<T><<<dim3((unsigned)((n_pts + 31) / 32), (unsigned)(2 * cps)), kThreads, 0, s>>>(
@@ -3747,12 +3757,28 @@ int xsdba_dqm_adjust_f64(const double* sim, int64_t n_pts, int64_t sp, int64_t s
 int xsdba_loess_trend_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
                           const float* scaling, int32_t kind, double f, int32_t niter, int32_t degree, const double* xn,
                           double* trend, void* stream) {
+  if (!(f > 0.0)) return XSDBA_ERR_INVALID_ARGUMENT;
   return launch_loess_trend<float>(x, n_pts, sp, st, grp, scaling, kind, f, niter, degree, xn, trend, stream);
 }
 int xsdba_loess_trend_f64(const double* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
                           const double* scaling, int32_t kind, double f, int32_t niter, int32_t degree, const double* xn,
                           double* trend, void* stream) {
+  if (!(f > 0.0)) return XSDBA_ERR_INVALID_ARGUMENT;
   return launch_loess_trend<double>(x, n_pts, sp, st, grp, scaling, kind, f, niter, degree, xn, trend, stream);
+}
+
+// weights: 0 = tricube, 1 = gaussian (loess.py:16-35, 247)
+int xsdba_loess_trend_w_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                            const float* scaling, int32_t kind, double f, int32_t niter, int32_t degree, int32_t weights,
+                            const double* xn, double* trend, void* stream) {
+  if (!(f > 0.0) || (weights != 0 && weights != 1)) return XSDBA_ERR_INVALID_ARGUMENT;
+  return launch_loess_trend<float>(x, n_pts, sp, st, grp, scaling, kind, weights ? -f : f, niter, degree, xn, trend, stream);
+}
+int xsdba_loess_trend_w_f64(const double* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
+                            const double* scaling, int32_t kind, double f, int32_t niter, int32_t degree, int32_t weights,
+                            const double* xn, double* trend, void* stream) {
+  if (!(f > 0.0) || (weights != 0 && weights != 1)) return XSDBA_ERR_INVALID_ARGUMENT;
+  return launch_loess_trend<double>(x, n_pts, sp, st, grp, scaling, kind, weights ? -f : f, niter, degree, xn, trend, stream);
 }
 
 // microbenchmark entry (see copy_rows_kernel); time-major float32 only, n_pts % (32*v) == 0 expected
