@@ -401,16 +401,19 @@ int xsdba_loess_trend_f64(const double* x_dev, int64_t n_pts, int64_t stride_pt,
                           const xsdba_grouping_t* grp, const double* scaling_dev, int32_t kind, double f,
                           int32_t niter, int32_t degree, const double* xn_dev, double* trend_dev,
                           void* cuda_stream);
-/* The same with the weight function selectable: weights 0 = tricube (loess.py:29-35), 1 = gaussian (loess.py:16-26,
- * `LoessDetrend(weights="gaussian")`, loess.py:247). */
+/* The same with the weight function and the spacing branch selectable: weights 0 = tricube (loess.py:29-35),
+ * 1 = gaussian (loess.py:16-26, `LoessDetrend(weights="gaussian")`, loess.py:247); equal_spacing 1 = the dx > 0 branch
+ * above, 0 = the dx == 0 branch (loess.py:107-111, 151-158: r = round(f n), bandwidth = distance of the r-th closest
+ * sample, weights recomputed for every output), which is what an irregular time axis and every grouped LoessDetrend
+ * (the members of a month or season are not equally spaced) take. */
 int xsdba_loess_trend_w_f32(const float* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
                             const xsdba_grouping_t* grp, const float* scaling_dev, int32_t kind, double f,
-                            int32_t niter, int32_t degree, int32_t weights, const double* xn_dev, double* trend_dev,
-                            void* cuda_stream);
+                            int32_t niter, int32_t degree, int32_t weights, int32_t equal_spacing,
+                            const double* xn_dev, double* trend_dev, void* cuda_stream);
 int xsdba_loess_trend_w_f64(const double* x_dev, int64_t n_pts, int64_t stride_pt, int64_t stride_time,
                             const xsdba_grouping_t* grp, const double* scaling_dev, int32_t kind, double f,
-                            int32_t niter, int32_t degree, int32_t weights, const double* xn_dev, double* trend_dev,
-                            void* cuda_stream);
+                            int32_t niter, int32_t degree, int32_t weights, int32_t equal_spacing,
+                            const double* xn_dev, double* trend_dev, void* cuda_stream);
 
 /*
  * Adjust (DQM): replaces _adjustment.dqm_adjust.func (_adjustment.py:748-780) once the trend of the

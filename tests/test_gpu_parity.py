@@ -1063,3 +1063,58 @@ def test_loess_gaussian_weights_reference_golden():
         np.testing.assert_allclose(got[:, j], want, rtol=1e-11, atol=1e-12, equal_nan=True)
     tas = xs.LoessDetrend(group="time", kind="+", f=0.2, niter=1, d=0, weights="gaussian")
     assert tas.weights == "gaussian"
+
+
+def test_loess_unequal_spacing_reference_golden(golden):
+    """The dx == 0 branch (loess.py:107-111, 151-158): golden cases 2 (d=0, f=0.3, niter=3) and 3 (d=1, f=0.2, niter=1)
+    of the reference's numba _loess_nb, then a genuinely irregular time axis against the restatement."""
+    xs = _xs()
+    x, y = golden["loess_x"], golden["loess_y"]
+    n = x.size
+    t = xs.TimeAxis.daily(2001, 1, "noleap")[:n]
+    series = np.stack([y, y[::-1].copy(), np.where(np.arange(n) % 17 == 3, np.nan, y)], axis=1)
+    for k in (2, 3):
+        d, f, niter, dx = golden[f"loess_case{k}_params"]
+        assert dx == 0.0
+        got = _np(xs.loess_trend(series, time=t, f=float(f), niter=int(niter), d=int(d), equal_spacing=False))
+        np.testing.assert_allclose(got[:, 0], golden[f"loess_case{k}_out"], rtol=1e-9, atol=1e-10, equal_nan=True)
+        for j in (1, 2):
+            want = o.loess_nb(x, series[:, j], f=float(f), niter=int(niter), d=int(d), dx=0.0)
+            np.testing.assert_allclose(got[:, j], want, rtol=1e-9, atol=1e-10, equal_nan=True)
+    rng = np.random.default_rng(12)
+    full = xs.TimeAxis.daily(2001, 2, "standard")
+    keep = np.sort(rng.choice(len(full), size=500, replace=False))
+    ti = full[keep]
+    og = np.asarray(ti.ordinal, np.float64)
+    xi = (og - og[0]) / (og[-1] - og[0])
+    yy = (np.sin(9 * xi)[:, None] + 0.3 * rng.standard_normal((500, 37))).astype(np.float32)
+    yy[40:60, 5] = np.nan
+    for d, f, niter, w in ((0, 0.2, 1, "tricube"), (1, 0.3, 2, "tricube"), (0, 0.25, 1, "gaussian")):
+        got = _np(xs.loess_trend(yy, time=ti, f=f, niter=niter, d=d, weights=w))     # spacing detected: unequal
+        for j in (0, 5, 31, 36):
+            want = o.loess_nb(xi, yy[:, j].astype(np.float64), f=f, niter=niter, weights=w, d=d, dx=0.0)
+            np.testing.assert_allclose(got[:, j], want, rtol=1e-9, atol=1e-10, equal_nan=True)
+
+
+def test_loess_grouped_detrend_matches_restatement():
+    """LoessDetrend(group="time.month") (detrending.py:211-296 through map_groups): every month's members are smoothed
+    on their own normalised time coordinate (unequally spaced: the dx == 0 branch), also through dqm_adjust."""
+    xs = _xs()
+    rng = np.random.default_rng(13)
+    tx = xs.TimeAxis.daily(1981, 4, "noleap")
+    T = len(tx)
+    og = np.asarray(tx.ordinal, np.float64)
+    y = (280 + 4 * np.sin(2 * np.pi * np.arange(T) / 365)[:, None] + rng.standard_normal((T, 9))).astype(np.float32)
+    y[100:140, 3] = np.nan
+    got = _np(xs.loess_trend(y, time=tx, f=0.3, niter=1, d=0, loess_group="time.month"))
+    month = tx.month
+    for j in (0, 3, 8):
+        want = np.full(T, np.nan)
+        for m in range(1, 13):
+            rows = np.nonzero(month == m)[0]
+            xg = (og[rows] - og[rows][0]) / (og[rows][-1] - og[rows][0])
+            want[rows] = o.loess_nb(xg, y[rows, j].astype(np.float64), f=0.3, niter=1, d=0, dx=0.0)
+        np.testing.assert_allclose(got[:, j], want, rtol=1e-9, atol=1e-10, equal_nan=True)
+    # point-major layout gives the same trend
+    got_pm = _np(xs.loess_trend(np.ascontiguousarray(y.T), time=tx, f=0.3, niter=1, d=0, loess_group="time.month", time_axis=-1))
+    np.testing.assert_array_equal(got_pm.T, got)

@@ -415,35 +415,81 @@ def poly_trend(x, *, time, group, degree, kind="+", scaling=None, time_axis=0, p
     return trend
 
 
+def _loess_spacing(o, equal_spacing):
+    """loess.py:250-260: the dx > 0 branch for an equally spaced coordinate unless it is switched off, the dx == 0
+    branch otherwise."""
+    diffs = np.diff(o)
+    if diffs.size and np.all(diffs == diffs[0]):
+        return True if equal_spacing is None else bool(equal_spacing)
+    if equal_spacing:
+        raise NotImplementedError("equal_spacing=True on an unequally spaced coordinate (the reference warns of 'strange "
+                                  "results', loess.py:255) is not built")
+    return False
+
+
 def loess_trend(x, *, time, f=0.2, niter=1, d=0, kind="+", scaling=None, scaling_group=None, loess_group="time",
-                time_axis=0, weights="tricube"):
-    """``LoessDetrend(group="time", f, niter, d).fit(x (+|*) scaling).ds.trend`` (detrending.py:274-296 ->
-    loess.loess_smoothing, loess.py:182-279): float64 tensor shaped like ``x``."""
+                time_axis=0, weights="tricube", equal_spacing=None):
+    """``LoessDetrend(group, f, niter, d, weights, equal_spacing).fit(x (+|*) scaling).ds.trend`` (detrending.py:211-296 ->
+    loess.loess_smoothing, loess.py:182-279): float64 tensor shaped like ``x``.  ``loess_group="time"`` smooths the
+    whole series; a grouped LoessDetrend (``"time.month"``, ``"time.season"``, ``"time.dayofyear"``, window 1) smooths
+    the members of every group on their own, normalised time coordinate -- never equally spaced, hence the dx == 0
+    branch."""
     loess_group = parse_group(loess_group)
-    if loess_group.prop != "group":
-        raise NotImplementedError("grouped LoessDetrend is not built in xsdba_b200 yet (group='time' only)")
-    lib = _lib.load()
-    dt = _widest(x)
-    xs, n_pts, sp, st, _ = _series(x, time_axis, len(time), dt)
-    o = np.asarray(time.ordinal, np.float64)
-    if len(o) < 3 or not np.all(np.diff(o) == np.diff(o)[0]):
-        raise NotImplementedError("only the equal-spacing LOESS branch is built (loess.py:251-263)")
-    xn = _as_device((o - o[0]) / (o[-1] - o[0])).contiguous()   # loess.py:244-245
-    g = parse_group(scaling_group) if scaling is not None else parse_group("time")
-    h = g.handle(time, with_window=False)
-    sc = None
-    if scaling is not None:
-        sc = _as_device(scaling, dt).contiguous()
-        if sc.numel() != n_pts * h.n_groups:
-            raise ValueError("scaling must be (*points, n_groups)")
-    trend = torch.empty(xs.shape, dtype=torch.float64, device=xs.device)
     if weights not in ("tricube", "gaussian"):
         raise NotImplementedError("LOESS weights: 'tricube' or 'gaussian' (loess.py:247)")
+    wflag = 1 if weights == "gaussian" else 0
+    lib = _lib.load()
+    dt = _widest(x)
+    ser = _series(x, time_axis, len(time), dt)
+    xs, n_pts, sp, st, _ = ser
+    o = np.asarray(time.ordinal, np.float64)
     fn = getattr(lib, f"xsdba_loess_trend_w_{_sfx(dt)}")
-    _lib.check(fn(xs.data_ptr(), n_pts, sp, st, h.ptr, sc.data_ptr() if sc is not None else None, _lib.KIND[kind],
-                  float(f), int(niter), int(d), 1 if weights == "gaussian" else 0, xn.data_ptr(), trend.data_ptr(),
-                  _stream()), "loess_trend")
-    return trend
+    if loess_group.prop == "group":
+        if len(o) < 3:
+            raise NotImplementedError("LOESS needs at least 3 time steps")
+        eq = _loess_spacing(o, equal_spacing)
+        xn = _as_device((o - o[0]) / (o[-1] - o[0])).contiguous()   # loess.py:244-245
+        g = parse_group(scaling_group) if scaling is not None else parse_group("time")
+        h = g.handle(time, with_window=False)
+        sc = None
+        if scaling is not None:
+            sc = _as_device(scaling, dt).contiguous()
+            if sc.numel() != n_pts * h.n_groups:
+                raise ValueError("scaling must be (*points, n_groups)")
+        trend = torch.empty(xs.shape, dtype=torch.float64, device=xs.device)
+        _lib.check(fn(xs.data_ptr(), n_pts, sp, st, h.ptr, sc.data_ptr() if sc is not None else None, _lib.KIND[kind],
+                      float(f), int(niter), int(d), wflag, 1 if eq else 0, xn.data_ptr(), trend.data_ptr(), _stream()),
+                   "loess_trend")
+        return trend
+    if loess_group.window != 1:
+        raise NotImplementedError("a grouped LoessDetrend with a window is not built in xsdba_b200")
+    # grouped: (time, points) time-major copy, scaling applied first, one smoothing per group on the gathered members
+    from .base import grouping_handle
+    x2 = (xs if ser.axis == 0 else xs.movedim(-1, 0)).reshape(len(time), n_pts).contiguous()
+    if scaling is not None:
+        sg = parse_group(scaling_group)
+        sc = _as_device(scaling, dt).reshape(n_pts, -1)
+        gi_s = torch.from_numpy(sg.zero_based_index(time).astype(np.int64)).to(x2.device)
+        sct = sc.t()[gi_s]                                         # (time, points)
+        x2 = x2 + sct if kind == "+" else x2 * sct
+    gi = loess_group.zero_based_index(time)
+    trend2 = torch.full((len(time), n_pts), float("nan"), dtype=torch.float64, device=x2.device)
+    for g in range(loess_group.n_groups(time)):
+        rows = np.nonzero(gi == g)[0]
+        if rows.size < 3:
+            continue
+        og = o[rows]
+        eq = _loess_spacing(og, equal_spacing)
+        xn = _as_device((og - og[0]) / (og[-1] - og[0])).contiguous()
+        rows_t = torch.from_numpy(rows.astype(np.int64)).to(x2.device)
+        sub = x2[rows_t].contiguous()
+        tr = torch.empty(sub.shape, dtype=torch.float64, device=x2.device)
+        h = grouping_handle(np.zeros(rows.size, np.int32), 1, 1)
+        _lib.check(fn(sub.data_ptr(), n_pts, 1, n_pts, h.ptr, None, _lib.KIND[kind], float(f), int(niter), int(d), wflag,
+                      1 if eq else 0, xn.data_ptr(), tr.data_ptr(), _stream()), "loess_trend")
+        trend2[rows_t] = tr
+    trend2 = trend2.reshape((len(time),) + tuple(ser[4]))
+    return trend2 if ser.axis == 0 else trend2.movedim(0, -1).contiguous()
 
 
 def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_thresh=None, max_tail_factor=None,
@@ -484,7 +530,8 @@ def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_
     elif isinstance(detrend, LoessDetrend):
         trend = loess_trend(sim, time=time, f=detrend.f, niter=detrend.niter, d=detrend.d, kind=kind, scaling=scaling,
                             scaling_group=group, loess_group=detrend.group, time_axis=ta,
-                            weights=getattr(detrend, "weights", "tricube"))
+                            weights=getattr(detrend, "weights", "tricube"),
+                            equal_spacing=getattr(detrend, "equal_spacing", None))
     else:
         raise TypeError("detrend must be an int, a PolyDetrend or a LoessDetrend")
     nq = af.shape[-1]

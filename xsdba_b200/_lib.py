@@ -46,7 +46,7 @@ for _t in ("f32", "f64"):
     SIGNATURES[f"xsdba_qdm_adjust_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp])
     SIGNATURES[f"xsdba_poly_trend_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, i32, i32, vp, vp, vp])
     SIGNATURES[f"xsdba_loess_trend_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, i32, C.c_double, i32, i32, vp, vp, vp])
-    SIGNATURES[f"xsdba_loess_trend_w_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, i32, C.c_double, i32, i32, i32, vp, vp, vp])
+    SIGNATURES[f"xsdba_loess_trend_w_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, i32, C.c_double, i32, i32, i32, i32, vp, vp, vp])
     SIGNATURES[f"xsdba_dqm_adjust_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp])
     SIGNATURES[f"xsdba_rank_lookup_{_t}"] = (C.c_int, [vp, i64, i64, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp])
     SIGNATURES[f"xsdba_rotate_{_t}"] = (C.c_int, [vp, i64, i32, c_f32p, vp, vp])

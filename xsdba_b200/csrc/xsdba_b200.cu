@@ -1509,6 +1509,67 @@ __device__ double loess_one(const T* __restrict__ y, const int32_t* __restrict__
   return beta0 + beta1 * xi;
 }
 
+// The unequal-spacing branch of _loess_nb (dx == 0, loess.py:107-111, 151-158): r = round(f n) (half to even), the
+// window of output i holds at most 2 (r + 2) samples around it, the bandwidth h is the distance of the r-th closest
+// sample (np.sort(diffs)[r], diffs[0] = 0 is the sample itself) -- found by walking outwards from i on the sorted
+// abscissa instead of sorting -- and the weights are recomputed for every output and iteration.
+template <typename T>
+__device__ double loess_one_unequal(const T* __restrict__ y, const int32_t* __restrict__ tcp, long long n_pts, int n, int i,
+                                    int r, bool gauss, const double* __restrict__ xn, int degree,
+                                    const double* __restrict__ delta) {
+  const int HW = min(r + 2, n), R = min(2 * HW, n);
+  int lo, hi;                                                 // loess.py:124-135
+  if (i < HW) { lo = 0; hi = R; }
+  else if (i >= n - HW - 1) { lo = n - R; hi = n; }
+  else { lo = i - HW; hi = i + HW + 1; }
+  if (r >= hi - lo) return __longlong_as_double(0x7ff8000000000000LL);   // (np.sort(diffs)[r] does not exist)
+  const double xi = xn[tcp[(long long)i * n_pts]];
+  double h = 0.0;
+  {
+    int l = i - 1, u = i + 1;
+    for (int s_ = 0; s_ < r; ++s_) {
+      const double dl = l >= lo ? xi - xn[tcp[(long long)l * n_pts]] : __longlong_as_double(0x7ff0000000000000LL);
+      const double du = u < hi ? xn[tcp[(long long)u * n_pts]] - xi : __longlong_as_double(0x7ff0000000000000LL);
+      if (dl <= du) { h = dl; --l; } else { h = du; ++u; }
+    }
+  }
+  double sw = 0, swy = 0, swx = 0, swxx = 0, swxy = 0;
+  for (int j = lo; j < hi; ++j) {
+    const double xj = xn[tcp[(long long)j * n_pts]];
+    const double uu = fabs(xj - xi) / h;
+    double w = gauss ? gaussian_w(uu) : tricube_w(uu);
+    if (delta) w = delta[(long long)j * n_pts] * w;            // w = di * weight_func(diffs / h)  (loess.py:158)
+    const double yj = (double)y[(long long)j * n_pts];
+    sw += w; swy += w * yj;
+    if (degree == 1) { swx += w * xj; swxx += w * xj * xj; swxy += w * yj * xj; }
+  }
+  if (degree == 0) return swy / sw;                           // loess.py:38-39
+  double a00 = sw, a01 = swx, a10 = swx, a11 = swxx, b0 = swy, b1 = swxy;  // loess.py:42-46
+  if (fabs(a10) > fabs(a00)) { double t_; t_ = a00; a00 = a10; a10 = t_; t_ = a01; a01 = a11; a11 = t_; t_ = b0; b0 = b1; b1 = t_; }
+  const double m = a10 / a00;
+  a11 -= m * a01; b1 -= m * b0;
+  const double beta1 = b1 / a11;
+  const double beta0 = (b0 - a01 * beta1) / a00;
+  return beta0 + beta1 * xi;
+}
+
+// K6n: the unequal-spacing branch, thread = (point, output), lane = point
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+loess_unequal_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, const int32_t* __restrict__ nvalid,
+                     long long n_pts, long long sp, long long st, const double* __restrict__ xn, double f_signed,
+                     int degree, const double* __restrict__ delta, double* __restrict__ trend) {
+  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5, rows_per_cta = blockDim.x >> 5;
+  const long long pt = (long long)blockIdx.x * 32 + lane;
+  if (pt >= n_pts) return;
+  const int n = nvalid[pt];
+  if (n == 0) return;
+  const int r = (int)rint(fabs(f_signed) * (double)n);         // np.round: half to even
+  for (int i = blockIdx.y * rows_per_cta + row; i < n; i += gridDim.y * rows_per_cta)
+    trend[pt * sp + (long long)tc[(long long)i * n_pts + pt] * st] =
+        loess_one_unequal<T>(yc + pt, tc + pt, n_pts, n, i, r, f_signed < 0.0, xn, degree, delta ? delta + pt : nullptr);
+}
+
 // K6b: thread = (point, chunk of RO consecutive outputs).  A chunk that is interior for the thread's series
 // runs as a register-tiled FIR on the precomputed weights (every y / w value is loaded once per chunk and
 // feeds RO accumulators); edge chunks and short series use the literal per-output rule.
@@ -3011,7 +3072,8 @@ loess_delta_kernel(const T* __restrict__ yc, const int32_t* __restrict__ tc, con
 
 template <typename T>
 int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping* grp, const T* scaling,
-                       int kind, double f, int niter, int degree, const double* xn, double* trend, void* stream) {
+                       int kind, double f, int niter, int degree, const double* xn, double* trend, void* stream,
+                       int unequal = 0) {
   if (wrong_device(grp)) return XSDBA_ERR_INVALID_ARGUMENT;  // the handle's tables live on another device
   if ((n_pts > 0 && !x) || !grp || (n_pts > 0 && !xn) || (n_pts > 0 && !trend) || n_pts < 0 || !(f != 0.0) || degree < 0 || degree > 1) return XSDBA_ERR_INVALID_ARGUMENT;
   if (niter < 1) return XSDBA_ERR_INVALID_ARGUMENT;
@@ -3031,6 +3093,33 @@ int launch_loess_trend(const T* x, int64_t n_pts, int64_t sp, int64_t st, const 
   }
   loess_compact_kernel<T><<<(unsigned)((n_pts + kThreads - 1) / kThreads), kThreads, 0, s>>>(
       x, n_pts, sp, st, n_time, grp->gidx, grp->n_groups, scaling, kind, yc, tc, nv, trend);
+  if (unequal) {   // dx == 0 (loess.py:257-260): every output recomputes its bandwidth and weights, no tables
+    double* delta_u = nullptr;
+    int rc_u = XSDBA_OK;
+    if (niter > 1) {
+      const int n_pad = std::max(2, next_pow2(n_time));
+      if ((size_t)n_pad * sizeof(double) > 200 * 1024) rc_u = XSDBA_ERR_SEGMENT_TOO_LONG;
+      else if (cudaMallocAsync(&delta_u, sizeof(double) * n_pts * n_time, s) != cudaSuccess) { cudaGetLastError(); rc_u = XSDBA_ERR_OUT_OF_MEMORY; }
+      else rc_u = set_smem(loess_delta_kernel<T>, (size_t)n_pad * sizeof(double));
+    }
+    const unsigned chunks_u = (unsigned)std::min<int64_t>(std::max<int64_t>(1, (n_time + 7) / 8), 4096);
+    for (int it = 0; it < niter && rc_u == XSDBA_OK; ++it) {
+      loess_unequal_kernel<T><<<dim3((unsigned)((n_pts + 31) / 32), chunks_u), kThreads, 0, s>>>(
+          yc, tc, nv, n_pts, sp, st, xn, f, degree, it > 0 ? delta_u : nullptr, trend);
+      ++g_launches;
+      if (it + 1 < niter) {
+        const int n_pad = std::max(2, next_pow2(n_time));
+        loess_delta_kernel<T><<<(unsigned)n_pts, kThreads, (size_t)n_pad * sizeof(double), s>>>(yc, tc, nv, n_pts, sp, st, n_pad,
+                                                                                                trend, delta_u);
+        ++g_launches;
+      }
+    }
+    ++g_launches;
+    if (delta_u) cudaFreeAsync(delta_u, s);
+    cudaFreeAsync(yc, s); cudaFreeAsync(tc, s); cudaFreeAsync(nv, s);
+    if (rc_u != XSDBA_OK) return rc_u;
+    return cuda_status(cudaGetLastError());
+  }
   // interior weight table: at most 2*HW+1 <= f*n_time + 6 rows per point
   const double fa = std::fabs(f);  // (f < 0: gaussian weights, see LoessGeom)
   const int w_rows = (int)std::min<double>((double)n_time, fa * (double)n_time + 8.0);
@@ -3767,18 +3856,21 @@ int xsdba_loess_trend_f64(const double* x, int64_t n_pts, int64_t sp, int64_t st
   return launch_loess_trend<double>(x, n_pts, sp, st, grp, scaling, kind, f, niter, degree, xn, trend, stream);
 }
 
-// weights: 0 = tricube, 1 = gaussian (loess.py:16-35, 247)
+// weights: 0 = tricube, 1 = gaussian (loess.py:16-35, 247); equal_spacing: 1 = the dx > 0 branch (xn equally spaced),
+// 0 = the dx == 0 branch (loess.py:251-260)
 int xsdba_loess_trend_w_f32(const float* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
                             const float* scaling, int32_t kind, double f, int32_t niter, int32_t degree, int32_t weights,
-                            const double* xn, double* trend, void* stream) {
+                            int32_t equal_spacing, const double* xn, double* trend, void* stream) {
   if (!(f > 0.0) || (weights != 0 && weights != 1)) return XSDBA_ERR_INVALID_ARGUMENT;
-  return launch_loess_trend<float>(x, n_pts, sp, st, grp, scaling, kind, weights ? -f : f, niter, degree, xn, trend, stream);
+  return launch_loess_trend<float>(x, n_pts, sp, st, grp, scaling, kind, weights ? -f : f, niter, degree, xn, trend, stream,
+                                   equal_spacing ? 0 : 1);
 }
 int xsdba_loess_trend_w_f64(const double* x, int64_t n_pts, int64_t sp, int64_t st, const xsdba_grouping_t* grp,
                             const double* scaling, int32_t kind, double f, int32_t niter, int32_t degree, int32_t weights,
-                            const double* xn, double* trend, void* stream) {
+                            int32_t equal_spacing, const double* xn, double* trend, void* stream) {
   if (!(f > 0.0) || (weights != 0 && weights != 1)) return XSDBA_ERR_INVALID_ARGUMENT;
-  return launch_loess_trend<double>(x, n_pts, sp, st, grp, scaling, kind, weights ? -f : f, niter, degree, xn, trend, stream);
+  return launch_loess_trend<double>(x, n_pts, sp, st, grp, scaling, kind, weights ? -f : f, niter, degree, xn, trend, stream,
+                                    equal_spacing ? 0 : 1);
 }
 
 // microbenchmark entry (see copy_rows_kernel); time-major float32 only, n_pts % (32*v) == 0 expected

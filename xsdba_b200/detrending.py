@@ -30,7 +30,7 @@ class LoessDetrend(BaseDetrend):
 
     def __init__(self, group="time", kind="+", f=0.2, niter=1, d=0, weights="tricube", equal_spacing=None,
                  skipna=True, mult_skip_zeros=False):
-        if mult_skip_zeros or not skipna or weights not in ("tricube", "gaussian") or equal_spacing is False:
-            raise NotImplementedError("only tricube / gaussian, skipna, equal-spacing LOESS is built in xsdba_b200")
+        if mult_skip_zeros or not skipna or weights not in ("tricube", "gaussian"):
+            raise NotImplementedError("only skipna LOESS with tricube / gaussian weights is built in xsdba_b200")
         super().__init__(group=group, kind=kind, f=f, niter=niter, d=d, weights=weights)
-        self.f, self.niter, self.d, self.weights = float(f), int(niter), int(d), weights
+        self.f, self.niter, self.d, self.weights, self.equal_spacing = float(f), int(niter), int(d), weights, equal_spacing
