@@ -156,3 +156,49 @@ def test_adapter_end_to_end_matches_oracle(dt):
     out2 = A.dqm_adjust(trd.drop_vars(["P0_ref", "P0_hist", "pth"]).assign(sim=da(sim, ("time", "lat", "lon"))), group=grp,
                         interp="nearest", extrapolation="constant", kind="+", detrend=poly)
     assert bits_equal(out2["scen"].values, out["scen"].values)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("group,window", [("time.month", 1), ("time.dayofyear", 31)])
+def test_adapter_add_dims_pools_realizations(group, window):
+    """Grouper(..., add_dims=["realization"]) (base.py:410-415): train pools the extra dimension into every group's
+    sample -- checked against nan_quantile on the concatenated group segments of all realizations -- and adjust applies
+    the pooled tables to every realization."""
+    from xsdba_b200 import xr_adapter as A
+    dt = np.float32
+    rng = np.random.default_rng(17)
+    years, R, P = 4, 3, 5
+    import xsdba_b200 as xs
+    tx = xs.TimeAxis.daily(1981, years, "noleap")
+    to = o.daily_time_axis(1981, years, "noleap")
+    T = len(tx)
+    ref = (280 + 3 * rng.standard_normal((T, R, P))).astype(dt)
+    hist = (282 + 4 * rng.standard_normal((T, R, P))).astype(dt)
+    hist[5:40, 1, 2] = np.nan
+    sim = (283 + 4 * rng.standard_normal((T, R, P))).astype(dt)
+    q = o.equally_spaced_nodes(15).astype(dt)
+    coords = {"time": xr.time_index(tx)}
+    da = lambda a, dims: xr.DataArray(a, dims, coords)  # noqa: E731
+    grp = types.SimpleNamespace(name=group, window=window, add_dims=["realization"], prop=group.split(".")[1])
+    ds = xr.Dataset({"ref": da(ref, ("time", "realization", "pt")), "hist": da(np.transpose(hist, (1, 0, 2)), ("realization", "time", "pt"))})
+    tr = A.eqm_train(ds, group=grp, kind="+", quantiles=q)
+    assert tr["af"].dims == ("pt", grp.prop, "quantiles")
+    gidx, G, _ = o.group_index(to, group)
+    hq = tr["hist_q"].values
+    af = tr["af"].values
+    for g in (0, 1, G // 2, G - 1):
+        seg_h = np.concatenate([o.group_segment(hist[:, r, :].T.copy(), gidx, g, window) for r in range(R)], axis=1)
+        seg_r = np.concatenate([o.group_segment(ref[:, r, :].T.copy(), gidx, g, window) for r in range(R)], axis=1)
+        hq_o = o.nan_quantile(seg_h, q)
+        rq_o = o.nan_quantile(seg_r, q)
+        assert bits_equal(hq[:, g], hq_o), g
+        assert bits_equal(af[:, g], (rq_o - hq_o).astype(dt)), g
+    trained = tr.drop_vars(["P0_ref", "P0_hist", "pth", "hist_q_raw"])
+    out = A.qm_adjust(trained.assign(sim=da(sim, ("time", "realization", "pt"))), group=grp, interp="nearest",
+                      extrapolation="constant", kind="+", adapt_freq_thresh=None, max_tail_factor=None)
+    assert out["scen"].dims == ("time", "realization", "pt")
+    grp0 = types.SimpleNamespace(name=group, window=window, add_dims=[], prop=grp.prop)
+    for r in range(R):   # every realization separately with the same (pooled) tables
+        one = A.qm_adjust(trained.assign(sim=da(sim[:, r, :], ("time", "pt"))), group=grp0, interp="nearest",
+                          extrapolation="constant", kind="+", adapt_freq_thresh=None, max_tail_factor=None)
+        assert bits_equal(out["scen"].values[:, r, :], one["scen"].values)

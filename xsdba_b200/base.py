@@ -71,11 +71,13 @@ class Grouper:
         if window > 1 and "." not in group:
             # base.py:151-156
             raise ValueError("Grouping windows are meant for grouping along a time accessor (e.g. 'time.dayofyear')")
-        if add_dims:
-            raise NotImplementedError("add_dims pooling is not built in xsdba_b200 yet (SURVEY.md 8b)")
         if prop not in ("group", "month", "dayofyear", "season"):
             raise NotImplementedError(f"grouping on time.{prop} is not supported")
-        self.dim, self.prop, self.name, self.window, self.add_dims = dim, prop, group, int(window), []
+        # add_dims (base.py:410-415): dimension NAMES pooled with time in the group-wise reductions.  Only the
+        # Dataset-level seam (xr_adapter) knows dimension names; it pools them into the time axis before it calls the
+        # array-level functions, which refuse a Grouper that still carries add_dims (see handle()).
+        self.dim, self.prop, self.name, self.window = dim, prop, group, int(window)
+        self.add_dims = list(add_dims or [])
 
     def __repr__(self):
         return f"Grouper(name='{self.name}', window={self.window})"
@@ -118,6 +120,9 @@ class Grouper:
         return (idx if self.prop == "season" else idx - 1).astype(np.int32)
 
     def handle(self, time: TimeAxis, with_window: bool = True) -> GroupingHandle:
+        if self.add_dims:
+            raise NotImplementedError("add_dims pooling needs named dimensions: go through xsdba_b200.xr_adapter "
+                                      "(base.py:410-415)")
         return grouping_handle(self.zero_based_index(time), self.n_groups(time), self.window if with_window else 1)
 
 

@@ -62,6 +62,54 @@ def time_axis_of(ds, dim="time") -> TimeAxis:
     return TimeAxis.from_fields(get("year"), get("month"), get("day"), cal)
 
 
+class _PooledGrouper(Grouper):
+    """``Grouper(..., add_dims=[...])`` after pooling (base.py:410-415): the extra dimensions are laid end to end along the
+    time axis -- block a holds the series of pooled coordinate a, blocks are separated by ``gap`` NaN time steps that
+    belong to no group, so that a window around the first days of one block cannot reach the last days of the block
+    before it (NaN samples are ignored by every group-wise reduction).  Group index, coordinate and number of groups
+    are those of the ORIGINAL time axis, repeated per block."""
+
+    def __init__(self, base: Grouper, time: TimeAxis, n_rep: int, gap: int):
+        super().__init__(base.name, window=base.window)
+        self._base_time, self._n_rep, self._gap = time, int(n_rep), int(gap)
+
+    def _tile(self, idx, fill):
+        T = len(self._base_time)
+        out = np.full((self._n_rep, T + self._gap), fill, dtype=np.asarray(idx).dtype)
+        out[:, :T] = idx
+        return out.reshape(-1)
+
+    def zero_based_index(self, time=None):
+        return self._tile(super().zero_based_index(self._base_time), -1).astype(np.int32)
+
+    def n_groups(self, time=None):
+        return super().n_groups(self._base_time)
+
+    def get_coordinate(self, time=None):
+        return super().get_coordinate(self._base_time)
+
+    def pooled_time(self) -> TimeAxis:
+        t = self._base_time
+        tile = lambda a: self._tile(np.asarray(a), np.asarray(a)[0])  # noqa: E731  (spacer steps: any valid date)
+        return TimeAxis(tile(t.year), tile(t.month), tile(t.day), tile(t.dayofyear), tile(t.days_in_month), t.calendar)
+
+
+def _pool(da, add_dims, gap, dtype):
+    """DataArray -> ((n_rep * (T + gap), n_pts) array with NaN spacer steps, other dims, their sizes, n_rep)."""
+    missing = [d for d in add_dims if d not in da.dims]
+    if missing:
+        raise ValueError(f"add_dims {missing} are not dimensions of the data")
+    other = [d for d in da.dims if d != "time" and d not in add_dims]
+    a = np.asarray(da.transpose(*add_dims, "time", *other).values)
+    n_rep = int(np.prod(a.shape[:len(add_dims)]))
+    T = a.shape[len(add_dims)]
+    sizes = a.shape[len(add_dims) + 1:]
+    a = a.reshape(n_rep, T, -1)
+    out = np.full((n_rep, T + gap, a.shape[2]), np.nan, dtype=dtype)
+    out[:, :T] = a
+    return out.reshape(n_rep * (T + gap), -1), other, tuple(sizes), n_rep
+
+
 def _series(da, dtype):
     """DataArray (time among its dims) -> (numpy (time, n_pts) C-contiguous, other dims, their sizes)."""
     other = [d for d in da.dims if d != "time"]
@@ -125,18 +173,31 @@ def _train(ds, *, group, kind, quantiles, normalize, adapt_freq_thresh=None, jit
            jitter_over_thresh_value=None, jitter_over_thresh_upper_bnd=None, max_tail_factor=None):
     grp = _group(group)
     dt = _widest(ds, ("ref", "hist"))
-    ref, pdims, psizes = _series(ds["ref"], dt)
-    hist, pdims_h, psizes_h = _series(ds["hist"].transpose(*ds["ref"].dims), dt)
+    time = time_axis_of(ds)
+    l4_time = time
+    if grp.add_dims:
+        # base.py:410-415: the group-wise reductions of train (quantiles, means, frequencies) pool the extra dimensions
+        if adapt_freq_thresh is not None:
+            raise NotImplementedError("adapt_freq_thresh together with add_dims is not built in xsdba_b200")
+        gap = grp.window // 2
+        ref, pdims, psizes, n_rep = _pool(ds["ref"], grp.add_dims, gap, dt)
+        hist, pdims_h, psizes_h, n_rep_h = _pool(ds["hist"], grp.add_dims, gap, dt)
+        if n_rep_h != n_rep:
+            raise ValueError("ref and hist must share their pooled dimensions")
+        grp = _PooledGrouper(grp, time, n_rep, gap)
+        l4_time = grp.pooled_time()
+    else:
+        ref, pdims, psizes = _series(ds["ref"], dt)
+        hist, pdims_h, psizes_h = _series(ds["hist"].transpose(*ds["ref"].dims), dt)
     if (pdims_h, psizes_h) != (pdims, psizes):
         raise ValueError("ref and hist must share their non-time dimensions")
-    time = time_axis_of(ds)
     kw = dict(adapt_freq_thresh=_thresh(adapt_freq_thresh, ds["hist"]),
               jitter_under_thresh_value=_thresh(jitter_under_thresh_value, ds["hist"]),
               jitter_over_thresh_value=_thresh(jitter_over_thresh_value, ds["hist"]),
               jitter_over_thresh_upper_bnd=_thresh(jitter_over_thresh_upper_bnd, ds["hist"]),
               max_tail_factor=max_tail_factor)
     fn = L4.dqm_train if normalize else L4.eqm_train
-    res = fn(L4.Dataset({"ref": ref, "hist": hist}, time=time, time_axis=0), group=grp, kind=kind,
+    res = fn(L4.Dataset({"ref": ref, "hist": hist}, time=l4_time, time_axis=0), group=grp, kind=kind,
              quantiles=np.asarray(quantiles), **kw)
     G, nq = res["af"].shape[-2], res["af"].shape[-1]
     shp = psizes + (G, nq)
@@ -174,16 +235,41 @@ def dqm_train(ds, *, group, kind, quantiles, adapt_freq_thresh=None, jitter_unde
                   jitter_over_thresh_upper_bnd=jitter_over_thresh_upper_bnd, max_tail_factor=max_tail_factor)
 
 
+def _adjust_group(group, pooled_ranks=False):
+    """The grouper of an adjust call: add_dims only matter to group-wise reductions, and adjust has one -- the ranks of
+    qdm_adjust with rank_window=True (Grouper.apply(main_only=False), base.py:410-415), not built for pooled dims."""
+    grp = _group(group)
+    if grp.add_dims:
+        if pooled_ranks:
+            raise NotImplementedError("qdm_adjust(rank_window=True) with add_dims (ranks pooled over the extra "
+                                      "dimensions) is not built in xsdba_b200")
+        grp = Grouper(grp.name, window=grp.window)
+    return grp
+
+
 def _adjust_inputs(ds, grp, names, extra=()):
+    """sim as (time, points); trained tables as (points, ...).  Dimensions of sim that the tables do not have (the
+    add_dims pooled at training time, base.py:410-415) are adjusted with the same table: the tables are repeated along
+    them."""
     dt = _widest(ds, ("sim", "af"))
     sim, pdims, psizes = _series(ds["sim"], dt)
+    tdims_of = lambda n: [d for d in pdims if d in ds[n].dims]  # noqa: E731
+    rep_dims = [d for d in pdims if d not in ds[names[0]].dims]
+    if rep_dims and list(pdims[:len(rep_dims)]) != rep_dims:   # pooled dims first, so that a repeat is a plain tile
+        order = rep_dims + [d for d in pdims if d not in rep_dims]
+        sim, pdims, psizes = _series(ds["sim"].transpose("time", *order), dt)
+    n_rep = int(np.prod([psizes[pdims.index(d)] for d in rep_dims])) if rep_dims else 1
+
+    def table(n, tail, tdt):
+        t = _table(ds[n], tdims_of(n), tail, tdt)
+        return np.ascontiguousarray(np.tile(t, (n_rep,) + (1,) * (t.ndim - 1))) if n_rep > 1 else t
     tables = {}
     for n in names:
-        tables[n] = _table(ds[n], pdims, [grp.prop, "quantiles"], dt)
+        tables[n] = table(n, [grp.prop, "quantiles"], dt)
     for n in extra:
         if n in ds and not np.isnan(np.asarray(ds[n].values)).all():
             tail = [grp.prop, "quantiles"] if n == "hist_q_raw" else [grp.prop]
-            tables[n] = _table(ds[n], pdims, tail, np.float64 if n.startswith("P0") else dt)
+            tables[n] = table(n, tail, np.float64 if n.startswith("P0") else dt)
     return dt, sim, pdims, psizes, tables
 
 
@@ -199,7 +285,7 @@ def _series_out(ds, name, data, pdims, psizes, like="sim"):
 
 def qm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None, max_tail_factor=None):
     """``xsdba._adjustment.qm_adjust`` (_adjustment.py:594-676)."""
-    grp = _group(group)
+    grp = _adjust_group(group)
     dt, sim, pdims, psizes, tb = _adjust_inputs(ds, grp, ("af", "hist_q"), ("hist_q_raw", "P0_ref", "P0_hist", "pth"))
     res = L4.qm_adjust(L4.Dataset({"sim": sim, **tb}, time=time_axis_of(ds), time_axis=0), group=grp, interp=interp,
                        extrapolation=extrapolation, kind=kind, adapt_freq_thresh=_thresh(adapt_freq_thresh, ds["sim"]),
@@ -211,7 +297,7 @@ def qm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None,
 def qdm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None, rank_window=None,
                max_tail_factor=None):
     """``xsdba._adjustment.qdm_adjust`` (_adjustment.py:783-886)."""
-    grp = _group(group)
+    grp = _adjust_group(group, pooled_ranks=bool(rank_window))
     dt, sim, pdims, psizes, tb = _adjust_inputs(ds, grp, ("af",), ("hist_q_raw", "P0_ref", "P0_hist", "pth"))
     q = np.asarray(ds["quantiles"].values)
     res = L4.qdm_adjust(L4.Dataset({"sim": sim, "quantiles": q, **tb}, time=time_axis_of(ds), time_axis=0), group=grp,
@@ -243,6 +329,8 @@ def _detrend(detrend, kind, grp):
 def dqm_adjust(ds, *, group, interp, extrapolation, kind, detrend=1, adapt_freq_thresh=None, max_tail_factor=None):
     """``xsdba._adjustment.dqm_adjust`` (_adjustment.py:679-780)."""
     grp = _group(group)
+    if grp.add_dims:
+        raise NotImplementedError("dqm_adjust with add_dims is not built in xsdba_b200")
     dt, sim, pdims, psizes, tb = _adjust_inputs(ds, grp, ("af", "hist_q"), ("hist_q_raw", "P0_ref", "P0_hist", "pth"))
     tb["scaling"] = _table(ds["scaling"], pdims, [grp.prop], dt)
     res = L4.dqm_adjust(L4.Dataset({"sim": sim, **tb}, time=time_axis_of(ds), time_axis=0), group=grp, interp=interp,
