@@ -47,6 +47,7 @@ extern "C" {
 
 #define XSDBA_INTERP_NEAREST 0
 #define XSDBA_INTERP_LINEAR 1
+#define XSDBA_INTERP_CUBIC 2   /* group = "time" only: scipy interp1d(kind="cubic"), the not-a-knot cubic spline */
 
 #define XSDBA_EXTRAP_CONSTANT 0
 #define XSDBA_EXTRAP_NAN 1

@@ -1118,3 +1118,37 @@ def test_loess_grouped_detrend_matches_restatement():
     # point-major layout gives the same trend
     got_pm = _np(xs.loess_trend(np.ascontiguousarray(y.T), time=tx, f=0.3, niter=1, d=0, loess_group="time.month", time_axis=-1))
     np.testing.assert_array_equal(got_pm.T, got)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_cubic_interpolation_group_time_matches_scipy(dt):
+    """interp="cubic" with group="time": scipy interp1d(kind="cubic") (the not-a-knot spline of make_interp_spline)
+    through the oracle, for EQM, QDM and DQM adjust.  Tolerances: 1e-6 (float32) / 1e-9 (float64) relative -- the spline
+    is solved by the second-derivative tridiagonal system here and by B-spline collocation in SciPy."""
+    xs = _xs()
+    case = ("time", 1, "noleap", 3, 20, "+", "tas", dt)
+    tx, to, ref, hist, sim = _make(case, n_pts=11)
+    q = o.equally_spaced_nodes(20).astype(dt)
+    gidx, G, _ = o.group_index(to, "time")
+    af_o, hq_o = o.eqm_train(ref.T.copy(), hist.T.copy(), gidx, G, 1, q, "+")
+    rtol = 1e-6 if dt == np.float32 else 1e-9
+    for extrap in ("constant", "nan"):
+        scen_o = o.qm_adjust(sim.T.copy(), af_o, hq_o, group="time", time=to, interp="cubic", extrapolation=extrap, kind="+")
+        out = xs.qm_adjust(xs.Dataset({"sim": sim, "af": af_o, "hist_q": hq_o}, time=tx), group="time", interp="cubic",
+                           extrapolation=extrap, kind="+")
+        np.testing.assert_allclose(_np(out.scen).T, scen_o, rtol=rtol, atol=0, equal_nan=True)
+    scen_q, simq_o = o.qdm_adjust(sim.T.copy(), af_o, q, group="time", time=to, window=1, interp="cubic",
+                                  extrapolation="constant", kind="+")
+    out = xs.qdm_adjust(xs.Dataset({"sim": sim, "af": af_o, "quantiles": q}, time=tx), group="time", interp="cubic",
+                        extrapolation="constant", kind="+")
+    assert bits_equal(_np(out.sim_q).T, simq_o)
+    np.testing.assert_allclose(_np(out.scen).T, scen_q, rtol=rtol, atol=0, equal_nan=True)
+    af_d, hq_d, sc_d = o.dqm_train(ref.T.copy(), hist.T.copy(), gidx, G, 1, q, "+")
+    scen_d, trend_d = o.dqm_adjust(sim.T.copy(), af_d, hq_d, sc_d, group="time", window=1, time=to, interp="cubic",
+                                   extrapolation="constant", kind="+", detrend=1)
+    out = xs.dqm_adjust(xs.Dataset({"sim": sim, "af": af_d, "hist_q": hq_d, "scaling": sc_d}, time=tx), group="time",
+                        interp="cubic", extrapolation="constant", kind="+", detrend=1)
+    np.testing.assert_allclose(_np(out.scen).T, scen_d, rtol=max(rtol, 2e-6), atol=0, equal_nan=True)
+    with pytest.raises(NotImplementedError):
+        xs.qm_adjust(xs.Dataset({"sim": sim, "af": af_o, "hist_q": hq_o}, time=tx), group="time.month", interp="cubic",
+                     extrapolation="constant", kind="+")

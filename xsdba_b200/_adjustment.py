@@ -266,9 +266,9 @@ def qm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None,
     for ``adapt_freq_thresh``; + hist_q_raw for ``max_tail_factor``)."""
     if interp not in ("nearest", "linear", "cubic") or extrapolation not in _lib.EXTRAP:
         raise ValueError("interp must be nearest/linear/cubic and extrapolation constant/nan")
-    if interp == "cubic":
-        raise NotImplementedError("cubic interpolation is not built in xsdba_b200 yet")
     group = parse_group(group)
+    if interp == "cubic" and group.prop != "group":
+        raise NotImplementedError("cubic interpolation over time.<prop> groups (2-D Clough-Tocher) is not built in xsdba_b200")
     lib = _lib.load()
     time = ds.time
     dt = _widest(ds["sim"], ds["af"])
@@ -325,9 +325,9 @@ def _qdm_linear_geometry(group, time, q, n_groups):
 def qdm_adjust(ds, *, group, interp, extrapolation, kind, adapt_freq_thresh=None, rank_window=None,
                max_tail_factor=None, seed=0):
     """``xsdba._adjustment.qdm_adjust`` (_adjustment.py:783-886): ds holds af, quantiles, sim."""
-    if interp == "cubic":
-        raise NotImplementedError("cubic interpolation is not built in xsdba_b200 yet")
     group = parse_group(group)
+    if interp == "cubic" and group.prop != "group":
+        raise NotImplementedError("cubic interpolation over time.<prop> groups (2-D Clough-Tocher) is not built in xsdba_b200")
     if rank_window is None:
         rank_window = False
         if group.window > 1:
@@ -497,9 +497,9 @@ def dqm_adjust(ds, *, group, interp, kind, extrapolation, detrend=1, adapt_freq_
     """``xsdba._adjustment.dqm_adjust`` (_adjustment.py:679-780): ds holds scaling, af, hist_q, sim (+ P0_ref,
     P0_hist, pth for ``adapt_freq_thresh``; + hist_q_raw for ``max_tail_factor``).
     ``detrend`` is an int (PolyDetrend degree on the adjust group) or a PolyDetrend / LoessDetrend."""
-    if interp == "cubic":
-        raise NotImplementedError("cubic interpolation is not built in xsdba_b200 yet")
     group = parse_group(group)
+    if interp == "cubic" and group.prop != "group":
+        raise NotImplementedError("cubic interpolation over time.<prop> groups (2-D Clough-Tocher) is not built in xsdba_b200")
     if group.prop not in ("group", "dayofyear") and interp != "nearest":
         raise NotImplementedError("broadcasting `scaling` with linear interpolation over months is not built yet")
     lib = _lib.load()

@@ -23,7 +23,7 @@ i64 = C.c_int64
 i32 = C.c_int32
 
 KIND = {"+": 43, "*": 42}
-INTERP = {"nearest": 0, "linear": 1}
+INTERP = {"nearest": 0, "linear": 1, "cubic": 2}
 EXTRAP = {"constant": 0, "nan": 1}
 
 # name -> (restype, argtypes).  Data pointers are passed as void* (device or host addresses).

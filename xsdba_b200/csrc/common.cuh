@@ -371,6 +371,20 @@ __device__ T lookup_1d(const Tables<T, C>& tb, int c, TX x, int interp, int extr
     }
     return ys[(size_t)lo * C];
   }
+  if (interp == 2) {
+    // cubic: scipy interp1d(kind="cubic") = make_interp_spline(k=3), the not-a-knot cubic spline through the kept nodes
+    // (needs four of them; SciPy raises below that).  Second derivatives M from stage_cubic (tb.ysl[0]); on
+    // [x_i, x_{i+1}]:  S = A y_i + B y_{i+1} + ((A^3 - A) M_i + (B^3 - B) M_{i+1}) h^2 / 6, float64.
+    if (n < 4) return Num<T>::nan();
+    const T* ms = tb.ysl[0] + c;
+    int idx = lower_bound_col<TX, T, C>(xs, n, x);
+    idx = idx < 1 ? 1 : (idx > n - 1 ? n - 1 : idx);
+    const double x0 = (double)xs[(size_t)(idx - 1) * C], x1 = (double)xs[(size_t)idx * C];
+    const double y0 = (double)ys[(size_t)(idx - 1) * C], y1 = (double)ys[(size_t)idx * C];
+    const double m0 = (double)ms[(size_t)(idx - 1) * C], m1 = (double)ms[(size_t)idx * C];
+    const double h = x1 - x0, A = (x1 - (double)x) / h, B = ((double)x - x0) / h;
+    return (T)(A * y0 + B * y1 + ((A * A * A - A) * m0 + (B * B * B - B) * m1) * (h * h) / 6.0);
+  }
   if (n < 2) return Num<T>::nan();
   if (sizeof(T) == 8 && sizeof(TX) == 8) {
     // float64 nodes and values: interp1d delegates to numpy.interp (compiled_base.c arr_interp)
@@ -400,6 +414,61 @@ __device__ T lookup_1d(const Tables<T, C>& tb, int c, TX x, int interp, int extr
   const TX w_hi = Num<TX>::div(Num<TX>::sub(x, (TX)x_lo), (TX)den);
   const TX w_lo = Num<TX>::div(Num<TX>::sub((TX)x_hi, x), (TX)den);
   return (T)Num<TX>::add(Num<TX>::mul(w_hi, (TX)y_hi), Num<TX>::mul(w_lo, (TX)y_lo));
+}
+
+// Second derivatives of the not-a-knot cubic spline through the compacted centre row of every column (1-D tables,
+// group = "time"): tridiagonal system in M_1..M_{n-2} with M_0, M_{n-1} eliminated by the not-a-knot conditions
+// (third derivative continuous at x_1 and x_{n-2}), Thomas algorithm with float64 arithmetic (recurrence values kept
+// in the table dtype), one thread per column.  M goes to the factor array of slot 0, the recurrences to the node
+// arrays of slots 0 and 2 -- the neighbour-row slots, which only grouped lookups use.  Needs the three-slot layout.
+// Call after stage_tables (ends with a barrier itself).
+template <typename T, int C>
+__device__ void stage_cubic(const Tables<T, C>& tb) {
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x, n = tb.nvl[1][c];
+    const T* xs = tb.xsl[1] + c;
+    const T* ys = tb.ysl[1] + c;
+    T* ms = tb.ysl[0] + c;
+    T* cp = tb.xsl[0] + c;   // modified super-diagonal
+    T* dp = tb.xsl[2] + c;   // modified right-hand side, then the solution
+    if (n >= 4) {
+      auto X = [&](int k) { return (double)xs[(size_t)k * C]; };
+      auto Y = [&](int k) { return (double)ys[(size_t)k * C]; };
+      const int m = n - 2;  // unknowns M_1..M_{n-2}, row i <-> M_{i+1}
+      for (int i = 0; i < m; ++i) {
+        const int k = i + 1;
+        const double h0 = X(k) - X(k - 1), h1 = X(k + 1) - X(k);
+        double a = h0, b = 2.0 * (h0 + h1), cc = h1;
+        const double r = 6.0 * ((Y(k + 1) - Y(k)) / h1 - (Y(k) - Y(k - 1)) / h0);
+        if (k == 1) {          // M_0 = ((h0 + h1) M_1 - h0 M_2) / h1
+          b += h0 * (h0 + h1) / h1; cc -= h0 * h0 / h1; a = 0.0;
+        }
+        if (k == n - 2) {      // M_{n-1} = ((h0 + h1) M_{n-2} - h1 M_{n-3}) / h0
+          b += h1 * (h0 + h1) / h0; a -= h1 * h1 / h0; cc = 0.0;
+        }
+        if (i == 0) { cp[0] = (T)(cc / b); dp[0] = (T)(r / b); }
+        else {
+          const double den = b - a * (double)cp[(size_t)(i - 1) * C];
+          cp[(size_t)i * C] = (T)(cc / den);
+          dp[(size_t)i * C] = (T)((r - a * (double)dp[(size_t)(i - 1) * C]) / den);
+        }
+      }
+      double next = 0.0;
+      for (int i = m - 1; i >= 0; --i) {
+        const double v = (double)dp[(size_t)i * C] - (double)cp[(size_t)i * C] * next;
+        ms[(size_t)(i + 1) * C] = (T)v;
+        dp[(size_t)i * C] = (T)v;
+        next = v;
+      }
+      {
+        const double h0 = X(1) - X(0), h1 = X(2) - X(1);
+        ms[0] = (T)(((h0 + h1) * (double)dp[0] - h0 * (double)dp[(size_t)1 * C]) / h1);
+        const double g0 = X(n - 2) - X(n - 3), g1 = X(n - 1) - X(n - 2);
+        ms[(size_t)(n - 1) * C] = (T)(((g0 + g1) * (double)dp[(size_t)(m - 1) * C] - g1 * (double)dp[(size_t)(m - 2) * C]) / g0);
+      }
+    }
+  }
+  __syncthreads();
 }
 
 // best candidate of one compacted row for the 2-D Euclidean-nearest rule

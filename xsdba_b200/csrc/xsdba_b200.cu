@@ -677,6 +677,7 @@ adjust_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long lon
   if (m0 == m1) return;
   const bool grouped = n_groups > 1;
   stage_tables<T, C>(tb, stage, n0, n_pts, g, grouped);
+  if (interp == XSDBA_INTERP_CUBIC && !grouped) stage_cubic<T, C>(tb);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const long long pt = n0 + lane;
@@ -1342,6 +1343,7 @@ dqm_adjust_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long
   if (m0 == m1) return;
   const bool grouped = n_groups > 1;
   stage_tables<T, C>(tb, stage, n0, n_pts, g, grouped);
+  if (interp == XSDBA_INTERP_CUBIC && !grouped) stage_cubic<T, C>(tb);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const long long pt = n0 + lane;
   if (pt >= n_pts) return;
@@ -1768,6 +1770,7 @@ rank_kernel(const T* __restrict__ sim, long long n_pts, long long sp, long long 
   if (do_adjust) {
     tb.gx = q; tb.gy = af; tb.x_shared = true; tb.G = n_groups; tb.pt_stride = (long long)n_groups * nq;
     stage_tables<T, C>(tb, stage, n0, n_pts, g, grouped);
+    if (interp == XSDBA_INTERP_CUBIC && !grouped) stage_cubic<T, C>(tb);
   }
   if (threadIdx.x < C) {
     const int c = threadIdx.x, n = cnt[c];
@@ -2766,7 +2769,7 @@ int launch_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsd
   if (wrong_device(grp)) return XSDBA_ERR_INVALID_ARGUMENT;  // the handle's tables live on another device
   if ((n_pts > 0 && !sim) || !grp || (n_pts > 0 && !af) || (n_pts > 0 && !hq) || (n_pts > 0 && !scen) || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
-  if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR && interp != XSDBA_INTERP_CUBIC) return XSDBA_ERR_INVALID_ARGUMENT;
   if (extrap != XSDBA_EXTRAP_CONSTANT && extrap != XSDBA_EXTRAP_NAN) return XSDBA_ERR_INVALID_ARGUMENT;
   if (grp->n_groups > 1 && interp != XSDBA_INTERP_NEAREST) return XSDBA_ERR_UNSUPPORTED;
   if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
@@ -2846,8 +2849,9 @@ int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba
   if (do_adjust) {
     if ((n_pts > 0 && !af) || (n_pts > 0 && !q) || (n_pts > 0 && !scen) || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
     if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
-    if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR) return XSDBA_ERR_INVALID_ARGUMENT;
+    if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR && interp != XSDBA_INTERP_CUBIC) return XSDBA_ERR_INVALID_ARGUMENT;
     if (extrap != XSDBA_EXTRAP_CONSTANT && extrap != XSDBA_EXTRAP_NAN) return XSDBA_ERR_INVALID_ARGUMENT;
+    if (grp->n_groups > 1 && interp == XSDBA_INTERP_CUBIC) return XSDBA_ERR_UNSUPPORTED;
     if (grp->n_groups > 1 && interp != XSDBA_INTERP_NEAREST && !(gcoord && diag)) return XSDBA_ERR_UNSUPPORTED;
   } else if (!sim_q) {
     return XSDBA_ERR_INVALID_ARGUMENT;
@@ -2866,7 +2870,7 @@ int launch_rank(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const xsdba
   // the linear rule interpolates between rows: it needs the three staged rows.  The nearest rule almost never
   // leaves the centre row (quantile nodes are < 1 apart, neighbouring rows are 1 away), so it stages that row only
   // and reads the neighbours from global memory in the rare case -- a third of the shared memory, 3x the occupancy
-  const int slots = (do_adjust && grp->n_groups > 1 && interp == XSDBA_INTERP_LINEAR) ? 3 : 1;
+  const int slots = (do_adjust && ((grp->n_groups > 1 && interp == XSDBA_INTERP_LINEAR) || interp == XSDBA_INTERP_CUBIC)) ? 3 : 1;
   // the staged lookup tables share the CTA's shared memory with the sort buffer: narrow the tile until both fit
   auto need = [&](int c) {
     size_t top = 1;
@@ -2909,7 +2913,7 @@ int launch_dqm_adjust(const T* sim, int64_t n_pts, int64_t sp, int64_t st, const
   if (wrong_device(grp)) return XSDBA_ERR_INVALID_ARGUMENT;  // the handle's tables live on another device
   if ((n_pts > 0 && !sim) || !grp || (n_pts > 0 && !af) || (n_pts > 0 && !hq) || (n_pts > 0 && !scaling) || (n_pts > 0 && !trend) || (n_pts > 0 && !scen) || n_pts < 0 || nq <= 0) return XSDBA_ERR_INVALID_ARGUMENT;
   if (kind != XSDBA_KIND_ADD && kind != XSDBA_KIND_MUL) return XSDBA_ERR_INVALID_ARGUMENT;
-  if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR) return XSDBA_ERR_INVALID_ARGUMENT;
+  if (interp != XSDBA_INTERP_NEAREST && interp != XSDBA_INTERP_LINEAR && interp != XSDBA_INTERP_CUBIC) return XSDBA_ERR_INVALID_ARGUMENT;
   if (extrap != XSDBA_EXTRAP_CONSTANT && extrap != XSDBA_EXTRAP_NAN) return XSDBA_ERR_INVALID_ARGUMENT;
   if (grp->n_groups > 1 && interp != XSDBA_INTERP_NEAREST) return XSDBA_ERR_UNSUPPORTED;
   if (grp->n_groups > 65535) return XSDBA_ERR_UNSUPPORTED;
