@@ -530,16 +530,21 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
     //      halves of a word are prefixed independently by the packed adds (no carry: totals <= 1024); the upper
     //      halves (buckets 512..1023) then start at the number of keys in buckets 0..511 ----------------------
     {
-      unsigned sum = 0, mxc = 0;
+      // "some bucket holds more than kBktAbort keys" with packed arithmetic: count + (0x8000 - (kBktAbort + 1)) sets
+      // bit 15 of its half (counts <= 1024: no carry between the halves); the two single-valued buckets (0: column
+      // minimum, 1023: +inf keys) are masked out
+      constexpr unsigned kBias = (0x8000u - (unsigned)(kBktAbort + 1)) * 0x00010001u;
+      unsigned sum = 0, over = 0;
 #pragma unroll
       for (int j = 0; j < kBktW / 32; ++j) {
         const unsigned w = hist[(warp * (kBktW / 32) + j) * 32 + lane];
         sum += w;
-        // largest bucket of the column, the two single-valued buckets (0: column minimum, 1023: +inf keys) aside
-        const unsigned lo = (warp == 0 && j == 0) ? 0u : (w & 0xffffu);
-        const unsigned hi = (warp == 31 && j == kBktW / 32 - 1) ? 0u : (w >> 16);
-        mxc = max(mxc, max(lo, hi));
+        unsigned wm = w;
+        if (j == 0) wm = warp == 0 ? (w & 0xffff0000u) : w;
+        if (j == kBktW / 32 - 1) wm = warp == 31 ? (wm & 0x0000ffffu) : wm;
+        over |= (wm + kBias) & 0x80008000u;
       }
+      const unsigned mxc = over ? (unsigned)kBktAbort + 1u : 0u;
       tot[warp * kBktPitch + lane] = sum;
       // Heavy buckets (ties away from the minimum, multi-scale data such as jittered precipitation) or a degenerate
       // column: selecting inside such buckets would cost more than sorting, so the whole tile goes to K1f's sorter
