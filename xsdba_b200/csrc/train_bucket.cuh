@@ -19,24 +19,23 @@
 //      slot and scatters it: the column is now sorted by bucket, buckets hold 1-3 samples for continuous data;
 //   5. order statistics i, i+1: the bucket of position i is a function of the VALUE stored there (no search); its
 //      range comes from the prefix table; up to 8 samples are selected in registers through a 19-exchange
-//      network.  A node that meets a bucket of 9..24 samples (~1e-4 of the nodes of smooth data, but one of them
-//      used to hold the other 31 warps at the barrier for a whole serial selection) is put on a shared-memory work
-//      list and served afterwards by a whole warp: one sample per lane, ranks by shuffles.  Columns with heavier
-//      buckets (ties, multi-scale data) or an infinite range send the tile to K1f's sorter right after the
+//      network; the few threads (~1e-3) that meet a bucket of 9..16 samples retry out of line with a 63-exchange
+//      network on a 16-slot window.  Columns with heavier buckets (ties, multi-scale data) or an infinite range send
+//      the tile to K1f's sorter right after the
 //      histogram -- same results.
 // Semantics: nbutils._nan_quantile_1d / _get_indexes / _linear_interpolation (nbutils.py:24-148), NaNs excluded,
 // utils.get_correction (utils.py:130-143), dqm_train's normalisation (_adjustment.py:163-179) -- as K1f.
 // =============================================================================================
 constexpr int kBktN = 1024;       // buckets per column
 constexpr int kBktW = kBktN / 2;  // counter words per column: bucket b lives in half b / 512 of word b % 512
-constexpr int kBktAbort = 24;     // a bucket with more keys than this (seen in the histogram) sends the tile to the sorter
+constexpr int kBktAbort = 16;     // a bucket with more keys than this (seen in the histogram) sends the tile to the sorter
 constexpr int kBktPitch = 33;     // row pitch of the [warp][column] partial tables (transposed reads are conflict free)
 
 struct BktSmem {
   static constexpr size_t buf = 0;                                   // float    [1024 + 16][32] scattered / sorted column, 16 rows of +inf
   static constexpr size_t hist = buf + (1024 + 16) * 32 * 4;          // unsigned [512][32] packed counters (aliases: psum)
-  static constexpr size_t part = hist + (size_t)kBktW * 32 * 4;      // [3][32][33]: pmin, pmax (float), pcnt (int); aliases: tot, work list
-  static constexpr size_t col = part + 3 * 32 * kBktPitch * 4;       // [8][32]: cmin, cmax (float), cnt (int), mu[2], scale (float), work-list length
+  static constexpr size_t part = hist + (size_t)kBktW * 32 * 4;      // [3][32][33]: pmin, pmax (float), pcnt (int); aliases: tot
+  static constexpr size_t col = part + 3 * 32 * kBktPitch * 4;       // [8][32]: cmin, cmax (float), cnt (int), mu[2], scale (float), row stride copies
   static constexpr size_t rows = col + 8 * 32 * 4;                   // int [1024] member rows of the group (-1 past S)
   static constexpr size_t q = rows + 1024 * 4;                       // double [kFastMaxNq]
   static constexpr size_t pos = q + kFastMaxNq * 8;                  // int [kFastMaxNq], float [kFastMaxNq]: node positions of a full column
@@ -186,42 +185,6 @@ __device__ __noinline__ bool bucket_select_pair16(const unsigned* __restrict__ e
   return true;
 }
 
-// The same pair by a whole warp (all 32 lanes call it with the same column): buckets of up to 32 samples, one sample
-// per lane, rank = number of samples that sort before it (value, then slot), by shuffles.
-__device__ __forceinline__ void bucket_select_pair_warp(const unsigned* __restrict__ endp, const float* __restrict__ col,
-                                                        float cmin, float scale, int i, float& left, float& right) {
-  const float inf = __int_as_float(0x7f800000);
-  const int lane = threadIdx.x & 31;
-  const float xi = col[i * 32], xj = col[(i + 1) * 32];
-  const unsigned b0 = bucket_key(xi, cmin, scale) & (kBktN - 1), b1 = bucket_key(xj, cmin, scale) & (kBktN - 1);
-  left = right = xi;
-  if (b0 != 0 && b0 != kBktN - 1) {
-    const int e0 = bucket_end(endp, b0);
-    const int s0 = bucket_end(endp, b0 - 1);
-    const int m = e0 - s0, r = i - s0;  // (m <= kBktAbort < 32)
-    const float x = lane < m ? col[(s0 + lane) * 32] : inf;
-    int rank = 0;
-    for (int j = 0; j < m; ++j) {
-      const float y = __shfl_sync(0xffffffffu, x, j);
-      rank += (y < x || (y == x && j < lane)) ? 1 : 0;
-    }
-    if (lane >= m) rank = 64;
-    left = __shfl_sync(0xffffffffu, x, __ffs(__ballot_sync(0xffffffffu, rank == r)) - 1);
-    const unsigned nxt = __ballot_sync(0xffffffffu, rank == r + 1);
-    if (nxt) right = __shfl_sync(0xffffffffu, x, __ffs(nxt) - 1);
-  }
-  if (b1 != b0) {
-    float mn = xj;
-    if (b1 != kBktN - 1) {
-      const int m1 = bucket_end(endp, b1) - (i + 1);
-      mn = lane < m1 ? col[(i + 1 + lane) * 32] : inf;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
-    }
-    right = mn;
-  }
-}
-
 // nbutils._linear_interpolation (nbutils.py:101-104, 146) on the pair
 __device__ __forceinline__ float bucket_interpolate(float left, float right, float gamma, float cmax) {
   const float diff = right - left;
@@ -256,8 +219,7 @@ __device__ __forceinline__ float bucket_quantile_node_fast(const unsigned* __res
 }
 
 // One quantile node of one column.  MODE 0: second try of a thread after bucket_quantile_node_fast (buckets of up to 16
-// samples; sets heavy beyond that); MODE 1: the same by a whole warp (up to 32); MODE 2: from the two sorted runs
-// the sorter leaves.
+// samples, the most the histogram check lets through); MODE 2: from the two sorted runs the sorter leaves.
 template <int MODE>
 __device__ __forceinline__ float bucket_quantile_node(const unsigned* __restrict__ endp, const float* __restrict__ colp,
                                                       int i, float gamma, int n, int S, float cmin, float cmax,
@@ -271,8 +233,6 @@ __device__ __forceinline__ float bucket_quantile_node(const unsigned* __restrict
     left = right = cmin;
     if (MODE == 0) {
       heavy = !bucket_select_pair16(endp, colp, cmin, scale, i, left, right);
-    } else if (MODE == 1) {
-      bucket_select_pair_warp(endp, colp, cmin, scale, i, left, right);
     } else {
       // both runs in full: the 1024 keys are the valid values plus +inf padding, and in a degenerate column
       // (infinite range: every key in one bucket) the slot order says nothing about which is which
@@ -332,13 +292,11 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
   float* pmax = pmin + 32 * kBktPitch;
   int* pcnt = reinterpret_cast<int*>(pmax + 32 * kBktPitch);
   unsigned* tot = reinterpret_cast<unsigned*>(pmin);                   // alias (prefix, after the min / max reduction)
-  unsigned short* work = reinterpret_cast<unsigned short*>(pmin);      // alias (selection, after the prefix)
   float* cminv = reinterpret_cast<float*>(smem_raw + BktSmem::col);
   float* cmaxv = cminv + 32;
   int* cnt = reinterpret_cast<int*>(cmaxv + 32);
   float* mu = reinterpret_cast<float*>(cnt + 32);                      // [2][32]
   float* scalev = cminv + 5 * 32;
-  int* n_work = reinterpret_cast<int*>(cminv + 7 * 32);
   int* rows_tab = reinterpret_cast<int*>(smem_raw + BktSmem::rows);
   double* qs = reinterpret_cast<double*>(smem_raw + BktSmem::q);
   int* pos_i = reinterpret_cast<int*>(smem_raw + BktSmem::pos);        // node positions of a column without NaNs (n == S)
@@ -498,7 +456,6 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
 #pragma unroll
       for (int j = 0; j < kBktW * 32 / kFastThreads; ++j) hist[tid + j * kFastThreads] = 0u;
     }
-    if (tid == 0) *n_work = 0;
     __syncthreads();
     {  // warp c reduces column c: lane r holds the partial of warp r (pitch 33: conflict free both ways)
       float mn = pmin[lane * kBktPitch + warp], mx = pmax[lane * kBktPitch + warp];
@@ -513,7 +470,7 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
     const float cmin = cminv[lane], cmax = cmaxv[lane];
     bool degenerate;  // infinite / NaN range: the bucket map says nothing, the column goes through the sorter
     const float scale = bucket_scale(cmin, cmax, degenerate);
-    if (warp == 0) scalev[lane] = scale;  // (read back by the scatter and by the work-list pass, both behind barriers)
+    if (warp == 0) scalev[lane] = scale;  // (read back by the scatter, behind a barrier)
     // ---- histogram: every slot has a key (valid value or +inf), no predicates --------------------------
     // (32-bit shared addresses: counter word = this lane's base + 128 bytes x (bucket mod 512) -- LOP3 + LEA)
     const uint32_t hist_lane = (uint32_t)__cvta_generic_to_shared(hist + lane);
@@ -613,8 +570,7 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
     // ---- quantiles: node k = item / 32 is warp-uniform, lane = column.  Results go straight to global memory
     //      (4-byte stores 2400 bytes apart; the 8 nodes of a 32-byte sector are written by 8 warps within the same
     //      round, the L2 write-back merges them) -- no staging buffer, no result registers across the barrier ----
-    // (o = offset of node 0 of the column in the trained tables: hoisted out of the node loop for the thread's own
-    //  column, recomputed only for the few work-list nodes)
+    // (o = offset of node 0 of the column in the trained tables: hoisted out of the node loop)
     auto emit = [&](long long o_col0, bool okc, int k, int c, float r) {
       const long long o = o_col0 + k;
       if (mode == 1) {
@@ -630,11 +586,10 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
     const long long o_own = (n0 + lane) * out_stride + (long long)g * nq;
     // a thread owns nodes tid / 32 and tid / 32 + 32 (nq = 50: two nodes for 18 warps, one for 14): both go through the
     // same straight-line code in one basic block, so the scheduler overlaps their shared-memory latencies
-    auto node_retry = [&](int item, int k, int i, float gamma) {  // a bucket of 9..24 samples (rare, divergent)
-      bool heavy = false;
+    auto node_retry = [&](int k, int i, float gamma) {  // a bucket of 9..16 samples (rare, divergent)
+      bool heavy = false;   // (stays false: more than kBktAbort = 16 keys in a bucket sent the tile to the sorter)
       const float r = bucket_quantile_node<0>(hist + lane, buf + lane, i, gamma, n, S, cmin, cmax, scale, heavy);
-      if (heavy) work[atomicAdd(n_work, 1)] = (unsigned short)item;  // more than 16: a warp's job
-      else emit(o_own, col_ok, k, lane, r);
+      emit(o_own, col_ok, k, lane, r);
     };
 #pragma unroll 1
     for (int item0 = tid; item0 < n_items; item0 += 2 * kFastThreads) {
@@ -650,28 +605,12 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
         bool h0, h1;
         const float r0 = bucket_quantile_node_fast(hist + lane, buf + lane, i0, g0, n, S, cmin, cmax, scale, h0);
         const float r1 = bucket_quantile_node_fast(hist + lane, buf + lane, i1, g1, n, S, cmin, cmax, scale, h1);
-        if (h0) node_retry(item0, k0, i0, g0); else emit(o_own, col_ok, k0, lane, r0);
-        if (h1) node_retry(item1, k1, i1, g1); else emit(o_own, col_ok, k1, lane, r1);
+        if (h0) node_retry(k0, i0, g0); else emit(o_own, col_ok, k0, lane, r0);
+        if (h1) node_retry(k1, i1, g1); else emit(o_own, col_ok, k1, lane, r1);
       } else {
         bool h0;
         const float r0 = bucket_quantile_node_fast(hist + lane, buf + lane, i0, g0, n, S, cmin, cmax, scale, h0);
-        if (h0) node_retry(item0, k0, i0, g0); else emit(o_own, col_ok, k0, lane, r0);
-      }
-    }
-    __syncthreads();
-    {
-      const int n_heavy = *n_work;
-#pragma unroll 1
-      for (int e = warp; e < n_heavy; e += 32) {
-        const int item = work[e], k = item >> 5, c = item & 31;
-        const float cmin_c = cminv[c], cmax_c = cmaxv[c];
-        const int n_c = cnt[c];
-        bool unused = false;
-        const float scale_c = scalev[c];
-        int i; float gamma;
-        bucket_node_position(n_c, qs[k], i, gamma);
-        const float r = bucket_quantile_node<1>(hist + c, buf + c, i, gamma, n_c, S, cmin_c, cmax_c, scale_c, unused);
-        if (lane == 0) emit((n0 + c) * out_stride + (long long)g * nq, n0 + c < n_pts, k, c, r);
+        if (h0) node_retry(k0, i0, g0); else emit(o_own, col_ok, k0, lane, r0);
       }
     }
     __syncthreads();  // refq complete; hist / buf / the partial tables are free for the next pass
