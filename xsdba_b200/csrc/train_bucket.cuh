@@ -282,7 +282,7 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
                     const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
                     const float* __restrict__ q, int nq, int kind, int normalize_arg, int mode, float* __restrict__ af,
                     float* __restrict__ hist_q, float* __restrict__ scaling, JitterParams jp, int use_jitter,
-                    const double* __restrict__ q64, int vec_enable) {
+                    const double* __restrict__ q64, int vec_enable, int n_sm) {
   const int normalize = NORM ? normalize_arg : 0;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* buf = reinterpret_cast<float*>(smem_raw + BktSmem::buf);
@@ -387,15 +387,15 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
     // ---- L2 prefetch of what this SM loads next, so that the next load phase (during which nothing else runs on
     //      this SM: one CTA per SM, all warps in the same phase) sees L2 latency and bandwidth, and the HBM traffic
     //      overlaps the histogram / scatter / selection phases.  Pass 0 prefetches this tile's hist rows; the last
-    //      pass the ref rows of the tile 148 blocks ahead in launch order (the one an SM of this wave picks up
+    //      pass the ref rows of the tile n_sm (148) blocks ahead in launch order (the one an SM of this wave picks up
     //      next).  Lane i of warp w prefetches slot w + 32 i: one instruction per warp. -------------------------
     {
       const float* nxt = nullptr;
       int gn = g;
       if (mode == 0 && pass == 0) {
         nxt = hist_in + n0;
-      } else if (n_tiles >= 148) {
-        long long x2 = (long long)blockIdx.x + 148;
+      } else if (n_tiles >= n_sm) {
+        long long x2 = (long long)blockIdx.x + n_sm;
         if (x2 >= n_tiles) { x2 -= n_tiles; ++gn; }
         if (gn < n_groups) nxt = ref + x2 * 32;
       }

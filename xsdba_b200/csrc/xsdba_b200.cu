@@ -887,33 +887,38 @@ pack_tables_kernel(const float* __restrict__ af, const float* __restrict__ hist_
   // float32 arithmetic with directed rounding, every bound moved TOWARDS its node: the decided intervals can only be
   // narrower than the exact ones (midpoint +- 1e-5 gap, node +- 0.99), never wider
   const float tiny = __int_as_float(1);  // smallest subnormal: x -+ tiny rounds to the neighbour of x
-  for (int j = warp; j < R; j += n_warps) {
-    float hi = finf, lo = finf, y = fnan;
+  // Row t of the image: thread t of a column handles the GAP between nodes t - 1 and t once (one midpoint, one
+  // half-width) and writes the two bounds that depend on it, hi[t] (end of node t - 1's interval) and lo[t + 1] (start
+  // of node t's), plus the factor y[t].  Rows 0 and 1 also need lo[0] / lo[1].
+  float* out_hi = out;
+  float* out_lo = out + (size_t)R * C;
+  float* out_y = out + (size_t)2 * R * C;
+  for (int t = warp; t < R; t += n_warps) {
+    float hi = finf, lo_next = finf, y = fnan;
     if (usable) {
-      if (j == 0) {
-        hi = __fadd_rd(blo, -tiny); lo = -finf; y = clo;
-      } else if (j <= n) {
-        const int k = j - 1;
-        const float xk = xs[k];
-        float L = blo, H = bhi;
-        if (k > 0) {
-          const float xl = xs[k - 1];
-          L = __fadd_ru(__fmul_ru(0.5f, __fadd_ru(xl, xk)), __fmul_ru(1e-5f, __fsub_ru(xk, xl)));
+      if (t == 0) {
+        hi = __fadd_rd(blo, -tiny); y = clo;
+        lo_next = fmaxf(blo, __fadd_ru(xs[0], -0.99f));            // lo[1]: node 0 answers from blo on
+      } else if (t <= n) {
+        const float xl = xs[t - 1];                                 // node t - 1 = interval t
+        y = ys[t - 1];
+        if (t < n) {
+          const float xh = xs[t];
+          const float w = __fmul_ru(1e-5f, __fsub_ru(xh, xl));
+          hi = fminf(__fsub_rd(__fmul_rd(0.5f, __fadd_rd(xl, xh)), w), __fadd_rd(xl, 0.99f));
+          lo_next = fmaxf(__fadd_ru(__fmul_ru(0.5f, __fadd_ru(xl, xh)), w), __fadd_ru(xh, -0.99f));
+        } else {
+          hi = fminf(bhi, __fadd_rd(xl, 0.99f));                    // the last node answers up to bhi
+          lo_next = __fadd_ru(bhi, tiny);                           // lo[n + 1]: beyond bhi
         }
-        if (k < n - 1) {
-          const float xh = xs[k + 1];
-          H = __fsub_rd(__fmul_rd(0.5f, __fadd_rd(xk, xh)), __fmul_ru(1e-5f, __fsub_ru(xh, xk)));
-        }
-        lo = fmaxf(L, __fadd_ru(xk, -0.99f));
-        hi = fminf(H, __fadd_rd(xk, 0.99f));
-        y = ys[k];
-      } else if (j == n + 1) {
-        lo = __fadd_ru(bhi, tiny); y = chi;
+      } else if (t == n + 1) {
+        y = chi;
       }
     }
-    out[(size_t)j * C + lane] = hi;
-    out[(size_t)(R + j) * C + lane] = lo;
-    out[(size_t)(2 * R + j) * C + lane] = y;
+    out_hi[(size_t)t * C + lane] = hi;
+    out_y[(size_t)t * C + lane] = y;
+    if (t + 1 < R) out_lo[(size_t)(t + 1) * C + lane] = lo_next;
+    if (t == 0) out_lo[lane] = usable ? -finf : finf;
   }
   if (warp == 0) reinterpret_cast<int*>(out + (size_t)3 * R * C)[lane] = n;
 }
@@ -2554,7 +2559,7 @@ bool launch_train_fast(const float* ref, const float* hist, int64_t n_pts, int64
     train_bucket_kernel<J, N><<<grid, kFastThreads, smem_b, s>>>(ref, hist, n_pts, st, grp->segments.off,            \
                                                                  grp->segments.rows, grp->n_groups, q, nq, kind,    \
                                                                  normalize, mode, af, hq, scaling, jp, use_jitter,  \
-                                                                 q64, vec_enable);                                  \
+                                                                 q64, vec_enable, sm_count());                      \
   } while (0)
     if (use_jitter && normalize) XS_TRAIN_BKT(true, true);
     else if (use_jitter) XS_TRAIN_BKT(true, false);
