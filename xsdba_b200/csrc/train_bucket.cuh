@@ -282,7 +282,7 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
                     const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rows, int n_groups,
                     const float* __restrict__ q, int nq, int kind, int normalize_arg, int mode, float* __restrict__ af,
                     float* __restrict__ hist_q, float* __restrict__ scaling, JitterParams jp, int use_jitter,
-                    const double* __restrict__ q64, int vec_enable, int n_sm) {
+                    const double* __restrict__ q64, int vec_enable, long long n_tiles) {
   const int normalize = NORM ? normalize_arg : 0;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* buf = reinterpret_cast<float*>(smem_raw + BktSmem::buf);
@@ -303,12 +303,21 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
   float* pos_g = reinterpret_cast<float*>(pos_i + kFastMaxNq);
   float* refq = reinterpret_cast<float*>(smem_raw + BktSmem::refq);
 
-  const int g = blockIdx.y;
-  const long long n0 = (long long)blockIdx.x * 32;
-  const int S = seg_off[g + 1] - seg_off[g];
   const long long out_stride = (long long)n_groups * nq;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float fnan = Num<float>::nan(), finf = Num<float>::inf();
+  if (tid < 32) reinterpret_cast<int*>(cminv + 6 * 32)[tid] = (int)st * 4;
+  if (tid < 16 * 32) buf[1024 * 32 + tid] = finf;  // the rows behind the column (the selection reads 8 / 16-slot windows)
+
+  // Persistent: one CTA per SM walks the (group, tile) work items in launch order -- CTA b takes items b, b + grid, ...,
+  // so the CTAs of a wave stream neighbouring tiles as before, without a CTA launch (198 KB of shared memory, 1024
+  // threads) between two items, and the per-group tables are rebuilt only when the group changes.
+  const long long n_work = n_tiles * n_groups;
+  int g_loaded = -1;
+  for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
+  const int g = (int)(w / n_tiles);
+  const long long n0 = (w - (long long)g * n_tiles) * 32;
+  const int S = seg_off[g + 1] - seg_off[g];
 
   if (S == 0) {  // group without members: NaN rows
     const int nqp = (nq + 31) & ~31;
@@ -320,17 +329,19 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
       if (mode == 0) hist_q[o] = fnan;
     }
     if (mode == 0 && scaling && tid < 32 && n0 + tid < n_pts) scaling[(n0 + tid) * n_groups + g] = fnan;
-    return;
+    continue;
   }
-  if (tid < nq) {
-    const double qk = q64 ? q64[tid] : (double)q[tid];
-    qs[tid] = qk;
-    bucket_node_position(S, qk, pos_i[tid], pos_g[tid]);
+  if (g != g_loaded) {   // (CTA-uniform) the tables of the group: member rows, node positions of a full column
+    __syncthreads();
+    if (tid < nq) {
+      const double qk = q64 ? q64[tid] : (double)q[tid];
+      qs[tid] = qk;
+      bucket_node_position(S, qk, pos_i[tid], pos_g[tid]);
+    }
+    rows_tab[tid] = tid < S ? seg_rows[seg_off[g] + tid] : -1;
+    g_loaded = g;
+    __syncthreads();
   }
-  rows_tab[tid] = tid < S ? seg_rows[seg_off[g] + tid] : -1;
-  if (tid < 32) reinterpret_cast<int*>(cminv + 6 * 32)[tid] = (int)st * 4;
-  if (tid < 16 * 32) buf[1024 * 32 + tid] = finf;  // the rows behind the column (the selection reads 8 / 16-slot windows)
-  __syncthreads();
   const bool col_ok = n0 + lane < n_pts;
   // whole tile inside the grid, rows 16-byte aligned: the vector load path
   const bool vec_ok = vec_enable && n0 + 32 <= n_pts && (st & 3) == 0 &&
@@ -340,7 +351,6 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
   // the row stride, read back from shared memory: a value ptxas cannot prove uniform stays in a vector register, and
   // row x stride + base is then ONE IMAD.WIDE per load instead of IMAD.WIDE (uniform operand) + a 64-bit add
   const int st4 = reinterpret_cast<volatile int*>(cminv + 6 * 32)[lane];  // (32 equal copies, one per lane)
-  const long long n_tiles = gridDim.x;
 
   for (int pass = 0; pass < n_pass; ++pass) {
     // ---- load: warp w takes slots 32 w .. 32 w + 31 (one 128-byte row per instruction); columns past n_pts read
@@ -387,17 +397,16 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
     // ---- L2 prefetch of what this SM loads next, so that the next load phase (during which nothing else runs on
     //      this SM: one CTA per SM, all warps in the same phase) sees L2 latency and bandwidth, and the HBM traffic
     //      overlaps the histogram / scatter / selection phases.  Pass 0 prefetches this tile's hist rows; the last
-    //      pass the ref rows of the tile n_sm (148) blocks ahead in launch order (the one an SM of this wave picks up
-    //      next).  Lane i of warp w prefetches slot w + 32 i: one instruction per warp. -------------------------
+    //      pass the ref rows of this CTA's next work item.  Lane i of warp w prefetches slot w + 32 i: one instruction per warp. -------------------------
     {
       const float* nxt = nullptr;
       int gn = g;
       if (mode == 0 && pass == 0) {
         nxt = hist_in + n0;
-      } else if (n_tiles >= n_sm) {
-        long long x2 = (long long)blockIdx.x + n_sm;
-        if (x2 >= n_tiles) { x2 -= n_tiles; ++gn; }
-        if (gn < n_groups) nxt = ref + x2 * 32;
+      } else if (w + gridDim.x < n_work) {   // this CTA's next work item
+        const long long w2 = w + gridDim.x;
+        gn = (int)(w2 / n_tiles);
+        nxt = ref + (w2 - (long long)gn * n_tiles) * 32;
       }
       if (nxt) {
         const int slot = slot0 + lane;
@@ -619,4 +628,5 @@ train_bucket_kernel(const float* __restrict__ ref, const float* __restrict__ his
     const float mr = mu[tid], mh = mu[32 + tid];  // scaling = get_correction(mu_hist, mu_ref)
     scaling[(n0 + tid) * n_groups + g] = kind == XSDBA_KIND_ADD ? __fsub_rn(mr, mh) : __fdiv_rn(mr, mh);
   }
+  }  // work items
 }

@@ -2551,15 +2551,18 @@ bool launch_train_fast(const float* ref, const float* hist, int64_t n_pts, int64
   // (its shared-memory image fits the 227 KB of an SM up to nq ~ 110; finer grids keep the sorter)
   if (!(algo && strcmp(algo, "sort") == 0) && BktSmem::total(nq) <= 227 * 1024) {
     const size_t smem_b = BktSmem::total(nq);
+    const long long n_tiles_b = (n_pts + 31) / 32;
+    // persistent: one CTA per SM (its shared-memory image leaves room for one) walks the (group, tile) items
+    const dim3 grid_b((unsigned)std::min<long long>(n_tiles_b * grp->n_groups, (long long)sm_count()));
     static const int vec_enable = getenv("XSDBA_B200_NO_VEC_LOAD") ? 0 : 1;  // (A/B switch of the 16-byte load path)
 #define XS_TRAIN_BKT(J, N)                                                                                            \
   do {                                                                                                               \
     *rc = set_smem(train_bucket_kernel<J, N>, smem_b);                                                               \
     if (*rc) return true;                                                                                            \
-    train_bucket_kernel<J, N><<<grid, kFastThreads, smem_b, s>>>(ref, hist, n_pts, st, grp->segments.off,            \
+    train_bucket_kernel<J, N><<<grid_b, kFastThreads, smem_b, s>>>(ref, hist, n_pts, st, grp->segments.off,          \
                                                                  grp->segments.rows, grp->n_groups, q, nq, kind,    \
                                                                  normalize, mode, af, hq, scaling, jp, use_jitter,  \
-                                                                 q64, vec_enable, sm_count());                      \
+                                                                 q64, vec_enable, n_tiles_b);                       \
   } while (0)
     if (use_jitter && normalize) XS_TRAIN_BKT(true, true);
     else if (use_jitter) XS_TRAIN_BKT(true, false);
