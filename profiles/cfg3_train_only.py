@@ -1,5 +1,6 @@
-"""Config 3's train step alone (QDM / EQM train, Grouper("time.dayofyear", 31), nq = 100, pre-jittered pr) on 8 lat rows.
-    python profiles/cfg3_train_only.py [lat_rows] [reps]"""
+"""Config 3's train step alone (QDM / EQM train, Grouper("time.dayofyear", 31), nq = 100, pre-jittered pr) on 8 lat rows,
+optionally followed by the rank_window=True adjust (K3w).
+    python profiles/cfg3_train_only.py [lat_rows] [reps] [adjust]"""
 import os, sys, warnings
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -20,3 +21,9 @@ for i in range(reps):
     obj = xs.QuantileDeltaMapping.train(ref, hist, time=tt, nquantiles=100, group=g, kind="*")
     e1.record(); e1.synchronize()
     print(f"cfg3 train {e0.elapsed_time(e1):.3f} ms ({n} points)")
+    if len(sys.argv) > 3 and sys.argv[3] == "adjust":
+        ts = xs.TimeAxis.daily(2041, 30, "noleap")
+        e0.record()
+        scen = obj.adjust(hist, time=ts, interp="nearest", extrapolation="constant", rank_window=True)
+        e1.record(); e1.synchronize()
+        print(f"cfg3 adjust rank_window=True {e0.elapsed_time(e1):.3f} ms")

@@ -15,6 +15,10 @@ ncu --set full --clock-control none --import-source on -k regex:train_window -c 
 python profiles/ncu_summary.py /tmp/win.ncu-rep "K1w train_window_kernel: config 3 train, 11 520 points x 365 day-of-year groups (window 31), nq = 100" > gpurun_out/r02_ncu_train_window.txt
 ncu -i /tmp/win.ncu-rep --page source --csv --print-source sass > /tmp/win_src.csv 2>/dev/null
 python profiles/phase_shares.py /tmp/win_src.csv >> gpurun_out/r02_ncu_train_window.txt
+ncu --set full --clock-control none --import-source on -k regex:rank_window -c 1 -o /tmp/rkw python profiles/cfg3_train_only.py 8 1 adjust > /tmp/c2.log 2>&1
+python profiles/ncu_summary.py /tmp/rkw.ncu-rep "K3w rank_window_kernel: config 3 adjust with rank_window=True, 11 520 points x 365 day-of-year groups (window 31), nq = 100" > gpurun_out/r02_ncu_rank_window.txt
+ncu -i /tmp/rkw.ncu-rep --page source --csv --print-source sass > /tmp/rkw_src.csv 2>/dev/null
+python profiles/phase_shares.py /tmp/rkw_src.csv >> gpurun_out/r02_ncu_rank_window.txt
 # launch lists of the bench command, our kernels only (the synthetic-data generators of torch run outside the timed region)
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"train_|pack_|adjust_|rank_" -c 400 --csv --log-file /tmp/l1.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --configs none --e2e-rows 0 > /tmp/d.log 2>&1
 python profiles/launch_shares.py /tmp/l1.csv > gpurun_out/r02_launches_bench_summary.csv

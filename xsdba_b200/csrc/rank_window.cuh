@@ -185,12 +185,15 @@ rank_window_kernel(const float* __restrict__ sim, long long n_pts, long long st,
       int first = nq, last = -1, cnt = 0;
       if (n0 + c < n_pts) {
         const float* row = af + (n0 + c) * pt_stride + (long long)(g0 + j) * nq;
-        for (int k0 = 0; k0 < nq; k0 += 32) {
-          const int k = k0 + lane;
-          const unsigned ok = __ballot_sync(0xffffffffu, k < nq && row[k] == row[k]);
+        float a[RankWinSmem::kWinMaxNq / 32];   // (all loads of the row first: four independent requests, not a chain)
+#pragma unroll
+        for (int b = 0; b < RankWinSmem::kWinMaxNq / 32; ++b) a[b] = b * 32 + lane < nq ? row[b * 32 + lane] : fnan;
+#pragma unroll
+        for (int b = 0; b < RankWinSmem::kWinMaxNq / 32; ++b) {
+          const unsigned ok = __ballot_sync(0xffffffffu, a[b] == a[b]);
           if (ok) {
-            if (first == nq) first = k0 + __ffs(ok) - 1;
-            last = k0 + 31 - __clz(ok);
+            if (first == nq) first = b * 32 + __ffs(ok) - 1;
+            last = b * 32 + 31 - __clz(ok);
             cnt += __popc(ok);
           }
         }
