@@ -66,6 +66,44 @@ def test_marshalling_with_stub_backend(monkeypatch):
         A.eqm_train(ds, group="time.month", kind="+", quantiles=q, jitter_under_thresh_value="0.01 degC")
 
 
+def test_add_dims_pooling_layout_with_stub_backend(monkeypatch):
+    """Grouper(add_dims=[...]) (base.py:410-415) on CPU: what the adapter hands to the array-level train -- the pooled
+    dimension laid end to end along time with window/2 NaN spacer steps that belong to no group -- and the tables it
+    repeats over that dimension for adjust."""
+    import xsdba_b200 as xs
+    from xsdba_b200 import xr_adapter as A
+    tx = xs.TimeAxis.daily(1981, 2, "noleap")
+    T, R, P = len(tx), 3, 2
+    rng = np.random.default_rng(4)
+    ref = rng.standard_normal((T, R, P)).astype(np.float32)
+    coords = {"time": xr.time_index(tx)}
+    da = lambda a, dims: xr.DataArray(a, dims, coords)  # noqa: E731
+    seen = {}
+
+    def fake_train(ds, *, group, kind, quantiles, **kw):
+        seen.update(ref=np.asarray(ds["ref"]), group=group, time=ds.time)
+        n, G, nq = ds["ref"].shape[1], group.n_groups(ds.time), len(quantiles)
+        af = torch.zeros((n, G, nq), dtype=torch.float32)
+        return xs.Dataset({"af": af, "hist_q": af, "hist_q_raw": None, "quantiles": quantiles})
+    monkeypatch.setattr(A.L4, "eqm_train", fake_train)
+    ds = xr.Dataset({"ref": da(ref, ("time", "realization", "pt")), "hist": da(np.transpose(ref, (1, 2, 0)), ("realization", "pt", "time"))})
+    grp = types.SimpleNamespace(name="time.dayofyear", window=5, add_dims=["realization"], prop="dayofyear")
+    out = A.eqm_train(ds, group=grp, kind="+", quantiles=xs.equally_spaced_nodes(4))
+    gap = 2
+    pooled = seen["ref"]
+    assert pooled.shape == (R * (T + gap), P) and len(seen["time"]) == R * (T + gap)
+    gidx = seen["group"].zero_based_index(seen["time"]).reshape(R, T + gap)
+    for r in range(R):
+        np.testing.assert_array_equal(pooled.reshape(R, T + gap, P)[r, :T], ref[:, r, :])
+        assert np.isnan(pooled.reshape(R, T + gap, P)[r, T:]).all()
+        np.testing.assert_array_equal(gidx[r, :T], tx.dayofyear - 1)
+        assert (gidx[r, T:] == -1).all()
+    assert seen["group"].n_groups(seen["time"]) == 365 and seen["group"].window == 5 and not seen["group"].add_dims
+    assert out["af"].dims == ("pt", "dayofyear", "quantiles")        # the pooled dimension is gone from the tables
+    with pytest.raises(NotImplementedError):
+        A.eqm_train(ds, group=grp, kind="+", quantiles=xs.equally_spaced_nodes(4), adapt_freq_thresh="1 mm/d")
+
+
 def test_adjust_marshalling_with_stub_backend(monkeypatch):
     import xsdba_b200 as xs
     from xsdba_b200 import xr_adapter as A
