@@ -2556,8 +2556,8 @@ bool launch_train_fast(const float* ref, const float* hist, int64_t n_pts, int64
     // normalising (DQM) variant keeps one CTA per item: measured 9 % faster that way on day-of-year groupings, where a
     // persistent CTA changes group -- and rebuilds the group's tables -- every 2.4 items.
     const long long n_work_b = n_tiles_b * grp->n_groups;
-    const dim3 grid_b((unsigned)(normalize ? std::min<long long>(n_work_b, 0x7fffffffLL)
-                                           : std::min<long long>(n_work_b, (long long)sm_count())));
+    if (normalize && n_work_b > 0x7fffffffLL) return false;  // (one CTA per item must fit grid.x: the generic kernel otherwise)
+    const dim3 grid_b((unsigned)(normalize ? n_work_b : std::min<long long>(n_work_b, (long long)sm_count())));
     static const int vec_enable = getenv("XSDBA_B200_NO_VEC_LOAD") ? 0 : 1;  // (A/B switch of the 16-byte load path)
 #define XS_TRAIN_BKT(J, N)                                                                                            \
   do {                                                                                                               \
